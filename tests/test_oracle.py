@@ -80,3 +80,52 @@ def test_fuzz_cases():
             (gold["n_nodes"], gold["num_edges"], gold["graph_digest"]), key
         lines = po.contigs(graph)
         assert (len(lines), po.contig_digest(lines)) == (gold["n_contigs"], gold["contig_digest"]), key
+
+
+# ---------------------------------------------------------------- C oracle (oracle/c_oracle.c)
+from oracle import c_oracle as co  # noqa: E402
+
+C_CASES = [n for n in GOLDEN["cases"] if not n.startswith("c")]
+
+
+def check_case_c(name):
+    gold = GOLDEN["cases"][name]
+    reads = reads_for(gold["recipe"])
+    res = co.assemble(reads, gold["k"], gold["F"], gold["recipe"]["paired"],
+                      sketch_rows=gold.get("sketch_rows", 0))
+    if "counts_sha" in gold:
+        assert res.n_distinct == gold["n_distinct"]
+        assert counts_sha(res.counts_dict().items()) == gold["counts_sha"]
+    for row in range(gold.get("sketch_rows", 0)):
+        assert sha16(res.sketch_row(row).tobytes()) == gold["sketch_row_sha"][row]
+    assert (res.n_nodes, res.num_edges) == (gold["n_nodes"], gold["num_edges"])
+    assert res.digest() == gold["graph_digest"]
+    lines = res.contigs()
+    assert (len(lines), po.contig_digest(lines)) == (gold["n_contigs"], gold["contig_digest"])
+    res.close()
+
+
+@pytest.mark.parametrize("name", C_CASES)
+def test_c_oracle_cases(name):
+    check_case_c(name)
+
+
+def test_c_oracle_murmur():
+    for text, want in GOLDEN["murmur3"]:
+        assert co.murmur3_32(text) == want
+
+
+def test_c_oracle_fuzz():
+    for key, gold in GOLDEN["fuzz"].items():
+        recipe, k, F = recipes.fuzz_recipe(int(key))
+        res = co.assemble(reads_for(recipe), k, F, recipe["paired"])
+        assert (res.n_nodes, res.num_edges, res.digest()) == \
+            (gold["n_nodes"], gold["num_edges"], gold["graph_digest"]), key
+        lines = res.contigs()
+        assert (len(lines), po.contig_digest(lines)) == (gold["n_contigs"], gold["contig_digest"]), key
+        res.close()
+
+
+def test_c_oracle_sketch_overflow():
+    with pytest.raises(OverflowError):
+        co.assemble(["A" * 70000], 4, 3, False, sketch_rows=2)
