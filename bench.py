@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: (k-1)-mer counting -> filter -> de Bruijn graph build -> CSR.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+
+One "step" = one full pass of the path over the workload's synthetic reads.
+  value   occurrences/s with the packed reads already resident in HBM (CUDA events)
+  e2e     the same through the host-buffer entry: ASCII reads in pinned host memory -> H2D ->
+          pack -> count -> filter -> build -> CSR -> D2H of the CSR arrays, all timed
+  roofline  algorithmic bytes of the dominant kernel / its CUDA-event duration vs measured HBM peak
+  cpu_baseline  the oracle's pure-Python port (the reference is pure Python) on a bounded sample
+`--impl reference` times that CPU port alone (the reference cannot travel to the GPU box).
+Workloads are synthetic stand-ins of BASELINE.json's configs ("Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "genome-assembler_b200")
+for path in (ROOT, PKG):
+    if path not in sys.path:
+        sys.path.insert(0, path)
+
+# name: (genome bp, reads (pairs when paired), read length, paired, k, F, description)
+WORKLOADS = {
+    "c1": (112031, 19000, 100, True, 28, 3, "C1-shaped: 112,031 bp genome, 19,000 read-pairs x 100 bp, k=28, F=3"),
+    "c2": (2872769, 861831, 100, False, 31, 3, "C2-shaped (S. aureus size): 2,872,769 bp genome, 861,831 reads x 100 bp (30x), k=31, F=3"),
+    "c3": (4641652, 700000, 100, True, 29, 3, "C3-shaped (E. coli size): 4,641,652 bp genome, 700,000 read-pairs x 100 bp, k=29, F=3"),
+    "c4": (50000000, 100000000, 150, False, 31, 3, "C4: 50 Mbp genome, 100M reads x 150 bp, 1% substitutions, k=31, F=3"),
+}
+SEED = 2026
+# algorithmic bytes per (k-1)-mer occurrence, 64-bit keys (SURVEY 8d / DESIGN.md)
+B_COUNT, B_BUILD, B_TOTAL = 16.35, 22.35, 40.0
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            cells = [c.strip() for c in row.split(",")]
+            if len(cells) < 6:
+                continue
+            try:
+                sm.append(float(cells[0]))
+                mx = float(cells[1])
+            except ValueError:
+                continue
+            for name, cell in zip(names, cells[2:6]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_occ(n_reads, read_len, paired, k):
+    return n_reads * (2 if paired else 1) * (read_len - k + 2)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(reads, k, F, paired):
+    """Occurrences/s of the oracle's pure-Python port (count + build), one core."""
+    from oracle import py_oracle as po
+    t0 = time.perf_counter()
+    tally = (po.count_paired if paired else po.count_unpaired)(k, reads)
+    (po.build_paired if paired else po.build_unpaired)(tally, reads, k, F)
+    dt = time.perf_counter() - t0
+    occ = sum(tally.values())
+    return occ / dt, dt, occ
+
+
+def host_sample_reads(genome_size, n_reads, sample, read_len, paired):
+    """A scaled-down instance of the workload as Python strings: `sample` reads over a genome
+    shrunk by the same factor, so coverage (and with it the share of k-mers that pass the filter
+    and reach the build) is that of the full workload.  Same generator arithmetic as the device
+    (oracle/readgen.py)."""
+    from oracle import readgen
+    small_genome = max(4 * read_len, int(round(genome_size * (sample / float(n_reads)))))
+    genome = readgen.splitmix_genome_codes(small_genome, SEED)
+    mates = sample * (2 if paired else 1)
+    codes = readgen.splitmix_reads_codes(genome, read_len, 0, mates, SEED, 100, paired, 125)
+    strings = readgen.codes_to_strings(codes)
+    return list(zip(strings[0::2], strings[1::2])) if paired else strings
+
+
+def run_reference_arm(args):
+    genome_size, n_reads, read_len, paired, k, F, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(n_reads, args.sample_reads)
+    reads = host_sample_reads(genome_size, n_reads, sample, read_len, paired)
+    times, occ = [], 0
+    for step in range(args.warmup + args.steps):
+        rate, dt, occ = cpu_port_rate(reads, k, F, paired)
+        if step >= args.warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    value = occ / mean
+    line = {"impl": "reference", "metric": "k-mers/sec counted+filtered+graph-built", "value": value,
+            "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "k": k, "filter": F, "paired": paired},
+            "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": 1, "kind": "port",
+                             "sample": "%d reads%s per step over a genome scaled to keep the workload's coverage; "
+                                       "oracle/py_oracle.py (pure-Python restatement; the reference is "
+                                       "single-threaded pure Python and cannot travel to the GPU box)"
+                                       % (sample, " pairs" if paired else "")},
+            "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ga_native as gn
+    import ga_device as gd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    genome_size, n_reads, read_len, paired, k, F, desc = WORKLOADS[args.workload]
+    if args.reads:
+        n_reads = args.reads
+    L = gn.lib()
+    mates = 2 if paired else 1
+    stride = (read_len + 31) // 32
+    occ_total = workload_occ(n_reads, read_len, paired, k)
+
+    # shard reads by index (contiguous ranges); every rank generates its own shard on the device
+    lo = n_reads * rank // world
+    hi = n_reads * (rank + 1) // world
+    n_local = hi - lo
+    genome = torch.empty(genome_size, dtype=torch.uint8, device=dev)
+    gn.check(L.ga_gen_genome(gn.ptr(genome), genome_size, SEED, None))
+    words = torch.empty(max(1, n_local * mates * stride), dtype=torch.int64, device=dev)
+    gn.check(L.ga_gen_reads(gn.ptr(genome), genome_size, lo * mates, n_local * mates, read_len, SEED, 100,
+                            gn.ptr(words), stride, int(paired), 125, None))
+    torch.cuda.synchronize()
+    reads = gd.DeviceReads.from_packed(words, n_local * mates, read_len, paired, first_read=lo,
+                                       estride=read_len)
+    if world > 1:
+        import ga_multi
+        step_fn = lambda timers=None: ga_multi.sharded_step(reads, k, F, timers=timers)   # noqa: E731
+    else:
+        step_fn = lambda timers=None: gd.device_step(reads, k, F, timers=timers)           # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_fn()
+    barrier()
+    launches0 = L.ga_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    timers = {"count": [], "build": []}
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    result = None
+    for _ in range(args.steps):
+        result = step_fn(timers)
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = L.ga_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = occ_total / (ms_per_step * 1e-3)
+
+    # dominant-kernel roofline from the per-launch CUDA events recorded inside the timed steps
+    kernel_ms = {name: sum(a.elapsed_time(b) for a, b in pairs) / max(len(pairs), 1)
+                 for name, pairs in timers.items()}
+    dominant = max(kernel_ms, key=kernel_ms.get)
+    occ_local = workload_occ(n_local, read_len, paired, k)
+    alg_bytes = occ_local * (B_COUNT if dominant == "count" else B_BUILD)
+    peak, peak_src = hbm_peak()
+    achieved = alg_bytes / (kernel_ms[dominant] * 1e-3) / 1e9 if kernel_ms[dominant] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "whole_path": {"achieved": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9,
+                               "frac": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "bytes_per_occurrence": B_TOTAL}}
+
+    # end to end through the host-buffer entry (ASCII reads in pinned memory -> CSR on the host)
+    e2e = None
+    if world == 1:
+        codes = _unpack_codes(words, n_local * mates, read_len, stride)
+        ascii_host = torch.from_numpy(np.frombuffer(b"ACGT", dtype=np.uint8)[codes.cpu().numpy()].reshape(-1))
+        pinned = torch.empty(ascii_host.shape, dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(ascii_host)
+        del codes, ascii_host
+        for _ in range(max(1, min(args.warmup, 2))):
+            gd.host_step(pinned, n_local * mates, read_len, paired, k, F)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            graph = gd.host_step(pinned, n_local * mates, read_len, paired, k, F)
+            d2h = sum(a.nbytes for a in (graph.rowptr, graph.col, graph.indeg, graph.branching,
+                                         graph.last_char, graph.keys_a))
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": occ_total / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(pinned.numel()),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
+
+    cpu_baseline = None
+    if rank == 0:
+        sample = min(n_reads, args.sample_reads)
+        sreads = host_sample_reads(genome_size, n_reads, sample, read_len, paired)
+        rate, dt, occ = cpu_port_rate(sreads, k, F, paired)
+        cpu_baseline = {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": "port",
+                        "sample": "%d reads%s over a genome scaled to keep the workload's coverage, %.1f s; "
+                                  "oracle/py_oracle.py (pure-Python restatement of the pure-Python reference)" %
+                                  (sample, " pairs" if paired else "", dt),
+                        "host_cores": os.cpu_count()}
+    if rank == 0:
+        line = {"metric": "k-mers/sec counted+filtered+graph-built", "value": value, "unit": "k-mers/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic",
+                "config": {"workload": desc, "k": k, "filter": F, "paired": paired, "reads": n_reads,
+                           "occurrences": occ_total, "sharding": "reads by index, k-mers by hash" if world > 1 else "none",
+                           "l2": "working set (count table %d MB) exceeds the 126 MB L2; tables rebuilt every step"
+                                 % (int(occ_total * 1.25 * 16) >> 20)},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks,
+                "graph": {"nodes": result.n_nodes, "edges": result.n_edges} if result is not None else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _unpack_codes(words, n, read_len, stride):
+    import torch
+    w = words[:n * stride].view(n, stride)
+    idx = torch.arange(read_len, device=words.device)
+    shifts = (2 * (idx % 32)).to(torch.int64)
+    return ((w[:, idx // 32] >> shifts) & 3).to(torch.uint8)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GA_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override the number of reads / pairs")
+    ap.add_argument("--sample-reads", type=int, default=100000, help="reads in the CPU-baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.sample_reads == 100000:
+            args.sample_reads = 30000
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+// ga_build.cu -- edge / node insertion with first-occurrence stamps, replacing
+// DeBruijnGraph._build_graph (debruijn_graph.py:113-142) and
+// PairedDeBruijnGraph._build_graph (:269-317).  The reference's dict insertion order is
+// reproduced by stamps: occurrence e = read * estride + position,
+// node stamp = min(2e | prefix, 2e+1 | suffix), edge stamp = min e.  Ordering itself happens in
+// ga_csr.cu; these kernels only fold stamps in with atomicMin.
+#include "ga_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void stamp_min(u64* p, u64 v) {
+    if (v < __ldcg(p)) atomicMin(p, v);
+}
+
+// Unpaired: one thread per read.
+template <class K, int SB>
+__global__ void __launch_bounds__(256)
+build_unpaired_kernel(ReadsView rv, int w, const Slot<K>* __restrict__ solid, u64 solid_cap,
+                      u64* __restrict__ node_stamp, StampSlot* __restrict__ edges, u64 edge_cap,
+                      u32* status) {
+    const K mask = ga_key_mask<K>(w, rv.sym_bits);
+    bool full = false;
+    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
+         r += (u64)gridDim.x * blockDim.x) {
+        u32 len = ga_read_len(rv, r);
+        if (len <= (u32)w) continue;  // fewer than two windows: no edge occurrence
+        const u64 e0 = (rv.first_read + r) * (u64)rv.estride;
+        u32 prev = GA_NONE32;
+        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
+            u32 id = ga_table_find(solid, solid_cap, key);
+            if (pos > 0 && prev != GA_NONE32 && id != GA_NONE32) {
+                const u64 e = e0 + (pos - 1);
+                stamp_min(node_stamp + prev, 2 * e);
+                stamp_min(node_stamp + id, 2 * e + 1);
+                if (ga_stamp_upsert(edges, edge_cap, ((u64)prev << 32) | id, e) == GA_NONE64) full = true;
+            }
+            prev = id;
+        });
+    }
+    if (full) atomicOr(status, GA_ST_STAMP_FULL);
+}
+
+// Keep the two smallest values ever offered (all values distinct): m[0] <= m[1].
+__device__ __forceinline__ void two_min(u64* m, u64 v) {
+    u64 old = atomicMin(m, v);
+    u64 loser = old > v ? old : v;
+    if (loser != GA_NONE64) atomicMin(m + 1, loser);
+}
+
+// Paired: one thread per pair; mates advance in lock step over mate 1's length.
+template <class K, int SB>
+__global__ void __launch_bounds__(256)
+build_paired_kernel(ReadsView rv, int w, const Slot<K>* __restrict__ solid, u64 solid_cap,
+                    StampSlot* __restrict__ queries, u64 query_cap, StampSlot* __restrict__ qedges,
+                    u64 qedge_cap, u64* __restrict__ dh, u32* status) {
+    constexpr u32 SPW = 64 / SB;
+    constexpr u64 SMASK = (1ull << SB) - 1;
+    const K mask = ga_key_mask<K>(w, rv.sym_bits);
+    const u32 smask = (1u << rv.sym_bits) - 1u;
+    const u64 n_pairs = rv.n_reads / 2;
+    bool full = false;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n_pairs; p += (u64)gridDim.x * blockDim.x) {
+        u32 len = ga_read_len(rv, 2 * p);
+        if (len <= (u32)w) continue;
+        const u64* wa = ga_read_ptr(rv, 2 * p);
+        const u64* wb = ga_read_ptr(rv, 2 * p + 1);
+        const u64 e0 = (rv.first_read + p) * (u64)rv.estride;
+        K ka = 0, kb = 0;
+        u32 prev_a = GA_NONE32, prev_b = GA_NONE32;
+        u64 prev_q = GA_NONE64;  // query slot of the previous position when it was part of an accepted occurrence
+        for (u32 base = 0; base < len; base += SPW) {
+            u64 word_a = __ldg(wa + base / SPW), word_b = __ldg(wb + base / SPW);
+            u32 lim = len - base < SPW ? len - base : SPW;
+            for (u32 j = 0; j < lim; ++j) {
+                ka = ((ka << rv.sym_bits) | (K)(word_a & SMASK)) & mask;
+                kb = ((kb << rv.sym_bits) | (K)(word_b & SMASK)) & mask;
+                word_a >>= SB;
+                word_b >>= SB;
+                u32 i = base + j + 1;
+                if (i < (u32)w) continue;
+                u32 pos = i - (u32)w;
+                u32 ida = ga_table_find(solid, solid_cap, ka);
+                u32 idb = ida == GA_NONE32 ? GA_NONE32 : ga_table_find(solid, solid_cap, kb);
+                bool here = ida != GA_NONE32 && idb != GA_NONE32;
+                u64 cur_q = GA_NONE64;
+                if (pos > 0 && here && prev_a != GA_NONE32 && prev_b != GA_NONE32) {
+                    const u64 e = e0 + (pos - 1);
+                    // prefix pair: already folded in with a smaller stamp if the previous
+                    // occurrence was accepted too (it was that occurrence's suffix pair)
+                    u64 qp = prev_q;
+                    if (qp == GA_NONE64)
+                        qp = ga_stamp_upsert(queries, query_cap, ((u64)prev_a << 32) | prev_b, 2 * e);
+                    u64 qs = ga_stamp_upsert(queries, query_cap, ((u64)ida << 32) | idb, 2 * e + 1);
+                    if (qp == GA_NONE64 || qs == GA_NONE64) full = true;
+                    else {
+                        if (ga_stamp_upsert(qedges, qedge_cap, (qp << 32) | qs, e) == GA_NONE64) full = true;
+                        if (prev_a == ida && prev_b == idb)  // both mates homopolymer (App. A-9 ii)
+                            two_min(dh + 2 * ((u64)((u32)ka & smask) * 256u + ((u32)kb & smask)), e);
+                    }
+                    cur_q = qs;
+                }
+                prev_a = ida;
+                prev_b = idb;
+                prev_q = cur_q;
+            }
+        }
+    }
+    if (full) atomicOr(status, GA_ST_STAMP_FULL);
+}
+
+}  // namespace
+
+extern "C" int ga_build_unpaired(const ga_reads* reads, int k, const void* solid_dev, uint64_t solid_capacity,
+                                 uint64_t* node_stamp_dev, void* edge_table_dev, uint64_t edge_capacity,
+                                 uint32_t* status_dev, ga_stream stream) {
+    if (!reads || !solid_dev || !node_stamp_dev || !edge_table_dev || solid_capacity == 0 || edge_capacity == 0) {
+        ga_set_error("ga_build_unpaired: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    int kw = ga_key_words(k, reads->sym_bits);
+    if (!kw || reads->paired) {
+        ga_set_error("ga_build_unpaired: unsupported key width or paired reads");
+        return GA_ERR_BAD_ARG;
+    }
+    if (reads->n_reads == 0) return GA_OK;
+    ReadsView rv = ga_view(reads);
+    unsigned grid = ga_grid(rv.n_reads, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GA_BUILD(K, SB)                                                                              \
+    build_unpaired_kernel<K, SB><<<grid, 256, 0, st>>>(rv, k - 1, (const Slot<K>*)solid_dev, solid_capacity, \
+                                                      (u64*)node_stamp_dev, (StampSlot*)edge_table_dev, \
+                                                      edge_capacity, status_dev)
+    if (kw == 1 && rv.storage_bits == 2) GA_BUILD(u64, 2);
+    else if (kw == 1) GA_BUILD(u64, 8);
+    else if (rv.storage_bits == 2) GA_BUILD(u128, 2);
+    else GA_BUILD(u128, 8);
+#undef GA_BUILD
+    GA_LAUNCH_CHECK("build_unpaired");
+    return GA_OK;
+}
+
+extern "C" int ga_build_paired(const ga_reads* reads, int k, const void* solid_dev, uint64_t solid_capacity,
+                               void* query_table_dev, uint64_t query_capacity, void* qedge_table_dev,
+                               uint64_t qedge_capacity, uint64_t* dh_dev, uint32_t* status_dev,
+                               ga_stream stream) {
+    if (!reads || !solid_dev || !query_table_dev || !qedge_table_dev || !dh_dev || solid_capacity == 0 ||
+        query_capacity == 0 || qedge_capacity == 0 || query_capacity >= 0xFFFFFFFFull) {
+        ga_set_error("ga_build_paired: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    int kw = ga_key_words(k, reads->sym_bits);
+    if (!kw || !reads->paired || (reads->n_reads & 1)) {
+        ga_set_error("ga_build_paired: unsupported key width or unpaired reads");
+        return GA_ERR_BAD_ARG;
+    }
+    if (reads->n_reads == 0) return GA_OK;
+    ReadsView rv = ga_view(reads);
+    unsigned grid = ga_grid(rv.n_reads / 2, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GA_BUILD(K, SB)                                                                            \
+    build_paired_kernel<K, SB><<<grid, 256, 0, st>>>(rv, k - 1, (const Slot<K>*)solid_dev, solid_capacity, \
+                                                    (StampSlot*)query_table_dev, query_capacity,   \
+                                                    (StampSlot*)qedge_table_dev, qedge_capacity,   \
+                                                    (u64*)dh_dev, status_dev)
+    if (kw == 1 && rv.storage_bits == 2) GA_BUILD(u64, 2);
+    else if (kw == 1) GA_BUILD(u64, 8);
+    else if (rv.storage_bits == 2) GA_BUILD(u128, 2);
+    else GA_BUILD(u128, 8);
+#undef GA_BUILD
+    GA_LAUNCH_CHECK("build_paired");
+    return GA_OK;
+}

@@ -1,0 +1,563 @@
+"""Host orchestration of the GPU path: read packing, the count table, the sketch-backed or exact
+filter, the stamp-based graph build and CSR emission.  Everything numeric happens in
+libga_b200.so (see include/ga_b200.h); this module owns device buffers (torch tensors), sizes
+hash tables, retries when one fills up, and converts between Python strings and packed keys.
+
+Reference behaviour reproduced here (paths into the upstream checkout):
+  read breaking / counting     debruijn_graph.py:144-157, 349-374
+  filter (strict >)            debruijn_graph.py:127-128, 275-278
+  node / edge insertion order  debruijn_graph.py:113-142, 269-347  (via stamps)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+import ga_native as gn
+
+_DNA = b"ACGT"
+TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
+
+
+def _timed(name):
+    """Context manager recording a CUDA-event pair around a kernel launch when TIMERS is set."""
+    class _Span:
+        def __enter__(self):
+            self.on = TIMERS is not None
+            if self.on:
+                self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+        def __exit__(self, *exc):
+            if self.on:
+                self.b.record()
+                TIMERS[name].append((self.a, self.b))
+    return _Span()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ----------------------------------------------------------------------------------- alphabet
+class Alphabet:
+    """Symbol coding of a read set: DNA packs 2 bits per base, anything else 8 bits per stored
+    symbol with the smallest code width that separates the symbols present."""
+
+    def __init__(self, present: np.ndarray):
+        present = np.asarray(present, dtype=np.int64)
+        self.lut = np.full(256, 0xFF, dtype=np.uint8)          # byte -> code
+        if present.size == 0 or set(present.tolist()) <= set(_DNA):
+            self.storage_bits, self.sym_bits = 2, 2
+            symbols = np.frombuffer(_DNA, dtype=np.uint8)
+        else:
+            self.storage_bits = 8
+            self.sym_bits = max(1, int(math.ceil(math.log2(present.size))))
+            symbols = present.astype(np.uint8)
+        self.lut[symbols] = np.arange(symbols.size, dtype=np.uint8)
+        self.inv = np.zeros(256, dtype=np.uint8)               # code -> byte
+        self.inv[:symbols.size] = symbols
+        self._lut_dev = self._inv_dev = None
+
+    @property
+    def lut_dev(self):
+        if self._lut_dev is None:
+            self._lut_dev = torch.from_numpy(self.lut).to(_dev())
+        return self._lut_dev
+
+    @property
+    def inv_dev(self):
+        if self._inv_dev is None:
+            self._inv_dev = torch.from_numpy(self.inv).to(_dev())
+        return self._inv_dev
+
+    # -- packed keys <-> strings (first symbol most significant, as in the kernels)
+    def pack_key(self, text: str, key_words: int):
+        """Packed key of a window as (lo, hi) or None if a symbol is outside the alphabet."""
+        value = 0
+        for ch in text:
+            o = ord(ch)
+            if o > 255 or self.lut[o] == 0xFF:
+                return None
+            value = (value << self.sym_bits) | int(self.lut[o])
+        if value >> (64 * key_words):
+            return None
+        return value & 0xFFFFFFFFFFFFFFFF, value >> 64
+
+    def decode_keys(self, keys: np.ndarray, w: int) -> np.ndarray:
+        """keys: (n, key_words) uint64 -> (n, w) uint8 bytes."""
+        n = keys.shape[0]
+        out = np.empty((n, w), dtype=np.uint8)
+        b = self.sym_bits
+        mask = np.uint64((1 << b) - 1)
+        lo = keys[:, 0]
+        hi = keys[:, 1] if keys.shape[1] > 1 else None
+        for i in range(w):
+            p = (w - 1 - i) * b
+            if p >= 64:
+                v = hi >> np.uint64(p - 64)
+            elif p == 0:
+                v = lo
+            else:
+                v = lo >> np.uint64(p)
+                if hi is not None and p + b > 64:
+                    v = v | (hi << np.uint64(64 - p))
+            out[:, i] = self.inv[(v & mask).astype(np.int64)]
+        return out
+
+    def decode_strings(self, keys: np.ndarray, w: int):
+        if keys.shape[0] == 0:
+            return []
+        raw = self.decode_keys(keys, w)
+        return [s.decode("latin-1") for s in raw.view("S%d" % w).ravel().tolist()] if w else [""] * len(raw)
+
+
+# ----------------------------------------------------------------------------------- reads
+class DeviceReads:
+    """Reads (or read pairs, mates interleaved) packed on the device."""
+
+    def __init__(self, reads, paired: bool, first_read: int = 0, estride: int | None = None):
+        gn.require_gpu()
+        self.source = reads
+        self.paired = bool(paired)
+        if self.paired:
+            flat = [s for pair in reads for s in (pair[0], pair[1])]
+        else:
+            flat = reads if isinstance(reads, list) else list(reads)
+        n = len(flat)
+        self.n_reads = n
+        lens = np.fromiter(map(len, flat), dtype=np.int64, count=n)
+        try:
+            raw = "".join(flat).encode("latin-1")
+        except UnicodeEncodeError:
+            raise ValueError("reads contain characters above U+00FF; the GPU path hashes symbols "
+                             "as single bytes and refuses to alias them") from None
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        self.alphabet = Alphabet(np.flatnonzero(np.bincount(buf, minlength=256)) if buf.size else np.zeros(0))
+        if self.paired and n and np.any(lens[1::2] < lens[0::2]):
+            raise ValueError("paired reads: mate 2 shorter than mate 1 is not supported "
+                             "(the reference would slice truncated k-mers)")
+        self.lens = lens
+        self.max_len = int(lens.max()) if n else 0
+        self.estride = int(estride) if estride is not None else max(self.max_len, 1)
+        self.first_read = int(first_read)
+        spw = 64 // self.alphabet.storage_bits
+        dev = _dev()
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        uniform = n > 0 and int(lens.min()) == self.max_len
+        self.uniform = uniform
+        ascii_dev = _to_device(buf) if buf.size else torch.zeros(1, dtype=torch.uint8, device=dev)
+        if uniform or n == 0:
+            self.stride_words = max(1, -(-self.max_len // spw))
+            self.words = torch.empty(max(1, n * self.stride_words), dtype=torch.int64, device=dev)
+            self.offsets = self.lengths = None
+            in_off = out_off = None
+        else:
+            words_per = -(-lens // spw)
+            off_words = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(words_per, out=off_words[1:])
+            off_bytes = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(lens, out=off_bytes[1:])
+            self.stride_words = 0
+            self.words = torch.empty(max(1, int(off_words[-1])), dtype=torch.int64, device=dev)
+            self.offsets = torch.from_numpy(off_words).to(dev)
+            self.lengths = torch.from_numpy(lens.astype(np.int32)).to(dev)
+            in_off = torch.from_numpy(off_bytes).to(dev)
+            out_off = self.offsets
+        if n:
+            gn.check(gn.lib().ga_pack_reads(
+                gn.ptr(ascii_dev), gn.ptr(in_off), n, self.max_len if uniform else 0,
+                gn.ptr(self.alphabet.lut_dev), self.alphabet.storage_bits, gn.ptr(self.words),
+                gn.ptr(out_off), self.stride_words, gn.ptr(self.status), _stream()))
+        self._struct = None
+
+    @classmethod
+    def from_packed(cls, words: torch.Tensor, n_reads: int, read_len: int, paired: bool,
+                    first_read: int = 0, estride: int | None = None, alphabet: "Alphabet | None" = None):
+        """Wrap uniform-length reads that already sit packed on the device (2-bit DNA unless an
+        8-bit alphabet is given): the bulk-ingest and synthetic-generator route, which never
+        materialises Python strings."""
+        gn.require_gpu()
+        self = cls.__new__(cls)
+        self.source = words
+        self.paired = bool(paired)
+        self.n_reads = int(n_reads)
+        self.alphabet = alphabet if alphabet is not None else Alphabet(np.zeros(0))
+        self.lens = None
+        self.max_len = int(read_len)
+        self.uniform = True
+        self.estride = int(estride) if estride is not None else max(self.max_len, 1)
+        self.first_read = int(first_read)
+        spw = 64 // self.alphabet.storage_bits
+        self.stride_words = max(1, -(-self.max_len // spw))
+        self.words = words
+        self.offsets = self.lengths = None
+        self.status = torch.zeros(4, dtype=torch.int32, device=words.device)
+        self._struct = None
+        return self
+
+    @classmethod
+    def from_ascii(cls, ascii_host: torch.Tensor, n_reads: int, read_len: int, paired: bool,
+                   alphabet: "Alphabet | None" = None, **kw):
+        """Uniform reads as one (pinned) host byte tensor of n_reads*read_len symbols: async H2D copy,
+        then 2-bit packing on the device (replaces assemble.py:45-71's per-line string list)."""
+        gn.require_gpu()
+        alphabet = alphabet if alphabet is not None else Alphabet(np.zeros(0))
+        dev = _dev()
+        ascii_dev = ascii_host.to(dev, non_blocking=True)
+        spw = 64 // alphabet.storage_bits
+        stride = max(1, -(-int(read_len) // spw))
+        words = torch.empty(max(1, n_reads * stride), dtype=torch.int64, device=dev)
+        self = cls.from_packed(words, n_reads, read_len, paired, alphabet=alphabet, **kw)
+        if n_reads:
+            gn.check(gn.lib().ga_pack_reads(gn.ptr(ascii_dev), None, n_reads, read_len, gn.ptr(alphabet.lut_dev),
+                                            alphabet.storage_bits, gn.ptr(words), None, stride,
+                                            gn.ptr(self.status), _stream()))
+        return self
+
+    def windows_total(self, k: int) -> int:
+        """Number of (k-1)-mer occurrences (both mates when paired)."""
+        w = k - 1
+        if self.n_reads == 0:
+            return 0
+        if self.lens is None:
+            return self.n_reads * max(self.max_len - w + 1, 0)
+        eff = np.repeat(self.lens[0::2], 2) if self.paired else self.lens
+        return int(np.maximum(eff - w + 1, 0).sum())
+
+    def struct(self) -> gn.GaReads:
+        if self._struct is None:
+            s = gn.GaReads()
+            s.words = gn.ptr(self.words)
+            s.offsets = gn.ptr(self.offsets)
+            s.lengths = gn.ptr(self.lengths)
+            s.n_reads = self.n_reads
+            s.first_read = self.first_read
+            s.uniform_len = self.max_len if self.uniform else 0
+            s.stride_words = self.stride_words
+            s.storage_bits = self.alphabet.storage_bits
+            s.sym_bits = self.alphabet.sym_bits
+            s.paired = int(self.paired)
+            s.estride = self.estride
+            self._struct = s
+        return self._struct
+
+    def key_words(self, k: int) -> int:
+        kw = gn.lib().ga_key_words(k, self.alphabet.sym_bits)
+        if kw == 0:
+            raise ValueError("kmer length %d with a %d-bit alphabet needs more than 127 key bits; "
+                             "supported: (k-1)*bits <= 127" % (k, self.alphabet.sym_bits))
+        return kw
+
+
+def _to_device(arr: np.ndarray) -> torch.Tensor:
+    """Host array -> device through a pinned staging buffer and an async copy."""
+    pinned = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = arr
+    return pinned.to(_dev(), non_blocking=True)
+
+
+def _check_status(status: torch.Tensor) -> int:
+    return int(status[0].item())
+
+
+# ----------------------------------------------------------------------------------- counting
+class KmerCounts:
+    """Exact (k-1)-mer counts in a device hash table, quacking like the dict the reference's
+    ``_count_kmers`` returns (``[]``, ``items()``, truthiness, ``len``)."""
+
+    def __init__(self, k: int, reads: DeviceReads):
+        self.k, self.w = k, k - 1
+        self.reads = reads
+        self.alphabet = reads.alphabet
+        self.key_words = reads.key_words(k)
+        self.slot_bytes = gn.lib().ga_slot_bytes(self.key_words)
+        self.n_occ = reads.windows_total(k)
+        self.table = None
+        self.capacity = 0
+        self._summary = {}
+        self._count()
+
+    def _count(self):
+        L = gn.lib()
+        dev = _dev()
+        free, _ = torch.cuda.mem_get_info()
+        limit = max(1024, int(free * 0.6) // self.slot_bytes)
+        cap = min(max(1024, int(self.n_occ * 1.25) + 64), limit)
+        while True:
+            self.table = torch.empty(cap * self.slot_bytes, dtype=torch.uint8, device=dev)
+            self.capacity = cap
+            self.reads.status.zero_()
+            gn.check(L.ga_table_clear(gn.ptr(self.table), cap, self.key_words, _stream()))
+            with _timed("count"):
+                gn.check(L.ga_count_kmers(C.byref(self.reads.struct()), self.k, gn.ptr(self.table), cap,
+                                          gn.ptr(self.reads.status), _stream()))
+            st = _check_status(self.reads.status)
+            if st & gn.ST_BAD_SYMBOL:
+                raise ValueError("read symbol outside the detected alphabet")
+            if not st & gn.ST_TABLE_FULL:
+                return
+            if cap >= limit:
+                raise MemoryError("k-mer count table does not fit in device memory")
+            self.table = None
+            cap = min(cap * 2, limit)
+
+    def summary(self, threshold: int):
+        """(distinct, above threshold, occurrences, max count)."""
+        if threshold not in self._summary:
+            out = torch.zeros(4, dtype=torch.int64, device=_dev())
+            gn.check(gn.lib().ga_table_summary(gn.ptr(self.table), self.capacity, self.key_words,
+                                               int(threshold), gn.ptr(out), _stream()))
+            self._summary[threshold] = tuple(int(v) for v in out.cpu().tolist())
+        return self._summary[threshold]
+
+    def export(self, min_exclusive: int = -1):
+        """(keys (n, key_words) uint64, counts (n,) uint32) on the host, table order."""
+        n_max = self.summary(min_exclusive)[1] if min_exclusive >= 0 else self.summary(0)[0]
+        dev = _dev()
+        keys = torch.empty((max(n_max, 1), self.key_words), dtype=torch.int64, device=dev)
+        counts = torch.empty(max(n_max, 1), dtype=torch.int32, device=dev)
+        n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        gn.check(gn.lib().ga_table_export(gn.ptr(self.table), self.capacity, self.key_words,
+                                          int(min_exclusive), gn.ptr(keys), gn.ptr(counts), gn.ptr(n_out),
+                                          _stream()))
+        n = int(n_out.item())
+        return (keys[:n].cpu().numpy().view(np.uint64), counts[:n].cpu().numpy().view(np.uint32))
+
+    # -- dict-like surface -----------------------------------------------------------------
+    def __len__(self):
+        return self.summary(0)[0]
+
+    def __bool__(self):
+        return self.n_occ > 0
+
+    def lookup_many(self, kmers):
+        keys = np.zeros((len(kmers), self.key_words), dtype=np.uint64)
+        known = np.zeros(len(kmers), dtype=bool)
+        for i, text in enumerate(kmers):
+            packed = self.alphabet.pack_key(text, self.key_words) if len(text) == self.w else None
+            if packed is not None:
+                keys[i, 0] = packed[0]
+                if self.key_words > 1:
+                    keys[i, 1] = packed[1]
+                known[i] = True
+        out = torch.zeros(max(len(kmers), 1), dtype=torch.int32, device=_dev())
+        if len(kmers):
+            kd = torch.from_numpy(keys.view(np.int64)).to(_dev())
+            gn.check(gn.lib().ga_table_lookup(gn.ptr(self.table), self.capacity, self.key_words, gn.ptr(kd),
+                                              len(kmers), gn.ptr(out), _stream()))
+        res = out[:len(kmers)].cpu().numpy().astype(np.int64)
+        res[~known] = 0
+        return res
+
+    def __getitem__(self, kmer):
+        return int(self.lookup_many([kmer])[0])
+
+    def get(self, kmer, default=None):
+        v = self[kmer]
+        return v if v else default
+
+    def __contains__(self, kmer):
+        return self[kmer] > 0
+
+    def items(self):
+        keys, counts = self.export()
+        return zip(self.alphabet.decode_strings(keys, self.w), (int(c) for c in counts))
+
+    def keys(self):
+        return (k for k, _ in self.items())
+
+    def values(self):
+        return (v for _, v in self.items())
+
+    def __iter__(self):
+        return self.keys()
+
+
+def sketch_struct(cells: torch.Tensor, widths) -> gn.GaSketch:
+    s = gn.GaSketch()
+    s.cells = gn.ptr(cells)
+    s.rows = len(widths)
+    for i, wdt in enumerate(widths):
+        s.width[i] = int(wdt)
+    return s
+
+
+# ----------------------------------------------------------------------------------- build
+class BuiltGraph:
+    """The CSR contract of SURVEY App. C.3 on the host."""
+
+    def __init__(self, paired, w, alphabet, key_words):
+        self.paired, self.w, self.alphabet, self.key_words = paired, w, alphabet, key_words
+        self.n_nodes = self.n_edges = self.num_edges_attr = 0
+        z = np.zeros(0, dtype=np.int32)
+        self.rowptr, self.col, self.indeg = np.zeros(1, dtype=np.int32), z, z
+        self.branching = self.last_char = np.zeros(0, dtype=np.uint8)
+        self.keys_a = np.zeros((0, key_words), dtype=np.uint64)
+        self.keys_b = None
+
+    def node_strings(self):
+        a = self.alphabet.decode_strings(self.keys_a, self.w)
+        if not self.paired:
+            return a
+        return list(zip(a, self.alphabet.decode_strings(self.keys_b, self.w)))
+
+    def contigs(self):
+        """Host traversal (libga_b200's ga_traverse_contigs) -> (contigs, edges left, left per node)."""
+        L = gn.lib()
+        text, offs, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        arrs = [np.ascontiguousarray(a) for a in (self.rowptr, self.col, self.indeg, self.branching, self.last_char)]
+        left = np.zeros(max(self.n_nodes, 1), dtype=np.int32)
+        gn.check(L.ga_traverse_contigs(*(a.ctypes.data for a in arrs), self.n_nodes, self.num_edges_attr,
+                                       int(self.paired), C.byref(text), C.byref(offs), C.byref(n),
+                                       left.ctypes.data))
+        try:
+            count = n.value
+            off = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_uint64)), shape=(count + 1,)).copy()
+            total = int(off[-1])
+            raw = C.string_at(text, total) if total else b""
+        finally:
+            L.ga_free_host(text)
+            L.ga_free_host(offs)
+        out = [raw[int(off[i]):int(off[i + 1])].decode("latin-1") for i in range(count)]
+        return out, self.num_edges_attr - total, left[:self.n_nodes]
+
+
+def _solid_keys(counts: KmerCounts, threshold: int, sketch=None):
+    """Device array of the keys that pass the filter, and their number."""
+    L = gn.lib()
+    dev = _dev()
+    n_max = counts.summary(threshold)[1] if sketch is None else counts.summary(0)[0]
+    keys = torch.empty((max(n_max, 1), counts.key_words), dtype=torch.int64, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    sk = C.byref(sketch) if sketch is not None else None
+    gn.check(L.ga_select_solid(gn.ptr(counts.table), counts.capacity, counts.key_words, counts.k,
+                               counts.alphabet.sym_bits, int(threshold), sk, gn.ptr(counts.alphabet.inv_dev),
+                               gn.ptr(keys), None, gn.ptr(n_out), _stream()))
+    return keys, int(n_out.item())
+
+
+def _solid_keys_from_flags(counts: KmerCounts, keep_fn):
+    """Compat path for a foreign ``kmer_counts`` mapping: ask it once per distinct window."""
+    keys, _ = counts.export()
+    strings = counts.alphabet.decode_strings(keys, counts.w)
+    mask = np.fromiter((bool(keep_fn(s)) for s in strings), dtype=bool, count=len(strings))
+    sel = np.ascontiguousarray(keys[mask])
+    if sel.shape[0] == 0:
+        return torch.zeros((1, counts.key_words), dtype=torch.int64, device=_dev()), 0
+    return torch.from_numpy(sel.view(np.int64)).to(_dev()), sel.shape[0]
+
+
+def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=None, keep_fn=None,
+                to_host: bool = True):
+    """count table (+ optional sketch) + reads -> BuiltGraph (or device tensors)."""
+    L = gn.lib()
+    dev = _dev()
+    k, w, kw = counts.k, counts.w, counts.key_words
+    alphabet = reads.alphabet
+    graph = BuiltGraph(reads.paired, w, alphabet, kw)
+    if keep_fn is not None:
+        solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
+    else:
+        solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
+    if n_solid == 0 or reads.n_reads == 0:
+        return graph
+    solid_cap = 2 * n_solid + 64
+    solid = torch.empty(solid_cap * counts.slot_bytes, dtype=torch.uint8, device=dev)
+    status = reads.status
+    status.zero_()
+    gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, _stream()))
+    gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap,
+                                   gn.ptr(status), _stream()))
+    n_nodes, n_edges, attr = C.c_int64(), C.c_int64(), C.c_int64()
+    plan = C.c_void_p()
+    free, _ = torch.cuda.mem_get_info()
+    cap_limit = min(0xFFFFFFF0, max(4096, int(free * 0.4) // 32))
+    cap = min(cap_limit, max(1024, 3 * n_solid))
+    while True:
+        status.zero_()
+        if not reads.paired:
+            node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
+            edges = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+            with _timed("build"):
+                gn.check(L.ga_build_unpaired(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap,
+                                             gn.ptr(node_stamp), gn.ptr(edges), cap, gn.ptr(status), _stream()))
+        else:
+            queries = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+            qedges = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+            dh = torch.full((256 * 256 * 2,), -1, dtype=torch.int64, device=dev)
+            with _timed("build"):
+                gn.check(L.ga_build_paired(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap, gn.ptr(queries),
+                                           cap, gn.ptr(qedges), cap, gn.ptr(dh), gn.ptr(status), _stream()))
+        st = _check_status(status)
+        if not st & gn.ST_STAMP_FULL:
+            break
+        if cap >= cap_limit:
+            raise MemoryError("edge tables do not fit in device memory")
+        cap = min(cap * 2, cap_limit)
+    if not reads.paired:
+        gn.check(L.ga_csr_plan_unpaired(gn.ptr(node_stamp), n_solid, gn.ptr(solid_keys), kw, alphabet.sym_bits,
+                                        gn.ptr(edges), cap, _stream(), C.byref(plan), C.byref(n_nodes),
+                                        C.byref(n_edges)))
+        attr.value = n_edges.value
+    else:
+        gn.check(L.ga_csr_plan_paired(gn.ptr(solid), solid_cap, gn.ptr(solid_keys), n_solid, kw, k,
+                                      alphabet.sym_bits, gn.ptr(queries), cap, gn.ptr(qedges), cap, gn.ptr(dh),
+                                      _stream(), C.byref(plan), C.byref(n_nodes), C.byref(n_edges),
+                                      C.byref(attr)))
+    try:
+        nn, ne = n_nodes.value, n_edges.value
+        rowptr = torch.empty(nn + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+        indeg = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        branching = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        last_sym = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        keys_a = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
+        keys_b = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev) if reads.paired else None
+        gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
+                               gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
+        torch.cuda.current_stream().synchronize()
+    finally:
+        L.ga_csr_plan_free(plan)
+    graph.n_nodes, graph.n_edges, graph.num_edges_attr = nn, ne, attr.value
+    if not to_host:
+        graph.device = dict(rowptr=rowptr, col=col, indeg=indeg, branching=branching, last_sym=last_sym,
+                            keys_a=keys_a, keys_b=keys_b)
+        return graph
+    graph.rowptr = rowptr.cpu().numpy()
+    graph.col = col[:ne].cpu().numpy()
+    graph.indeg = indeg[:nn].cpu().numpy()
+    graph.branching = branching[:nn].cpu().numpy()
+    graph.last_char = alphabet.inv[last_sym[:nn].cpu().numpy()]
+    graph.keys_a = keys_a[:nn].cpu().numpy().view(np.uint64)
+    graph.keys_b = keys_b[:nn].cpu().numpy().view(np.uint64) if reads.paired else None
+    return graph
+
+
+# ----------------------------------------------------------------------------------- whole path
+def device_step(reads: DeviceReads, k: int, threshold: int, timers=None):
+    """One pass of the hot path over device-resident packed reads; the CSR stays on the device."""
+    global TIMERS
+    TIMERS = timers
+    try:
+        counts = KmerCounts(k, reads)
+        return build_graph(counts, reads, threshold, to_host=False)
+    finally:
+        TIMERS = None
+
+
+def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: bool, k: int, threshold: int):
+    """The same from host memory: ASCII reads (pinned) -> H2D -> pack -> count -> filter -> build ->
+    CSR arrays on the host.  This is the call bench.py times as `e2e`."""
+    reads = DeviceReads.from_ascii(ascii_pinned, n_reads, read_len, paired, estride=read_len)
+    counts = KmerCounts(k, reads)
+    if _check_status(reads.status) & gn.ST_BAD_SYMBOL:
+        raise ValueError("read symbol outside the alphabet")
+    return build_graph(counts, reads, threshold, to_host=True)

@@ -1,0 +1,116 @@
+"""ctypes binding of libga_b200.so (include/ga_b200.h) -- the only door from the Python
+host code to the sm_100a kernels.
+
+There is deliberately no CPU implementation behind this module: if the shared library is
+missing, or no CUDA device is visible, every compute entry raises.  PyTorch is used for
+device buffers and streams only (tensors are handed over as raw pointers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libga_b200.so")
+
+GA_OK = 0
+GA_ERR_BAD_ARG, GA_ERR_CAPACITY, GA_ERR_CUDA, GA_ERR_NCCL, GA_ERR_OVERFLOW_U16, GA_ERR_ALPHABET = \
+    -1, -2, -3, -4, -5, -6
+ST_TABLE_FULL, ST_BAD_SYMBOL, ST_STAMP_FULL, ST_U16_OVERFLOW = 1, 2, 4, 8
+MAX_SKETCH_ROWS = 20
+
+
+class GaError(RuntimeError):
+    """A libga_b200 call failed (message from ga_last_error())."""
+
+
+class GaReads(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("offsets", C.c_void_p), ("lengths", C.c_void_p),
+                ("n_reads", C.c_uint64), ("first_read", C.c_uint64),
+                ("uniform_len", C.c_uint32), ("stride_words", C.c_uint32),
+                ("storage_bits", C.c_int32), ("sym_bits", C.c_int32), ("paired", C.c_int32),
+                ("estride", C.c_uint32)]
+
+
+class GaSketch(C.Structure):
+    _fields_ = [("cells", C.c_void_p), ("width", C.c_uint32 * MAX_SKETCH_ROWS), ("rows", C.c_int32)]
+
+
+_vp, _u64, _u32, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int
+_PR, _PS = C.POINTER(GaReads), C.POINTER(GaSketch)
+
+# name -> (restype, argtypes); mirrors include/ga_b200.h one to one
+SIGNATURES = {
+    "ga_version": (_i32, []),
+    "ga_last_error": (C.c_char_p, []),
+    "ga_device_count": (_i32, []),
+    "ga_launch_count": (_u64, []),
+    "ga_fill_bytes": (_i32, [_vp, _i32, _u64, _vp]),
+    "ga_key_words": (_i32, [_i32, _i32]),
+    "ga_slot_bytes": (_i32, [_i32]),
+    "ga_pack_reads": (_i32, [_vp, _vp, _u64, _u32, _vp, _i32, _vp, _vp, _u32, _vp, _vp]),
+    "ga_gen_genome": (_i32, [_vp, _u64, _u64, _vp]),
+    "ga_gen_reads": (_i32, [_vp, _u64, _u64, _u64, _u32, _u64, _u32, _vp, _u32, _i32, _u32, _vp]),
+    "ga_table_clear": (_i32, [_vp, _u64, _i32, _vp]),
+    "ga_count_kmers": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp]),
+    "ga_count_keys": (_i32, [_vp, _vp, _u64, _i32, _vp, _u64, _vp, _vp]),
+    "ga_table_summary": (_i32, [_vp, _u64, _i32, _i64, _vp, _vp]),
+    "ga_table_export": (_i32, [_vp, _u64, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "ga_table_lookup": (_i32, [_vp, _u64, _i32, _vp, _u64, _vp, _vp]),
+    "ga_table_insert_ids": (_i32, [_vp, _u64, _i32, _u32, _vp, _u64, _vp, _vp]),
+    "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
+    "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
+    "ga_sketch_estimate_bytes": (_i32, [_vp, _vp, _u64, _PS, _vp, _vp]),
+    "ga_sketch_narrow": (_i32, [_PS, _vp, _vp, _vp]),
+    "ga_select_solid": (_i32, [_vp, _u64, _i32, _i32, _i32, _i64, _PS, _vp, _vp, _vp, _vp, _vp]),
+    "ga_build_unpaired": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
+    "ga_build_paired": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "ga_csr_plan_unpaired": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _u64, _vp,
+                                    C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ga_csr_plan_paired": (_i32, [_vp, _u64, _vp, _u64, _i32, _i32, _i32, _vp, _u64, _vp, _u64, _vp, _vp,
+                                  C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ga_csr_emit": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ga_csr_plan_free": (None, [_vp]),
+    "ga_traverse_contigs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
+                                   C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp]),
+    "ga_free_host": (None, [_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises ImportError if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libga_b200.so is missing: build it with `python __graft_entry__.py` or "
+                "`make -C genome-assembler_b200` (there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().ga_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != GA_OK:
+        raise GaError("libga_b200 error %d: %s" % (rc, last_error()))
+
+
+def require_gpu() -> None:
+    if lib().ga_device_count() < 1:
+        raise GaError("no CUDA device visible: the k-mer counting / graph build path runs on "
+                      "the GPU only (no CPU fallback)")
+
+
+def ptr(tensor) -> int:
+    """Raw device (or host) pointer of a torch tensor, None -> NULL."""
+    return None if tensor is None else tensor.data_ptr()

@@ -1,0 +1,212 @@
+/*
+ * ga_b200.h -- C ABI of libga_b200.so: the B200 (sm_100a) implementation of the k-mer
+ * counting / CountMinSketch / de Bruijn graph construction path of
+ * tonycheang/genome-assembler.
+ *
+ * The reference is pure Python and has no FFI; the functions below are what a ctypes
+ * binding for that path binds.  Each entry names the reference
+ * code it replaces (paths relative to the upstream checkout).
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every pointer named *_dev is a CUDA device pointer
+ *    owned by the caller; `stream` is a cudaStream_t passed as void*.
+ *  - every function returns 0 (GA_OK) or a negative GA_ERR_* code and never throws or
+ *    exits; ga_last_error() gives the message (thread-local).
+ *  - functions are asynchronous on `stream` unless documented as synchronising.
+ *  - device-side conditions (a full hash table, a symbol outside the alphabet, a sketch
+ *    cell above 65535) are OR-ed into the caller's `status_dev[0]` (GA_ST_* bits); the
+ *    caller reads it at its next synchronisation point.
+ *  - there is no CPU fallback: without a CUDA device every compute entry returns
+ *    GA_ERR_CUDA.
+ */
+#ifndef GA_B200_H
+#define GA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GA_OK 0
+#define GA_ERR_BAD_ARG (-1)
+#define GA_ERR_CAPACITY (-2)
+#define GA_ERR_CUDA (-3)
+#define GA_ERR_NCCL (-4)
+#define GA_ERR_OVERFLOW_U16 (-5)
+#define GA_ERR_ALPHABET (-6)
+
+#define GA_STATUS_TABLE_FULL 1u
+#define GA_STATUS_BAD_SYMBOL 2u
+#define GA_STATUS_STAMP_FULL 4u
+#define GA_STATUS_U16_OVERFLOW 8u
+
+#define GA_MAX_SKETCH_ROWS 20
+
+typedef void* ga_stream;
+
+/* Packed reads resident on the device.  A read is a run of 64-bit words; symbol i sits at bits
+ * [storage_bits*(i % spw), +storage_bits) of word i / spw, spw = 64 / storage_bits.
+ * storage_bits = 2: A,C,G,T = 0..3 (DNA); storage_bits = 8: one code byte per symbol
+ * (arbitrary alphabets, codes < 2^sym_bits).  Paired input stores mate 1 of pair p as read 2p
+ * and mate 2 as read 2p+1; windows are taken over mate 1's length (debruijn_graph.py:369-374)
+ * so mate 2 must be at least as long. */
+typedef struct ga_reads {
+    const void* words;       /* device */
+    const uint64_t* offsets; /* device, first word of each read; NULL = r * stride_words */
+    const uint32_t* lengths; /* device, symbols per read; NULL = uniform_len */
+    uint64_t n_reads;        /* reads, or 2 * pairs when paired */
+    uint64_t first_read;     /* global index of the first read / pair of this shard (stamps) */
+    uint32_t uniform_len;
+    uint32_t stride_words;
+    int32_t storage_bits;    /* 2 or 8 */
+    int32_t sym_bits;        /* bits per symbol inside a key: 2, or 1..8 for storage_bits 8 */
+    int32_t paired;
+    uint32_t estride;        /* stamp stride per read, >= longest read; same on all shards */
+} ga_reads;
+
+/* CountMinSketch geometry (countminsketch.py:26-32): `rows` rows, row i has width[i] cells.
+ * cells_dev holds 32-bit working cells, rows back to back; ga_sketch_narrow() produces the
+ * reference's unsigned-16 rows and reports cells above 65535. */
+typedef struct ga_sketch {
+    void* cells;             /* device, uint32_t[sum(width)] */
+    uint32_t width[GA_MAX_SKETCH_ROWS];
+    int32_t rows;
+} ga_sketch;
+
+/* ---- housekeeping ------------------------------------------------------------------------- */
+int ga_version(void);
+const char* ga_last_error(void);
+int ga_device_count(void);                 /* number of CUDA devices, 0 without a GPU */
+uint64_t ga_launch_count(void);            /* kernels of this library launched so far (process-wide) */
+int ga_fill_bytes(void* dev, int value, uint64_t bytes, ga_stream stream);
+
+/* key geometry: 1 word (64-bit keys) when (k-1)*sym_bits <= 63, 2 words when <= 127,
+ * otherwise 0 (unsupported on this build). */
+int ga_key_words(int k, int sym_bits);
+/* bytes per slot of a count / id table with that key width (16 or 32) */
+int ga_slot_bytes(int key_words);
+
+/* ---- read ingestion: replaces IOHandler.read_input's string list (assemble.py:40-71) ------ */
+/* ASCII symbols -> packed reads.  ascii_dev: all reads back to back; in_offsets_dev[n+1] byte
+ * offsets (NULL: read r at r*uniform_len).  lut_dev[256]: byte -> code, 0xFF = not in the
+ * alphabet (sets GA_STATUS_BAD_SYMBOL).  Output layout as described at ga_reads. */
+int ga_pack_reads(const uint8_t* ascii_dev, const uint64_t* in_offsets_dev, uint64_t n_reads,
+                  uint32_t uniform_len, const uint8_t* lut_dev, int storage_bits, void* words_dev,
+                  const uint64_t* out_offsets_dev, uint32_t stride_words, uint32_t* status_dev,
+                  ga_stream stream);
+
+/* Synthetic reads on the device (our replacement for generate_reads.py:42-74 where it cannot
+ * produce the shape: any length, per-base substitutions, seeded; arithmetic documented in
+ * oracle/readgen.py splitmix_*).  genome_codes_dev: one 2-bit code per byte.  first_read /
+ * n_reads count stored reads (mates when paired: read r is mate r&1 of pair r>>1, mate 2 drawn
+ * mate_distance bases after mate 1). */
+int ga_gen_genome(uint8_t* genome_codes_dev, uint64_t size, uint64_t seed, ga_stream stream);
+int ga_gen_reads(const uint8_t* genome_codes_dev, uint64_t genome_size, uint64_t first_read,
+                 uint64_t n_reads, uint32_t read_len, uint64_t seed, uint32_t sub_per_10k,
+                 void* words_dev, uint32_t stride_words, int paired, uint32_t mate_distance,
+                 ga_stream stream);
+
+/* ---- exact counting: replaces _count_kmers (debruijn_graph.py:144-152, 349-367) ----------- */
+int ga_table_clear(void* table_dev, uint64_t capacity, int key_words, ga_stream stream);
+/* one increment per window occurrence of every read (both mates when paired) */
+int ga_count_kmers(const ga_reads* reads, int k, void* table_dev, uint64_t capacity,
+                   uint32_t* status_dev, ga_stream stream);
+/* add `amounts_dev[i]` (NULL: 1) for explicit packed keys (multi-GPU owner side; dict upload) */
+int ga_count_keys(const void* keys_dev, const uint32_t* amounts_dev, uint64_t n, int key_words,
+                  void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
+/* out4_dev = { distinct keys, keys with count > threshold, sum of counts, max count } */
+int ga_table_summary(const void* table_dev, uint64_t capacity, int key_words, int64_t threshold,
+                     uint64_t* out4_dev, ga_stream stream);
+/* compact (key, count) of every slot with count > min_exclusive (-1: all) into keys_out_dev /
+ * counts_out_dev (either may be NULL); *n_out_dev must be zeroed by the caller */
+int ga_table_export(const void* table_dev, uint64_t capacity, int key_words, int64_t min_exclusive,
+                    void* keys_out_dev, uint32_t* counts_out_dev, uint64_t* n_out_dev,
+                    ga_stream stream);
+/* counts_out_dev[i] = count of keys_dev[i], 0 when absent (dict __getitem__ of a defaultdict) */
+int ga_table_lookup(const void* table_dev, uint64_t capacity, int key_words, const void* keys_dev,
+                    uint64_t n, uint32_t* counts_out_dev, ga_stream stream);
+/* id table: insert keys_dev[i] -> id_base + i (keys must be distinct) */
+int ga_table_insert_ids(const void* keys_dev, uint64_t n, int key_words, uint32_t id_base,
+                        void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
+
+/* ---- CountMinSketch: replaces countminsketch.py:34-44 and _make_sketch --------------------- */
+/* cells[row][murmur3(window) % width[row]] += count for every key of the count table
+ * (debruijn_graph.py:181-188, 398-405).  lut_dev[256]: symbol code -> byte. */
+int ga_sketch_update_table(const void* table_dev, uint64_t capacity, int key_words, int k,
+                           int sym_bits, const uint8_t* lut_dev, const ga_sketch* sketch,
+                           ga_stream stream);
+/* update(string, amount) / estimate(string) in bulk on raw bytes: string i is
+ * bytes_dev[offsets_dev[i] .. offsets_dev[i+1]) */
+int ga_sketch_update_bytes(const uint8_t* bytes_dev, const uint64_t* offsets_dev,
+                           const uint32_t* amounts_dev, uint64_t n, const ga_sketch* sketch,
+                           ga_stream stream);
+int ga_sketch_estimate_bytes(const uint8_t* bytes_dev, const uint64_t* offsets_dev, uint64_t n,
+                             const ga_sketch* sketch, uint32_t* est_out_dev, ga_stream stream);
+/* 32-bit working cells -> the reference's array('H') rows; a cell above 65535 sets
+ * GA_STATUS_U16_OVERFLOW (the reference raises OverflowError there) */
+int ga_sketch_narrow(const ga_sketch* sketch, uint16_t* rows_out_dev, uint32_t* status_dev,
+                     ga_stream stream);
+
+/* ---- filter: the strict `> threshold` test of _build_graph (debruijn_graph.py:127-128,
+ *      275-278) evaluated once per distinct window ---------------------------------------- */
+/* Compacts the keys whose exact count (sketch == NULL) or sketch estimate is > threshold.
+ * *n_out_dev must be zeroed by the caller.  counts_out_dev may be NULL. */
+int ga_select_solid(const void* table_dev, uint64_t capacity, int key_words, int k, int sym_bits,
+                    int64_t threshold, const ga_sketch* sketch, const uint8_t* lut_dev,
+                    void* keys_out_dev, uint32_t* counts_out_dev, uint64_t* n_out_dev,
+                    ga_stream stream);
+
+/* ---- graph build: replaces _build_graph (debruijn_graph.py:113-142 unpaired, 269-317 paired) */
+/* Unpaired.  solid_dev: id table (key -> dense id < n_solid).  node_stamp_dev[n_solid] and the
+ * edge stamp table (16-byte slots, key = src_id << 32 | dst_id) must be filled with 0xFF. */
+int ga_build_unpaired(const ga_reads* reads, int k, const void* solid_dev, uint64_t solid_capacity,
+                      uint64_t* node_stamp_dev, void* edge_table_dev, uint64_t edge_capacity,
+                      uint32_t* status_dev, ga_stream stream);
+/* Paired.  query table: key = idA << 32 | idB -> min stamp; query-edge table: key =
+ * query_slot(P) << 32 | query_slot(S) -> min occurrence; dh_dev: 256*256*2 uint64 (0xFF filled),
+ * the two smallest occurrences of "prefix pair == suffix pair" per (symbol A, symbol B)
+ * (SURVEY App. A-9). */
+int ga_build_paired(const ga_reads* reads, int k, const void* solid_dev, uint64_t solid_capacity,
+                    void* query_table_dev, uint64_t query_capacity, void* qedge_table_dev,
+                    uint64_t qedge_capacity, uint64_t* dh_dev, uint32_t* status_dev,
+                    ga_stream stream);
+
+/* ---- CSR emission in the reference's insertion order --------------------- */
+typedef struct ga_csr_plan ga_csr_plan;
+/* Both plan calls synchronise `stream` and report the graph size; ga_csr_emit then fills
+ * caller-allocated arrays:
+ *   rowptr[n_nodes+1], col[n_edges] (successor ids, each row in edge-insertion order),
+ *   indeg[n_nodes], branching[n_nodes], last_sym[n_nodes] (code of the node's last symbol),
+ *   node_keys_a[n_nodes*key_words] (+ node_keys_b when paired) packed window keys.
+ * num_edges_attr = the reference's graph.num_edges (n_edges plus orphaned self-loops). */
+int ga_csr_plan_unpaired(const uint64_t* node_stamp_dev, uint64_t n_solid, const void* solid_keys_dev,
+                         int key_words, int sym_bits, const void* edge_table_dev,
+                         uint64_t edge_capacity, ga_stream stream, ga_csr_plan** plan_out,
+                         int64_t* n_nodes, int64_t* n_edges);
+int ga_csr_plan_paired(const void* solid_dev, uint64_t solid_capacity, const void* solid_keys_dev,
+                       uint64_t n_solid, int key_words, int k, int sym_bits,
+                       const void* query_table_dev, uint64_t query_capacity,
+                       const void* qedge_table_dev, uint64_t qedge_capacity, const uint64_t* dh_dev,
+                       ga_stream stream, ga_csr_plan** plan_out, int64_t* n_nodes, int64_t* n_edges,
+                       int64_t* num_edges_attr);
+int ga_csr_emit(ga_csr_plan* plan, int32_t* rowptr_dev, int32_t* col_dev, int32_t* indeg_dev,
+                uint8_t* branching_dev, uint8_t* last_sym_dev, void* node_keys_a_dev,
+                void* node_keys_b_dev, ga_stream stream);
+void ga_csr_plan_free(ga_csr_plan* plan);
+
+/* ---- host-side contig traversal over the CSR (debruijn_graph.py:72-111, 222-267) ----------- */
+/* Arrays are HOST pointers.  last_char: the byte each node contributes.  Allocates *text_out
+ * (all contigs back to back) and *offsets_out[n_contigs+1]; release both with ga_free_host.
+ * left_out (optional, [n_nodes]): edges remaining per node afterwards (each row is consumed
+ * from its end, as dict.popitem does). */
+int ga_traverse_contigs(const int32_t* rowptr, const int32_t* col, const int32_t* indeg,
+                        const uint8_t* branching, const uint8_t* last_char, int64_t n_nodes,
+                        int64_t num_edges_attr, int paired, uint8_t** text_out,
+                        uint64_t** offsets_out, uint64_t* n_contigs, int32_t* left_out);
+void ga_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GA_B200_H */

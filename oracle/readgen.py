@@ -80,12 +80,14 @@ def splitmix_genome_codes(size: int, seed: int) -> np.ndarray:
 
 
 def splitmix_reads_codes(genome_codes: np.ndarray, read_len: int, first_read: int,
-                         num_reads: int, seed: int, sub_per_10k: int = 100) -> np.ndarray:
+                         num_reads: int, seed: int, sub_per_10k: int = 100,
+                         paired: bool = False, mate_distance: int = 0) -> np.ndarray:
     """``num_reads`` x ``read_len`` uint8 codes for reads ``first_read..``: circular start
     uniform in [0, G), every base independently replaced with probability
     ``sub_per_10k / 10000`` by a uniform draw from ACGT (may equal the original).
 
-    start(r)   = splitmix64(seed*2^40 + 2^39 + r) % G
+    start(r)   = splitmix64(seed*2^40 + 2^39 + r) % G      [paired: r>>1 is drawn, and mate
+                 r&1 == 1 starts mate_distance later; rows are stored reads = mates]
     h(r, i)    = splitmix64((seed+1)*2^40 ^ (r*read_len + i))   [xor; r*L+i < 2^40]
     replace    iff h % 10000 < sub_per_10k, with code (h >> 32) & 3
     """
@@ -93,7 +95,10 @@ def splitmix_reads_codes(genome_codes: np.ndarray, read_len: int, first_read: in
     r = np.arange(first_read, first_read + num_reads, dtype=np.uint64)
     with np.errstate(over="ignore"):
         base = (np.uint64(seed) << np.uint64(40)) + (np.uint64(1) << np.uint64(39))
-        start = splitmix64(base + r) % size
+        draw = (r >> np.uint64(1)) if paired else r
+        start = splitmix64(base + draw) % size
+        if paired:
+            start = (start + (r & np.uint64(1)) * np.uint64(mate_distance)) % size
         pos = (start[:, None] + np.arange(read_len, dtype=np.uint64)[None, :]) % size
         codes = genome_codes[pos.astype(np.int64)]
         ctr = (r[:, None] * np.uint64(read_len)) + np.arange(read_len, dtype=np.uint64)[None, :]

@@ -155,6 +155,10 @@ def main():
                     [list(t) for t in ref_dbg.PairedDeBruijnGraph._break_read_into_k_minus_one_mers(4, ("ACTGAC", "TCGATC"))]]],
     }
 
+    gold["prime_tables"] = {name: list(getattr(ref_cms.CountMinSketch, name))
+                            for name in ("primes_6_10_7", "primes_1_10_7", "primes_5_10_6")}
+    gold["sketch_sizeof_10"] = 199998988  # sys.getsizeof(CountMinSketch(10)), SURVEY App. B.1
+
     kat = [["nnabe_Lee;", "_Lee;By_th"], ["By_the_nam", "e_name_of_"], ["abe_Lee;By", "ee;By_the_"],
            ["e_of_Annab", "Annabe_Lee"], ["e_name_of_", "e_of_Annab"]]
     circles = ["ACGTTGCAAC" * 3] * 5 + ["GGATCCTAGG" * 3] * 5
@@ -191,6 +195,9 @@ def main():
         ("nd-unpaired-k33", refgen("n_delto", 100, 20000, False, 5), 33, 2, "DeBruijnGraph"),
         ("nd-unpaired-k41", refgen("n_delto", 100, 20000, False, 5), 41, 2, "DeBruijnGraph"),
         ("nd-unpaired-k65", refgen("n_delto", 100, 20000, False, 5), 65, 1, "DeBruijnGraph"),
+        ("nd-unpaired-k64", refgen("n_delto", 100, 20000, False, 5), 64, 1, "DeBruijnGraph"),
+        ("nd-unpaired-k32", refgen("n_delto", 100, 20000, False, 5), 32, 2, "DeBruijnGraph"),
+        ("nd-paired-k64", refgen("n_delto", 100, 12000, True, 6, 1), 64, 1, "PairedDeBruijnGraph"),
         ("nd-paired-k35", refgen("n_delto", 100, 12000, True, 6, 1), 35, 2, "PairedDeBruijnGraph"),
     ]
     big = [

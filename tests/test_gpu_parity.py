@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped classes) with the oracle and
+with the golden vectors the unmodified reference produced.  Bit-exact: counts, sketch cells,
+node order, edge order, in-degrees, was_branching, contigs."""
+import hashlib
+import io
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, ROOT, counts_sha, reads_for, sha16
+from oracle import py_oracle as po
+from oracle import c_oracle as co
+import recipes
+
+pytestmark = pytest.mark.gpu
+
+CLASS_BY_NAME = {}
+
+
+def _classes():
+    if not CLASS_BY_NAME:
+        import debruijn_graph as dg
+        for name in ("DeBruijnGraph", "CMSDeBruijnGraph", "PairedDeBruijnGraph", "CMSPairedDeBruijnGraph"):
+            CLASS_BY_NAME[name] = getattr(dg, name)
+    return CLASS_BY_NAME
+
+
+def digest_of(graph) -> str:
+    """Graph digest from the CSR a product graph object holds."""
+    csr = graph._csr
+    keys = csr.node_strings()
+    h = hashlib.sha256()
+    rowptr, col = csr.rowptr, csr.col
+    for i, key in enumerate(keys):
+        edges = [keys[j] for j in col[rowptr[i]:rowptr[i + 1]]]
+        h.update(repr((key, edges, int(csr.indeg[i]), bool(csr.branching[i]))).encode())
+    return h.hexdigest()[:16]
+
+
+def check_against_gold(name, check_counts=True):
+    gold = GOLDEN["cases"][name]
+    reads = reads_for(gold["recipe"])
+    cls = _classes()[gold["cls"]]
+    if check_counts and "counts_sha" in gold:
+        counts = cls._count_kmers(gold["k"], reads)
+        assert len(counts) == gold["n_distinct"]
+        assert counts.summary(gold["F"])[1] == gold["n_solid"]
+        assert counts.summary(gold["F"])[2] == gold["n_occ"]
+        assert counts_sha(counts.items()) == gold["counts_sha"]
+        if "sketch_rows" in gold:
+            sk = cls._make_sketch(counts)
+            assert sk.num_rows == gold["sketch_rows"]
+            assert [sha16(row.tobytes()) for row in sk.hash_values] == gold["sketch_row_sha"]
+    graph = cls(reads, k=gold["k"], hamming_dist=gold["F"])
+    assert graph._csr.n_nodes == gold["n_nodes"]
+    assert graph.num_edges == gold["num_edges"]
+    assert digest_of(graph) == gold["graph_digest"]
+    contigs = graph.enumerate_contigs()
+    assert len(contigs) == gold["n_contigs"]
+    assert po.contig_digest(contigs) == gold["contig_digest"]
+    assert graph.num_edges == gold["edges_left"]
+    if "contigs" in gold:
+        assert contigs == gold["contigs"]
+
+
+SMALL = ["kat-f1", "kat-f0", "homopoly-A-paired", "homopoly-AC-paired", "homopoly-unpaired", "two-circles",
+         "ragged", "toy-unpaired", "toy-paired"]
+MEDIUM = ["nd-unpaired", "nd-paired", "nd-paired-jitter2", "nd-unpaired-s1", "nd-unpaired-k32",
+          "nd-unpaired-k33", "nd-unpaired-k41", "nd-unpaired-k64", "nd-paired-k35", "nd-paired-k64"]
+SKETCHED = ["kat-f1-cms", "toy-unpaired-cms", "nd-unpaired-s1-cms", "nd-paired-cms8"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_small_golden(name):
+    check_against_gold(name)
+
+
+@pytest.mark.parametrize("name", MEDIUM)
+def test_medium_golden(name):
+    check_against_gold(name)
+
+
+@pytest.mark.parametrize("name", SKETCHED)
+def test_sketch_golden(name):
+    check_against_gold(name)
+
+
+def test_fuzz_golden():
+    """206 small random graphs (tiny alphabets, jittered pairs, homopolymers, cycles)."""
+    bad = []
+    for key, gold in GOLDEN["fuzz"].items():
+        recipe, k, F = recipes.fuzz_recipe(int(key))
+        cls = _classes()["PairedDeBruijnGraph" if recipe["paired"] else "DeBruijnGraph"]
+        graph = cls(reads_for(recipe), k=k, hamming_dist=F)
+        got = (graph._csr.n_nodes, graph.num_edges, digest_of(graph))
+        contigs = graph.enumerate_contigs()
+        got += (len(contigs), po.contig_digest(contigs))
+        want = (gold["n_nodes"], gold["num_edges"], gold["graph_digest"], gold["n_contigs"], gold["contig_digest"])
+        if got != want:
+            bad.append((key, got, want))
+    assert not bad, bad[:5]
+
+
+def test_fuzz_counts_vs_oracle():
+    for i in range(0, 40):
+        recipe, k, F = recipes.fuzz_recipe(i)
+        reads = reads_for(recipe)
+        cls = _classes()["PairedDeBruijnGraph" if recipe["paired"] else "DeBruijnGraph"]
+        want = (po.count_paired if recipe["paired"] else po.count_unpaired)(k, reads)
+        got = dict(cls._count_kmers(k, reads).items())
+        assert got == dict(want), i
+
+
+@pytest.mark.parametrize("name", ["c2-s-aureus", "c3-ecoli-standin"])
+def test_full_size_configs(name):
+    """BASELINE configs C2 and C3 at full size against the reference's own digests."""
+    check_against_gold(name, check_counts=False)
+
+
+def test_full_size_count_properties():
+    """Size-independent invariants on C2: occurrences conserved, table deterministic."""
+    gold = GOLDEN["cases"]["c2-s-aureus"]
+    reads = reads_for(gold["recipe"])
+    cls = _classes()["DeBruijnGraph"]
+    a = cls._count_kmers(gold["k"], reads)
+    distinct, solid, occ, top = a.summary(gold["F"])
+    assert occ == len(reads) * (100 - gold["k"] + 2)
+    b = cls._count_kmers(gold["k"], reads)
+    assert b.summary(gold["F"]) == (distinct, solid, occ, top)
+    ka, ca = a.export(gold["F"])
+    kb, cb = b.export(gold["F"])
+    oa, ob = np.argsort(ka[:, 0], kind="stable"), np.argsort(kb[:, 0], kind="stable")
+    assert np.array_equal(ka[oa], kb[ob]) and np.array_equal(ca[oa], cb[ob])
+
+
+# ------------------------------------------------------------------------------ edge cases
+def test_empty_and_short_inputs():
+    dg = _classes()
+    for reads in ([], [""], ["AC"], ["ACG", "", "A"]):
+        g = dg["DeBruijnGraph"](reads, k=5, hamming_dist=0)
+        assert g.num_edges == 0 and g.enumerate_contigs() == [] and len(g.nodes) == 0
+    g = dg["PairedDeBruijnGraph"]([], k=5, hamming_dist=0)
+    assert g.enumerate_contigs() == [] and len(g.nodes) == 0
+    g = dg["DeBruijnGraph"](["ACGTA"], k=6, hamming_dist=0)      # exactly one window, no edge
+    assert dict(g._count_kmers(6, ["ACGTA"]).items()) == {"ACGTA": 1}
+    assert g.num_edges == 0
+
+
+def test_error_behaviour():
+    dg = _classes()
+    with pytest.raises(ValueError, match="Allowed error must be less than the kmer length."):
+        dg["DeBruijnGraph"](["ACGT"], k=2)
+    with pytest.raises(ValueError):
+        dg["DeBruijnGraph"](["ACĀT" * 4], k=3, hamming_dist=0)
+    with pytest.raises(ValueError):
+        dg["PairedDeBruijnGraph"]([("ACGTACGT", "ACG")], k=4, hamming_dist=0)
+    with pytest.raises(ValueError):
+        dg["DeBruijnGraph"](["ACGT" * 40], k=66, hamming_dist=0)   # 130 key bits
+    from countminsketch import CountMinSketch
+    with pytest.raises(AssertionError):
+        CountMinSketch(20)
+
+
+def test_arbitrary_alphabet_against_oracle():
+    text = "It was many and many a year ago, In a kingdom by the sea, That a maiden there lived whom you may know"
+    reads = [text[i:i + 14] for i in range(0, len(text) - 14)] * 3
+    for k in (4, 7, 12):
+        _, _, want = po.assemble(reads, k, 1, False)
+        g = _classes()["DeBruijnGraph"](reads, k=k, hamming_dist=1)
+        assert digest_of(g) == want.digest()
+        assert g.enumerate_contigs() == po.contigs(want)
+
+
+def test_against_c_oracle_random_dna():
+    rng = np.random.default_rng(5)
+    genome = "".join("ACGT"[c] for c in rng.integers(0, 4, 3000))
+    for paired in (False, True):
+        reads = []
+        for _ in range(4000):
+            s = int(rng.integers(0, 3000))
+            r = (genome * 2)[s:s + 60]
+            if rng.random() < 0.5:
+                p = int(rng.integers(0, 60))
+                r = r[:p] + "ACGT"[int(rng.integers(0, 4))] + r[p + 1:]
+            if paired:
+                s2 = (s + 80 + int(rng.integers(-2, 3))) % 3000
+                reads.append((r, (genome * 2)[s2:s2 + 60]))
+            else:
+                reads.append(r)
+        for k in (12, 21, 33, 40):
+            want = co.assemble(reads, k, 2, paired)
+            cls = _classes()["PairedDeBruijnGraph" if paired else "DeBruijnGraph"]
+            g = cls(reads, k=k, hamming_dist=2)
+            assert (g._csr.n_nodes, g.num_edges) == (want.n_nodes, want.num_edges), (paired, k)
+            assert digest_of(g) == want.digest(), (paired, k)
+            assert g.enumerate_contigs() == want.contigs(), (paired, k)
+            want.close()
+
+
+def test_deterministic_across_runs():
+    gold = GOLDEN["cases"]["nd-paired-jitter2"]
+    reads = reads_for(gold["recipe"])
+    cls = _classes()["PairedDeBruijnGraph"]
+    a = cls(reads, k=gold["k"], hamming_dist=gold["F"])._csr
+    b = cls(reads, k=gold["k"], hamming_dist=gold["F"])._csr
+    for field in ("rowptr", "col", "indeg", "branching", "last_char", "keys_a", "keys_b"):
+        assert np.array_equal(getattr(a, field), getattr(b, field)), field
+
+
+# ------------------------------------------------------------------------------ API surface
+def test_counts_mapping_surface():
+    reads = ["ACGTACGTAC", "CGTACGTTTT"]
+    counts = _classes()["DeBruijnGraph"]._count_kmers(5, reads)
+    want = po.count_unpaired(5, reads)
+    assert len(counts) == len(want) and bool(counts)
+    assert counts["ACGT"] == want["ACGT"] and counts["GGGG"] == 0 and counts["AC"] == 0
+    assert "ACGT" in counts and "NNNN" not in counts
+    assert dict(counts.items()) == dict(want)
+
+
+def test_sketch_scalar_interface():
+    from countminsketch import CountMinSketch
+    sk = CountMinSketch(3)
+    ref = po.Sketch(3)
+    rng = np.random.default_rng(3)
+    words = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(1, 40)))) for _ in range(300)]
+    for i, word in enumerate(words):
+        sk.update(word, i % 7 + 1)
+        ref.update(word, i % 7 + 1)
+    assert [sk.estimate(wd) for wd in words[:50]] == [ref.estimate(wd) for wd in words[:50]]
+    assert sk["ACGT"] == ref["ACGT"]
+    assert [row.tobytes() for row in sk.hash_values] == [row.tobytes() for row in ref.rows]
+    assert CountMinSketch._hash("ACGT") == po.murmur3_32("ACGT")
+    assert sys.getsizeof(CountMinSketch(10)) == GOLDEN["sketch_sizeof_10"]
+    sk.update("ACGT", 65535)
+    with pytest.raises(OverflowError):
+        sk.update("ACGT", 1)
+        sk.estimate("ACGT")
+
+
+def test_nodes_materialise_like_reference():
+    gold = GOLDEN["cases"]["toy-paired"]
+    reads = reads_for(gold["recipe"])
+    g = _classes()["PairedDeBruijnGraph"](reads, k=gold["k"], hamming_dist=gold["F"])
+    _, _, want = po.assemble(reads, gold["k"], gold["F"], True)
+    flat = [((a, b), node) for a, inner in g.nodes.items() for b, node in inner.items()]
+    assert [key for key, _ in flat] == want.keys
+    assert [list(node.edges) for _, node in flat] == [[want.keys[j] for j in row] for row in want.succ]
+    assert [node.indegree for _, node in flat] == want.indeg
+    # traversal over the materialised objects gives the same contigs as the CSR walk
+    assert g.enumerate_contigs() == po.contigs(want)
+
+
+def test_debug_mixin_composes(capsys):
+    import debug_graph
+    gold = GOLDEN["cases"]["kat-f1"]
+    reads = reads_for(gold["recipe"])
+    g = debug_graph.DebugCMSPairedDeBruijnGraph(print_runtime=True, print_syssizeof=True, start_time=0.0,
+                                                reads=reads, k=5, hamming_dist=1, paired_error=None)
+    assert g.enumerate_contigs() == gold["contigs"]
+    out = capsys.readouterr().out
+    for needle in ("STARTING TO COUNT KMERS", "FINISHED COUNTING KMERS", "SIZE OF COUNTS CONTAINER",
+                   "STARTING TO MAKE COUNTMIN SKETCH", "SIZE OF COUNTMIN SKETCH: 199,998,988",
+                   "STARTING TO BUILD GRAPH", "SIZE OF ALL NODES", "STARTING TO ENUMERATE CONTIGS"):
+        assert needle in out, needle
+
+
+def _run_cli(args, stdin_text):
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "genome-assembler_b200"))
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "genome-assembler_b200", "assemble.py")] + args,
+                          input=stdin_text, capture_output=True, text=True, env=env, timeout=600)
+    assert proc.returncode == 0, proc.stderr
+    return [ln for ln in proc.stdout.split("\n") if not ln.startswith(">Time")]
+
+
+def test_cli_readme_known_answer():
+    text = ("5\nnnabe_Lee;|_Lee;By_th|5\nBy_the_nam|e_name_of_|5\nabe_Lee;By|ee;By_the_|5\n"
+            "e_of_Annab|Annabe_Lee|5\ne_name_of_|e_of_Annab|5\n")
+    want = [">Number of contigs:  2", ">CONTIG1", "he_", ">CONTIG2", "me_of_Annabe_Lee;By", ""]
+    assert _run_cli(["--kmer_length", "5", "--filter", "1", "--stdout"], text) == want
+    assert _run_cli(["-k", "5", "-f", "1", "-s", "-c", "--paired"], text) == want
+    one = _run_cli(["--kmer_length", "5", "--filter", "0", "--stdout"], text)
+    assert one[2] == "he_name_of_Annabe_Lee;By"
+
+
+def test_synthetic_generator_matches_numpy_model():
+    import ctypes as C
+    import torch
+    import ga_native as gn
+    from oracle import readgen
+    L = gn.lib()
+    dev = torch.device("cuda", 0)
+    G, n, rl, seed = 5003, 700, 150, 11
+    genome = torch.empty(G, dtype=torch.uint8, device=dev)
+    gn.check(L.ga_gen_genome(gn.ptr(genome), G, seed, None))
+    want_g = readgen.splitmix_genome_codes(G, seed)
+    assert np.array_equal(genome.cpu().numpy(), want_g)
+    stride = (rl + 31) // 32
+    words = torch.empty(n * stride, dtype=torch.int64, device=dev)
+    for paired, dist in ((0, 0), (1, 125)):
+        gn.check(L.ga_gen_reads(gn.ptr(genome), G, 40, n, rl, seed, 100, gn.ptr(words), stride, paired, dist,
+                                None))
+        torch.cuda.synchronize()
+        w = words.cpu().numpy().view(np.uint64).reshape(n, stride)
+        codes = np.stack([(w[:, i // 32] >> np.uint64(2 * (i % 32))) & np.uint64(3) for i in range(rl)], axis=1)
+        want = readgen.splitmix_reads_codes(want_g, rl, 40, n, seed, 100, bool(paired), dist)
+        assert np.array_equal(codes.astype(np.uint8), want)

@@ -1,0 +1,137 @@
+"""CPU-only checks of the product's host side: the C ABI loads and exports every symbol the
+header declares, key packing round-trips, input parsing follows the reference's rules, and the
+host contig traversal (ga_traverse_contigs) reproduces the oracle on oracle-built graphs.
+No kernel is launched here."""
+import ctypes as C
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, ROOT, reads_for
+from oracle import py_oracle as po
+import recipes
+
+
+def _lib():
+    import ga_native as gn
+    if not os.path.exists(gn.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    return gn.lib()
+
+
+def test_abi_exports_every_declared_symbol():
+    import ga_native as gn
+    header = open(os.path.join(ROOT, "include", "ga_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|void|uint64_t|const char\*)\s+(ga_\w+)\(", header, flags=re.M))
+    assert len(declared) >= 25
+    lib = _lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(gn.SIGNATURES), declared ^ set(gn.SIGNATURES)
+    assert lib.ga_version() >= 100
+
+
+def test_key_geometry():
+    lib = _lib()
+    assert [lib.ga_key_words(k, 2) for k in (2, 32, 33, 64, 65)] == [1, 1, 2, 2, 0]
+    assert [lib.ga_key_words(k, 5) for k in (5, 13, 14, 26, 27)] == [1, 1, 2, 2, 0]
+    assert (lib.ga_slot_bytes(1), lib.ga_slot_bytes(2)) == (16, 32)
+
+
+def test_no_gpu_fails_loudly():
+    import ga_native as gn
+    lib = _lib()
+    if lib.ga_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    import debruijn_graph as dg
+    with pytest.raises(gn.GaError, match="no CPU fallback"):
+        dg.DeBruijnGraph(["ACGTACGT"], k=4, hamming_dist=0)
+
+
+def test_alphabet_roundtrip():
+    from ga_device import Alphabet
+    rng = np.random.default_rng(1)
+    for symbols, w in ((b"ACGT", 31), (b"ACGT", 63), (b"_abcdefgh;", 9), (bytes(range(48, 48 + 33)), 20)):
+        alpha = Alphabet(np.array(sorted(symbols)))
+        kw = 1 if w * alpha.sym_bits <= 63 else 2
+        words = ["".join(chr(symbols[c]) for c in rng.integers(0, len(symbols), w)) for _ in range(50)]
+        keys = np.zeros((len(words), kw), dtype=np.uint64)
+        for i, word in enumerate(words):
+            lo, hi = alpha.pack_key(word, kw)
+            keys[i, 0] = lo
+            if kw > 1:
+                keys[i, 1] = hi
+        assert alpha.decode_strings(keys, w) == words
+    assert Alphabet(np.array(sorted(b"ACGT"))).pack_key("ACGN", 1) is None
+
+
+def test_read_input_rules():
+    import assemble
+    parse = lambda text: assemble.IOHandler.read_input(io.StringIO(text))   # noqa: E731
+    assert parse("3\nACGT\n  CCC \r\nGG\nignored\n") == (["ACGT", "CCC", "GG"], False, 0, 9)
+    assert parse("2\nAC|GT|5\nCC|GG|7\n") == ([("AC", "GT"), ("CC", "GG")], True, 7, 8)
+    assert parse("0\nACGT\n")[0] == ["ACGT"]                  # n = 0 still consumes one read
+    assert parse("3\nACGT\n")[0] == ["ACGT", "", ""]          # missing lines become empty reads
+    with pytest.raises(ValueError):
+        parse("2\nAC|GT|5\nCCGG\n")
+    args = assemble.IOHandler.read_args(["--kmer_length", "28", "--filter", "3", "--stdout", "--paired"])
+    assert (args.kmer_length, args.filter_threshold, args.stdout, args.paired) == (28, 3, True, True)
+
+
+def _traverse(graph):
+    lib = _lib()
+    n = len(graph.keys)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum([len(s) for s in graph.succ])
+    col = np.array([j for s in graph.succ for j in s] or [0], dtype=np.int32)
+    indeg = np.array(graph.indeg or [0], dtype=np.int32)
+    br = np.array(graph.branching or [0], dtype=np.uint8)
+    last = np.array([ord(graph.last_char(i)) for i in range(n)] or [0], dtype=np.uint8)
+    text, offs, cnt = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    left = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib.ga_traverse_contigs(rowptr.ctypes.data, col.ctypes.data, indeg.ctypes.data, br.ctypes.data,
+                                 last.ctypes.data, n, graph.num_edges, int(graph.paired), C.byref(text),
+                                 C.byref(offs), C.byref(cnt), left.ctypes.data)
+    assert rc == 0
+    off = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_uint64)), shape=(cnt.value + 1,)).copy()
+    raw = C.string_at(text, int(off[-1]))
+    lib.ga_free_host(text)
+    lib.ga_free_host(offs)
+    return [raw[int(off[i]):int(off[i + 1])].decode("latin-1") for i in range(cnt.value)]
+
+
+def test_host_traversal_matches_oracle():
+    for key in list(GOLDEN["fuzz"])[:120]:
+        recipe, k, F = recipes.fuzz_recipe(int(key))
+        _, _, graph = po.assemble(reads_for(recipe), k, F, recipe["paired"])
+        assert _traverse(graph) == po.contigs(graph), key
+    for name in ("two-circles", "homopoly-AC-paired", "kat-f1", "nd-paired-jitter2"):
+        gold = GOLDEN["cases"][name]
+        _, _, graph = po.assemble(reads_for(gold["recipe"]), gold["k"], gold["F"], gold["recipe"]["paired"])
+        got = _traverse(graph)
+        assert po.contig_digest(got) == gold["contig_digest"], name
+
+
+def test_prime_tables_and_hash_helper():
+    from countminsketch import CountMinSketch
+    for name, want in GOLDEN["prime_tables"].items():
+        assert getattr(CountMinSketch, name) == want, name
+    for text, want in GOLDEN["murmur3"]:
+        assert CountMinSketch._hash(text) == want
+    with pytest.raises(AssertionError):
+        CountMinSketch(20)
+
+
+def test_break_helpers():
+    import debruijn_graph as dg
+    for read, k, want in GOLDEN["break"]["unpaired"]:
+        assert dg.DeBruijnGraph._break_read_into_k_minus_one_mers(k, read) == want
+    for pair, k, want in GOLDEN["break"]["paired"]:
+        got = dg.PairedDeBruijnGraph._break_read_into_k_minus_one_mers(k, tuple(pair))
+        assert [list(t) for t in got] == want
+    for a, b, want in GOLDEN["overlap"]:
+        assert dg.PairedDeBruijnGraph._find_longest_overlap_brute(a, b) == want
