@@ -38,7 +38,12 @@ WORKLOADS = {
 }
 SEED = 2026
 # algorithmic bytes per (k-1)-mer occurrence, 64-bit keys (SURVEY 8d / DESIGN.md)
-B_COUNT, B_BUILD, B_TOTAL = 16.35, 22.35, 40.0
+B_TOTAL = 40.0
+# per kernel: packed bases (0.35) + what the kernel itself must touch per occurrence
+B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
+            "prefilter": 1.35,     # sketch cell read-modify-write (4-bit cell, counted as 1 B)
+            "count": 16.85,        # cell read 0.5 + key probe 8 + count RMW 8
+            "build": 22.35}        # key probe 8 + id/epoch word 4 + edge + node stamp RMW 10
 
 
 def hbm_peak():
@@ -201,7 +206,7 @@ def run_gpu_arm(args):
     barrier()
     launches0 = L.ga_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    timers = {"count": [], "build": []}
+    timers = {}
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     result = None
@@ -224,7 +229,7 @@ def run_gpu_arm(args):
                  for name, pairs in timers.items()}
     dominant = max(kernel_ms, key=kernel_ms.get)
     occ_local = workload_occ(n_local, read_len, paired, k)
-    alg_bytes = occ_local * (B_COUNT if dominant == "count" else B_BUILD)
+    alg_bytes = occ_local * B_KERNEL.get(dominant, B_TOTAL)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (kernel_ms[dominant] * 1e-3) / 1e9 if kernel_ms[dominant] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

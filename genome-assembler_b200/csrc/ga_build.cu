@@ -40,6 +40,80 @@ build_unpaired_kernel(ReadsView rv, int w, const Slot<K>* __restrict__ solid, u6
     if (full) atomicOr(status, GA_ST_STAMP_FULL);
 }
 
+// ---- unpaired, alphabets of at most 4 symbols (DNA): no edge table ---------------------------
+// aux word of an id-table slot: five 6-bit fields, each the earliest read epoch (0..61, 63 = none)
+// that has already folded in the corresponding stamp: field 0 the node stamp, field 1+s the stamp of
+// the edge leaving through symbol s.  Epochs partition reads by index, so a stamp offered from a
+// later epoch is larger than the one the recorded epoch folded in (or will fold in before the kernel
+// ends): the later occurrence can stop at the slot.  That is the common case (coverage >> 1) and it
+// keeps the per-occurrence working set to the id table, which fits the L2.
+#define GA_EPOCH_NONE 63u
+#define GA_EPOCHS 62u
+__device__ __forceinline__ u32 epoch_field(u32 aux, u32 f) { return (aux >> (6u * f)) & 63u; }
+
+// Lower the selected fields of *p to `epoch` (true minimum under concurrency: CAS loop).
+__device__ __forceinline__ u32 epoch_lower(u32* p, u32 seen, u32 fields, u32 epoch) {
+    u32 old = seen;
+    for (;;) {
+        u32 neu = old;
+        for (u32 f = 0; f < 5u; ++f)
+            if (((fields >> f) & 1u) && epoch_field(neu, f) > epoch)
+                neu = (neu & ~(63u << (6u * f))) | (epoch << (6u * f));
+        if (neu == old) return old;
+        u32 prev = atomicCAS(p, old, neu);
+        if (prev == old) return neu;
+        old = prev;
+    }
+}
+
+template <class K> __device__ __forceinline__ u32* slot_aux(Slot<K>* s) { return &s->aux; }
+
+template <class K, int SB>
+__global__ void __launch_bounds__(256)
+build_unpaired_dna_kernel(ReadsView rv, int w, Slot<K>* solid, u64 solid_cap, u64* __restrict__ node_stamp,
+                          u64* __restrict__ edge_stamp, u64 reads_per_epoch) {
+    const K mask = ga_key_mask<K>(w, rv.sym_bits);
+    const u32 smask = (1u << rv.sym_bits) - 1u;
+    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
+         r += (u64)gridDim.x * blockDim.x) {
+        u32 len = ga_read_len(rv, r);
+        if (len <= (u32)w) continue;
+        const u64 e0 = (rv.first_read + r) * (u64)rv.estride;
+        u64 ep64 = r / reads_per_epoch;
+        const u32 epoch = ep64 < GA_EPOCHS ? (u32)ep64 : GA_EPOCHS - 1u;
+        u64 prev_slot = GA_NONE64;
+        u32 prev_id = 0, prev_aux = 0;
+        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
+            u32 id, aux;
+            u64 slot = ga_table_find_slot(solid, solid_cap, key, id, aux);
+            if (pos > 0 && prev_slot != GA_NONE64 && slot != GA_NONE64) {
+                const u64 e = e0 + (pos - 1);
+                const u32 sym = (u32)key & smask;
+                u32 want = 0;
+                if (epoch_field(prev_aux, 0) >= epoch) {
+                    atomicMin(node_stamp + prev_id, 2 * e);
+                    want |= 1u;
+                }
+                if (epoch_field(prev_aux, 1u + sym) >= epoch) {
+                    atomicMin(edge_stamp + 4ull * prev_id + sym, e);
+                    want |= 2u << sym;
+                }
+                if (want) {
+                    u32 neu = epoch_lower(slot_aux(solid + prev_slot), prev_aux, want, epoch);
+                    if (slot == prev_slot) aux = neu;   // homopolymer: prefix and suffix share a slot
+                }
+                if (epoch_field(aux, 0) >= epoch) {
+                    atomicMin(node_stamp + id, 2 * e + 1);
+                    aux = epoch_lower(slot_aux(solid + slot), aux, 1u, epoch);
+                }
+            }
+            prev_slot = slot;
+            prev_id = id;
+            prev_aux = aux;
+        });
+    }
+}
+
 // Keep the two smallest values ever offered (all values distinct): m[0] <= m[1].
 __device__ __forceinline__ void two_min(u64* m, u64 v) {
     u64 old = atomicMin(m, v);
@@ -136,6 +210,38 @@ extern "C" int ga_build_unpaired(const ga_reads* reads, int k, const void* solid
     else GA_BUILD(u128, 8);
 #undef GA_BUILD
     GA_LAUNCH_CHECK("build_unpaired");
+    return GA_OK;
+}
+
+extern "C" int ga_build_unpaired_dna(const ga_reads* reads, int k, void* solid_dev, uint64_t solid_capacity,
+                                     uint64_t* node_stamp_dev, uint64_t* edge_stamp_dev, uint32_t* status_dev,
+                                     ga_stream stream) {
+    (void)status_dev;
+    if (!reads || !solid_dev || !node_stamp_dev || !edge_stamp_dev || solid_capacity == 0) {
+        ga_set_error("ga_build_unpaired_dna: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    int kw = ga_key_words(k, reads->sym_bits);
+    if (!kw || reads->paired || reads->sym_bits > 2) {
+        ga_set_error("ga_build_unpaired_dna: needs unpaired reads over at most 4 symbols");
+        return GA_ERR_BAD_ARG;
+    }
+    if (reads->n_reads == 0) return GA_OK;
+    ReadsView rv = ga_view(reads);
+    u64 reads_per_epoch = (rv.n_reads + GA_EPOCHS - 1) / GA_EPOCHS;
+    if (reads_per_epoch == 0) reads_per_epoch = 1;
+    unsigned grid = ga_grid(rv.n_reads, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GA_BUILD(K, SB)                                                                                  \
+    build_unpaired_dna_kernel<K, SB><<<grid, 256, 0, st>>>(rv, k - 1, (Slot<K>*)solid_dev, solid_capacity, \
+                                                          (u64*)node_stamp_dev, (u64*)edge_stamp_dev,     \
+                                                          reads_per_epoch)
+    if (kw == 1 && rv.storage_bits == 2) GA_BUILD(u64, 2);
+    else if (kw == 1) GA_BUILD(u64, 8);
+    else if (rv.storage_bits == 2) GA_BUILD(u128, 2);
+    else GA_BUILD(u128, 8);
+#undef GA_BUILD
+    GA_LAUNCH_CHECK("build_unpaired_dna");
     return GA_OK;
 }
 

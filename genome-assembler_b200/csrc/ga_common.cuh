@@ -138,6 +138,34 @@ __device__ __forceinline__ void ga_load_slot_ro(const Slot<u128>* s, u128& key, 
     key = ((u128)(((u64)a.w << 32) | a.z) << 64) | (((u64)a.y << 32) | a.x);
     val = b.x;
 }
+// Coherent (L2) whole-slot load for tables whose aux word is still being updated.
+__device__ __forceinline__ void ga_load_slot_cg(const Slot<u64>* s, u64& key, u32& val, u32& aux) {
+    uint4 v = __ldcg(reinterpret_cast<const uint4*>(s));
+    key = ((u64)v.y << 32) | v.x;
+    val = v.z;
+    aux = v.w;
+}
+__device__ __forceinline__ void ga_load_slot_cg(const Slot<u128>* s, u128& key, u32& val, u32& aux) {
+    const uint4* p = reinterpret_cast<const uint4*>(s);
+    uint4 a = __ldcg(p), b = __ldcg(p + 1);
+    key = ((u128)(((u64)a.w << 32) | a.z) << 64) | (((u64)a.y << 32) | a.x);
+    val = b.x;
+    aux = b.y;
+}
+// Slot index of `key` (GA_NONE64 when absent) with its val / aux words.
+template <class K>
+__device__ __forceinline__ u64 ga_table_find_slot(const Slot<K>* table, u64 capacity, K key, u32& val, u32& aux) {
+    u64 s = ga_slot_of(ga_key_hash(key), capacity);
+    for (u64 probes = 0; probes < capacity; ++probes) {
+        K cur;
+        ga_load_slot_cg(table + s, cur, val, aux);
+        if (cur == key) return s;
+        if (cur == ga_empty_key<K>()) return GA_NONE64;
+        if (++s == capacity) s = 0;
+    }
+    return GA_NONE64;
+}
+
 template <class K>
 __device__ __forceinline__ u32 ga_table_find(const Slot<K>* __restrict__ table, u64 capacity, K key) {
     u64 s = ga_slot_of(ga_key_hash(key), capacity);
@@ -330,6 +358,59 @@ __device__ __forceinline__ u32 ga_sketch_estimate(const SketchView& sk, u32 h) {
         est = c < est ? c : est;
     }
     return est;
+}
+
+// Block-aggregated append for blocks of up to 1024 threads: every thread of the block must call
+// it (uniform control flow); returns the first output index reserved for this thread's `n` items.
+__device__ __forceinline__ u64 ga_block_append(u64* counter, u32 n) {
+    __shared__ u32 warp_sum[32];
+    __shared__ u64 block_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    u32 incl = n;
+    for (int off = 1; off < 32; off <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 v = lane < nw ? warp_sum[lane] : 0u, inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane < nw) warp_sum[lane] = inc - v;           // exclusive prefix per warp
+        u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (lane == 0) block_base = total ? atomicAdd(counter, (u64)total) : 0ull;
+    }
+    __syncthreads();
+    u64 pos = block_base + warp_sum[wid] + (incl - n);
+    __syncthreads();                                       // shared scratch is reused by the next call
+    return pos;
+}
+
+// Pre-filter sketch (ga_prefilter.cu): one row of small saturating counters, packed in 32-bit words.
+struct PrefilterView {
+    u32* words;
+    u64 n_cells;
+    u32 lg_per;     // log2(cells per word): 3 for 4-bit cells, 2 for 8-bit cells
+    u32 cell_bits;  // 4 or 8
+    u32 limit;      // threshold + 1: a cell that reached it marks its k-mers as candidates
+};
+static inline PrefilterView ga_prefilter_view(const ga_prefilter* p, long long threshold) {
+    PrefilterView v;
+    v.words = (u32*)p->words;
+    v.n_cells = p->n_cells;
+    v.cell_bits = (u32)p->cell_bits;
+    v.lg_per = p->cell_bits == 4 ? 3u : 2u;
+    v.limit = (u32)(threshold < 0 ? 0 : threshold + 1);
+    return v;
+}
+__device__ __forceinline__ u32 ga_prefilter_value(const PrefilterView& pf, u64 hash, u64& word_index, u32& shift) {
+    u64 cell = ga_slot_of(hash, pf.n_cells);
+    word_index = cell >> pf.lg_per;
+    shift = (u32)(cell & ((1u << pf.lg_per) - 1u)) * pf.cell_bits;
+    return (__ldcg(pf.words + word_index) >> shift) & ((1u << pf.cell_bits) - 1u);
 }
 
 // warp-aggregated append: returns this thread's output index (valid only if `take`)

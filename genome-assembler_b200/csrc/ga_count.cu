@@ -113,25 +113,35 @@ __global__ void export_kernel(const Slot<K>* __restrict__ table, u64 capacity, l
         for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
         __syncthreads();
     }
-    u64 rounds = (capacity + (u64)gridDim.x * blockDim.x - 1) / ((u64)gridDim.x * blockDim.x);
-    for (u64 it = 0; it < rounds; ++it) {  // uniform trip count: every lane reaches the ballot
-        u64 i = it * (u64)gridDim.x * blockDim.x + blockIdx.x * (u64)blockDim.x + threadIdx.x;
-        bool take = false;
-        K key = 0;
-        u32 c = 0;
-        if (i < capacity) {
-            key = slot_key<K>(table + i);
-            if (key != ga_empty_key<K>()) {
-                c = table[i].val;
-                long long score = c;
-                if (sk.rows > 0) score = ga_sketch_estimate(sk, ga_murmur_key<K>(key, w, sym_bits, lut));
-                take = score > min_exclusive;
+    // tiles of 4 slots per thread; one append-counter atomic per tile (every thread of the block
+    // takes part in the block scan, so the trip count is uniform)
+    constexpr u32 ITEMS = 4;
+    const u64 tile = (u64)blockDim.x * ITEMS;
+    const u64 n_tiles = (capacity + tile - 1) / tile;
+    const u64 rounds = (n_tiles + gridDim.x - 1) / gridDim.x;
+    for (u64 it = 0; it < rounds; ++it) {
+        const u64 t = it * gridDim.x + blockIdx.x;
+        K keys[ITEMS];
+        u32 cnts[ITEMS];
+        u32 n = 0;
+        for (u32 j = 0; j < ITEMS; ++j) {
+            u64 i = t * tile + (u64)j * blockDim.x + threadIdx.x;
+            if (t >= n_tiles || i >= capacity) continue;
+            K key = slot_key<K>(table + i);
+            if (key == ga_empty_key<K>()) continue;
+            u32 c = table[i].val;
+            long long score = c;
+            if (sk.rows > 0) score = ga_sketch_estimate(sk, ga_murmur_key<K>(key, w, sym_bits, lut));
+            if (score > min_exclusive) {
+                keys[n] = key;
+                cnts[n] = c;
+                ++n;
             }
         }
-        u64 pos = ga_warp_append(n_out, take);
-        if (take) {
-            if (keys_out) keys_out[pos] = key;
-            if (counts_out) counts_out[pos] = c;
+        u64 pos = ga_block_append(n_out, n);
+        for (u32 j = 0; j < n; ++j) {
+            if (keys_out) keys_out[pos + j] = keys[j];
+            if (counts_out) counts_out[pos + j] = cnts[j];
         }
     }
 }

@@ -19,6 +19,11 @@ struct ga_csr_plan {
     u64 ecap = 0;
     u32* rank = nullptr;          // unpaired: solid id -> node index (edge keys hold solid ids)
     int* extra_in = nullptr;      // paired: in-edges held by orphaned prefix nodes
+    // "dna4" mode (unpaired, <= 4 symbols): edges live in edge_stamp4[4 * solid id + symbol]
+    const u64* edge_stamp4 = nullptr;
+    const void* solid = nullptr;  // id table, to turn a successor key into its id
+    u64 solid_cap = 0;
+    int w = 0;
     cudaStream_t stream = nullptr;
     std::vector<void*> owned;
 };
@@ -136,6 +141,69 @@ __global__ void finish_nodes_kernel(long long n_nodes, const int* __restrict__ r
         last_sym[i] = (u8)((u32)ka & smask);
         if (keys_a) keys_a[i] = ka;
         if (keys_b && node_b) keys_b[i] = solid_keys[node_b[i]];
+    }
+}
+
+// ---- dna4 mode: rows straight from the per-node edge stamps ------------------------------------
+__global__ void count_stamps_kernel(const u64* __restrict__ stamps, u64 n, u64* counter) {
+    u64 c = 0;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        c += stamps[i] != GA_NONE64;
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, c);
+}
+
+__global__ void dna4_outdeg_kernel(const u64* __restrict__ edge_stamp4, const u32* __restrict__ node_a,
+                                   u64 n_nodes, int* __restrict__ outdeg) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_nodes; i += (u64)gridDim.x * blockDim.x) {
+        const u64* st = edge_stamp4 + 4ull * node_a[i];
+        outdeg[i] = (st[0] != GA_NONE64) + (st[1] != GA_NONE64) + (st[2] != GA_NONE64) + (st[3] != GA_NONE64);
+    }
+}
+
+template <class K>
+__global__ void dna4_rows_kernel(const u64* __restrict__ edge_stamp4, const u32* __restrict__ node_a,
+                                 u64 n_nodes, const K* __restrict__ solid_keys, const Slot<K>* __restrict__ solid,
+                                 u64 solid_cap, const u32* __restrict__ rank, int w, int sym_bits,
+                                 const int* __restrict__ rowptr, int* __restrict__ col, int* __restrict__ indeg) {
+    const K mask = ga_key_mask<K>(w, sym_bits);
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_nodes; i += (u64)gridDim.x * blockDim.x) {
+        const u32 id = node_a[i];
+        const K key = solid_keys[id];
+        u64 st[4];
+        u32 sy[4];
+        int n = 0;
+        for (u32 s = 0; s < 4u; ++s) {
+            u64 v = edge_stamp4[4ull * id + s];
+            if (v == GA_NONE64) continue;
+            int j = n++;
+            while (j > 0 && st[j - 1] > v) {   // insertion sort by first occurrence
+                st[j] = st[j - 1];
+                sy[j] = sy[j - 1];
+                --j;
+            }
+            st[j] = v;
+            sy[j] = s;
+        }
+        int base = rowptr[i];
+        for (int j = 0; j < n; ++j) {
+            K succ = ((key << sym_bits) | (K)sy[j]) & mask;
+            u32 succ_rank = rank[ga_table_find(solid, solid_cap, succ)];
+            col[base + j] = (int)succ_rank;
+            atomicAdd(indeg + succ_rank, 1);
+        }
+    }
+}
+
+template <class K>
+__global__ void dna4_finish_kernel(u64 n_nodes, const int* __restrict__ rowptr, const int* __restrict__ indeg,
+                                   const K* __restrict__ solid_keys, const u32* __restrict__ node_a, u32 smask,
+                                   u8* __restrict__ branching, u8* __restrict__ last_sym, K* __restrict__ keys_a) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n_nodes; i += (u64)gridDim.x * blockDim.x) {
+        branching[i] = (u8)((rowptr[i + 1] - rowptr[i] > 1) || indeg[i] > 1);
+        K ka = solid_keys[node_a[i]];
+        last_sym[i] = (u8)((u32)ka & smask);
+        if (keys_a) keys_a[i] = ka;
     }
 }
 
@@ -503,6 +571,59 @@ extern "C" int ga_csr_plan_unpaired(const uint64_t* node_stamp_dev, uint64_t n_s
     return GA_OK;
 }
 
+extern "C" int ga_csr_plan_unpaired_dna(const uint64_t* node_stamp_dev, const uint64_t* edge_stamp_dev,
+                                        uint64_t n_solid, const void* solid_keys_dev, int key_words, int k,
+                                        int sym_bits, const void* solid_dev, uint64_t solid_capacity,
+                                        ga_stream stream, ga_csr_plan** plan_out, int64_t* n_nodes,
+                                        int64_t* n_edges) {
+    if (!plan_out || !n_nodes || !n_edges || !solid_dev || solid_capacity == 0 || sym_bits > 2 ||
+        (key_words != 1 && key_words != 2) || (n_solid && (!node_stamp_dev || !edge_stamp_dev || !solid_keys_dev))) {
+        ga_set_error("ga_csr_plan_unpaired_dna: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    ga_csr_plan* plan = new ga_csr_plan();
+    plan->key_words = key_words;
+    plan->sym_bits = sym_bits;
+    plan->solid_keys = solid_keys_dev;
+    plan->stream = (cudaStream_t)stream;
+    plan->edge_stamp4 = (const u64*)edge_stamp_dev;
+    plan->solid = solid_dev;
+    plan->solid_cap = solid_capacity;
+    plan->w = k - 1;
+    Scratch sc{plan->stream, &plan->owned};
+    cudaStream_t st = plan->stream;
+    u64* counters = sc.get<u64>(2);
+    u64* stamps0 = sc.get<u64>(n_solid);
+    u32* ids0 = sc.get<u32>(n_solid);
+    GA_NEED(counters); GA_NEED(stamps0); GA_NEED(ids0);
+    GA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(u64), st));
+    if (n_solid) {
+        compact_nodes_kernel<<<scan_grid(n_solid), 256, 0, st>>>((const u64*)node_stamp_dev, n_solid, stamps0, ids0, counters);
+        count_stamps_kernel<<<scan_grid(4 * n_solid), 256, 0, st>>>((const u64*)edge_stamp_dev, 4 * n_solid, counters + 1);
+        ga_note_launches(2);
+    }
+    GA_TRY(cudaGetLastError());
+    u64 host[2];
+    GA_TRY(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
+    GA_TRY(cudaStreamSynchronize(st));
+    const u64 nn = host[0];
+    u64* stamps1 = sc.get<u64>(nn);
+    plan->node_a = sc.get<u32>(nn, true);
+    plan->rank = sc.get<u32>(n_solid, true);
+    GA_NEED(stamps1); GA_NEED(plan->node_a); GA_NEED(plan->rank);
+    GA_TRY((sort_pairs<u64, u32>(sc, stamps0, stamps1, ids0, plan->node_a, nn)));
+    if (nn) scatter_rank_kernel<<<scan_grid(nn), 256, 0, st>>>(plan->node_a, nn, plan->rank);
+    ga_note_launches(1);
+    GA_TRY(cudaGetLastError());
+    plan->n_nodes = (long long)nn;
+    plan->n_edges = (long long)host[1];
+    *n_nodes = plan->n_nodes;
+    *n_edges = plan->n_edges;
+    *plan_out = plan;
+    sc.release();
+    return GA_OK;
+}
+
 extern "C" int ga_csr_plan_paired(const void* solid_dev, uint64_t solid_capacity, const void* solid_keys_dev,
                                   uint64_t n_solid, int key_words, int k, int sym_bits,
                                   const void* query_table_dev, uint64_t query_capacity,
@@ -563,6 +684,32 @@ extern "C" int ga_csr_emit(ga_csr_plan* plan, int32_t* rowptr_dev, int32_t* col_
             return ga_cuda_fail(_e, #expr);         \
         }                                           \
     } while (0)
+    if (plan->edge_stamp4) {
+        GA_TRY2(cudaMemsetAsync(outdeg, 0, (nn + 1) * sizeof(int), st));
+        if (nn) GA_TRY2(cudaMemsetAsync(indeg_dev, 0, nn * sizeof(int), st));
+        if (nn) dna4_outdeg_kernel<<<scan_grid(nn), 256, 0, st>>>(plan->edge_stamp4, plan->node_a, nn, outdeg);
+        GA_TRY2(exclusive_sum(sc, outdeg, rowptr_dev, nn + 1));
+        if (nn) {
+            u32 smask = (1u << plan->sym_bits) - 1u;
+            if (plan->key_words == 1) {
+                dna4_rows_kernel<u64><<<scan_grid(nn), 256, 0, st>>>(plan->edge_stamp4, plan->node_a, nn,
+                    (const u64*)plan->solid_keys, (const Slot<u64>*)plan->solid, plan->solid_cap, plan->rank, plan->w,
+                    plan->sym_bits, rowptr_dev, col_dev, indeg_dev);
+                dna4_finish_kernel<u64><<<scan_grid(nn), 256, 0, st>>>(nn, rowptr_dev, indeg_dev, (const u64*)plan->solid_keys,
+                    plan->node_a, smask, branching_dev, last_sym_dev, (u64*)node_keys_a_dev);
+            } else {
+                dna4_rows_kernel<u128><<<scan_grid(nn), 256, 0, st>>>(plan->edge_stamp4, plan->node_a, nn,
+                    (const u128*)plan->solid_keys, (const Slot<u128>*)plan->solid, plan->solid_cap, plan->rank, plan->w,
+                    plan->sym_bits, rowptr_dev, col_dev, indeg_dev);
+                dna4_finish_kernel<u128><<<scan_grid(nn), 256, 0, st>>>(nn, rowptr_dev, indeg_dev, (const u128*)plan->solid_keys,
+                    plan->node_a, smask, branching_dev, last_sym_dev, (u128*)node_keys_a_dev);
+            }
+            ga_note_launches(3);
+        }
+        GA_TRY2(cudaGetLastError());
+        sc.release();
+        return GA_OK;
+    }
     GA_TRY2(cudaMemsetAsync(outdeg, 0, (nn + 1) * sizeof(int), st));
     if (plan->extra_in && nn)
         GA_TRY2(cudaMemcpyAsync(indeg_dev, plan->extra_in, nn * sizeof(int), cudaMemcpyDeviceToDevice, st));

@@ -34,7 +34,7 @@ def _timed(name):
         def __exit__(self, *exc):
             if self.on:
                 self.b.record()
-                TIMERS[name].append((self.a, self.b))
+                TIMERS.setdefault(name, []).append((self.a, self.b))
     return _Span()
 
 
@@ -270,8 +270,15 @@ def _check_status(status: torch.Tensor) -> int:
 
 # ----------------------------------------------------------------------------------- counting
 class KmerCounts:
-    """Exact (k-1)-mer counts in a device hash table, quacking like the dict the reference's
-    ``_count_kmers`` returns (``[]``, ``items()``, truthiness, ``len``)."""
+    """Exact (k-1)-mer counts on the device, quacking like the dict the reference's
+    ``_count_kmers`` returns (``[]``, ``items()``, truthiness, ``len``).
+
+    Two device representations, both exact:
+      * the full table (every distinct window), filled on first use by anything that needs all
+        counts: ``items()``, ``len()``, ``[]``, a CountMinSketch pour;
+      * the candidate table of ``candidates(threshold)``: only windows whose pre-filter cell says
+        they may exceed the threshold -- all the graph build needs, at a fraction of the traffic.
+    """
 
     def __init__(self, k: int, reads: DeviceReads):
         self.k, self.w = k, k - 1
@@ -280,10 +287,16 @@ class KmerCounts:
         self.key_words = reads.key_words(k)
         self.slot_bytes = gn.lib().ga_slot_bytes(self.key_words)
         self.n_occ = reads.windows_total(k)
-        self.table = None
+        self._table = None
         self.capacity = 0
         self._summary = {}
-        self._count()
+        self._cand = {}
+
+    @property
+    def table(self):
+        if self._table is None:
+            self._count()
+        return self._table
 
     def _count(self):
         L = gn.lib()
@@ -292,12 +305,12 @@ class KmerCounts:
         limit = max(1024, int(free * 0.6) // self.slot_bytes)
         cap = min(max(1024, int(self.n_occ * 1.25) + 64), limit)
         while True:
-            self.table = torch.empty(cap * self.slot_bytes, dtype=torch.uint8, device=dev)
+            self._table = torch.empty(cap * self.slot_bytes, dtype=torch.uint8, device=dev)
             self.capacity = cap
             self.reads.status.zero_()
-            gn.check(L.ga_table_clear(gn.ptr(self.table), cap, self.key_words, _stream()))
+            gn.check(L.ga_table_clear(gn.ptr(self._table), cap, self.key_words, _stream()))
             with _timed("count"):
-                gn.check(L.ga_count_kmers(C.byref(self.reads.struct()), self.k, gn.ptr(self.table), cap,
+                gn.check(L.ga_count_kmers(C.byref(self.reads.struct()), self.k, gn.ptr(self._table), cap,
                                           gn.ptr(self.reads.status), _stream()))
             st = _check_status(self.reads.status)
             if st & gn.ST_BAD_SYMBOL:
@@ -306,8 +319,53 @@ class KmerCounts:
                 return
             if cap >= limit:
                 raise MemoryError("k-mer count table does not fit in device memory")
-            self.table = None
+            self._table = None
             cap = min(cap * 2, limit)
+
+    def candidates(self, threshold: int):
+        """(table, capacity) holding the exact count of every window that may exceed `threshold`
+        (pre-filter sketch -> candidate table, ga_prefilter.cu), or None when the threshold is
+        outside what the sketch cells can represent."""
+        if threshold in self._cand:
+            return self._cand[threshold]
+        if threshold < 0 or threshold + 1 > 255:
+            return None
+        L = gn.lib()
+        dev = _dev()
+        bits = 4 if threshold + 1 <= 15 else 8
+        free, _ = torch.cuda.mem_get_info()
+        n_cells = max(1 << 16, min(self.n_occ, int(free * 0.25) * 8 // bits))
+        words = torch.zeros((n_cells * bits + 31) // 32, dtype=torch.int32, device=dev)
+        pf = gn.GaPrefilter()
+        pf.words, pf.n_cells, pf.cell_bits = gn.ptr(words), n_cells, bits
+        status = self.reads.status
+        with _timed("prefilter"):
+            gn.check(L.ga_prefilter_update(C.byref(self.reads.struct()), self.k, C.byref(pf), threshold, _stream()))
+        n_hot = torch.zeros(1, dtype=torch.int64, device=dev)
+        gn.check(L.ga_prefilter_hot(C.byref(pf), threshold, gn.ptr(n_hot), _stream()))
+        hot = int(n_hot.item())
+        limit = max(1024, int(free * 0.5) // self.slot_bytes)
+        cap = min(limit, max(1024, int(hot * 2.2) + 1024))
+        while True:
+            table = torch.empty(cap * self.slot_bytes, dtype=torch.uint8, device=dev)
+            status.zero_()
+            gn.check(L.ga_table_clear(gn.ptr(table), cap, self.key_words, _stream()))
+            with _timed("count"):
+                gn.check(L.ga_count_candidates(C.byref(self.reads.struct()), self.k, C.byref(pf), threshold,
+                                               gn.ptr(table), cap, gn.ptr(status), _stream()))
+            out = torch.zeros(4, dtype=torch.int64, device=dev)
+            gn.check(L.ga_table_summary(gn.ptr(table), cap, self.key_words, int(threshold), gn.ptr(out), _stream()))
+            st = _check_status(status)
+            if st & gn.ST_BAD_SYMBOL:
+                raise ValueError("read symbol outside the detected alphabet")
+            if not st & gn.ST_TABLE_FULL:
+                break
+            if cap >= limit:
+                raise MemoryError("candidate table does not fit in device memory")
+            cap = min(cap * 2, limit)
+        summary = tuple(int(v) for v in out.cpu().tolist())
+        self._cand[threshold] = (table, cap, summary)
+        return self._cand[threshold]
 
     def summary(self, threshold: int):
         """(distinct, above threshold, occurrences, max count)."""
@@ -434,13 +492,23 @@ def _solid_keys(counts: KmerCounts, threshold: int, sketch=None):
     """Device array of the keys that pass the filter, and their number."""
     L = gn.lib()
     dev = _dev()
-    n_max = counts.summary(threshold)[1] if sketch is None else counts.summary(0)[0]
+    cand = None
+    if sketch is None and counts._table is None:
+        cand = counts.candidates(threshold)
+    if cand is not None:
+        table, capacity, summary = cand
+        n_max = summary[1]
+    else:
+        table, capacity = counts.table, counts.capacity
+        n_max = counts.summary(threshold)[1] if sketch is None else counts.summary(0)[0]
     keys = torch.empty((max(n_max, 1), counts.key_words), dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int64, device=dev)
     sk = C.byref(sketch) if sketch is not None else None
-    gn.check(L.ga_select_solid(gn.ptr(counts.table), counts.capacity, counts.key_words, counts.k,
+    gn.check(L.ga_select_solid(gn.ptr(table), capacity, counts.key_words, counts.k,
                                counts.alphabet.sym_bits, int(threshold), sk, gn.ptr(counts.alphabet.inv_dev),
                                gn.ptr(keys), None, gn.ptr(n_out), _stream()))
+    if sketch is None:
+        return keys, n_max           # exact filter: the summary already counted them (no sync)
     return keys, int(n_out.item())
 
 
@@ -469,7 +537,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
     if n_solid == 0 or reads.n_reads == 0:
         return graph
-    solid_cap = 2 * n_solid + 64
+    solid_cap = int(1.7 * n_solid) + 64
     solid = torch.empty(solid_cap * counts.slot_bytes, dtype=torch.uint8, device=dev)
     status = reads.status
     status.zero_()
@@ -478,10 +546,24 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
                                    gn.ptr(status), _stream()))
     n_nodes, n_edges, attr = C.c_int64(), C.c_int64(), C.c_int64()
     plan = C.c_void_p()
+    dna4 = (not reads.paired) and alphabet.sym_bits <= 2
+    if dna4:
+        # <= 4 symbols: per-node edge stamps, epoch-tagged slots (ga_build_unpaired_dna)
+        node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
+        edge_stamp = torch.full((4 * n_solid,), -1, dtype=torch.int64, device=dev)
+        with _timed("build"):
+            gn.check(L.ga_build_unpaired_dna(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap,
+                                             gn.ptr(node_stamp), gn.ptr(edge_stamp), gn.ptr(status), _stream()))
+        gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
+                                            kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),
+                                            C.byref(plan), C.byref(n_nodes), C.byref(n_edges)))
+        attr.value = n_edges.value
+        if _check_status(status) & gn.ST_TABLE_FULL:
+            raise gn.GaError("id table overflow")
     free, _ = torch.cuda.mem_get_info()
     cap_limit = min(0xFFFFFFF0, max(4096, int(free * 0.4) // 32))
     cap = min(cap_limit, max(1024, 3 * n_solid))
-    while True:
+    while not dna4:
         status.zero_()
         if not reads.paired:
             node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
@@ -502,7 +584,9 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         if cap >= cap_limit:
             raise MemoryError("edge tables do not fit in device memory")
         cap = min(cap * 2, cap_limit)
-    if not reads.paired:
+    if dna4:
+        pass
+    elif not reads.paired:
         gn.check(L.ga_csr_plan_unpaired(gn.ptr(node_stamp), n_solid, gn.ptr(solid_keys), kw, alphabet.sym_bits,
                                         gn.ptr(edges), cap, _stream(), C.byref(plan), C.byref(n_nodes),
                                         C.byref(n_edges)))

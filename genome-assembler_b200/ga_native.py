@@ -32,12 +32,16 @@ class GaReads(C.Structure):
                 ("estride", C.c_uint32)]
 
 
+class GaPrefilter(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("n_cells", C.c_uint64), ("cell_bits", C.c_int32)]
+
+
 class GaSketch(C.Structure):
     _fields_ = [("cells", C.c_void_p), ("width", C.c_uint32 * MAX_SKETCH_ROWS), ("rows", C.c_int32)]
 
 
 _vp, _u64, _u32, _i64, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int
-_PR, _PS = C.POINTER(GaReads), C.POINTER(GaSketch)
+_PR, _PS, _PF = C.POINTER(GaReads), C.POINTER(GaSketch), C.POINTER(GaPrefilter)
 
 # name -> (restype, argtypes); mirrors include/ga_b200.h one to one
 SIGNATURES = {
@@ -58,15 +62,21 @@ SIGNATURES = {
     "ga_table_export": (_i32, [_vp, _u64, _i32, _i64, _vp, _vp, _vp, _vp]),
     "ga_table_lookup": (_i32, [_vp, _u64, _i32, _vp, _u64, _vp, _vp]),
     "ga_table_insert_ids": (_i32, [_vp, _u64, _i32, _u32, _vp, _u64, _vp, _vp]),
+    "ga_prefilter_update": (_i32, [_PR, _i32, _PF, _i64, _vp]),
+    "ga_prefilter_hot": (_i32, [_PF, _i64, _vp, _vp]),
+    "ga_count_candidates": (_i32, [_PR, _i32, _PF, _i64, _vp, _u64, _vp, _vp]),
     "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
     "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
     "ga_sketch_estimate_bytes": (_i32, [_vp, _vp, _u64, _PS, _vp, _vp]),
     "ga_sketch_narrow": (_i32, [_PS, _vp, _vp, _vp]),
     "ga_select_solid": (_i32, [_vp, _u64, _i32, _i32, _i32, _i64, _PS, _vp, _vp, _vp, _vp, _vp]),
     "ga_build_unpaired": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
+    "ga_build_unpaired_dna": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp, _vp, _vp]),
     "ga_build_paired": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "ga_csr_plan_unpaired": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _u64, _vp,
                                     C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ga_csr_plan_unpaired_dna": (_i32, [_vp, _vp, _u64, _vp, _i32, _i32, _i32, _vp, _u64, _vp,
+                                        C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "ga_csr_plan_paired": (_i32, [_vp, _u64, _vp, _u64, _i32, _i32, _i32, _vp, _u64, _vp, _u64, _vp, _vp,
                                   C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "ga_csr_emit": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

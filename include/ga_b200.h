@@ -74,6 +74,16 @@ typedef struct ga_sketch {
     int32_t rows;
 } ga_sketch;
 
+/* Pre-filter sketch: one row of n_cells saturating counters of cell_bits (4 or 8) bits packed in
+ * 32-bit words (zero-filled by the caller).  Internal to the exact path: a cell only ever
+ * over-estimates the occurrences hashed to it, so "cell > threshold" selects a superset of the
+ * windows whose exact count is > threshold; the superset is then counted exactly. */
+typedef struct ga_prefilter {
+    void* words;             /* device, uint32_t[ceil(n_cells * cell_bits / 32)] */
+    uint64_t n_cells;
+    int32_t cell_bits;       /* 4 (threshold <= 14) or 8 (threshold <= 254) */
+} ga_prefilter;
+
 /* ---- housekeeping ------------------------------------------------------------------------- */
 int ga_version(void);
 const char* ga_last_error(void);
@@ -130,6 +140,17 @@ int ga_table_lookup(const void* table_dev, uint64_t capacity, int key_words, con
 int ga_table_insert_ids(const void* keys_dev, uint64_t n, int key_words, uint32_t id_base,
                         void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
 
+/* Two-pass exact counting of the windows that can pass the filter (same results as
+ * ga_count_kmers + "count > threshold", without giving every singleton a table slot):
+ * pass A bumps one pre-filter cell per window occurrence; ga_prefilter_hot counts the cells that
+ * reached threshold+1 (sizes the candidate table); pass B counts exactly, in `table_dev`, the
+ * windows whose cell reached threshold+1. */
+int ga_prefilter_update(const ga_reads* reads, int k, const ga_prefilter* pf, int64_t threshold,
+                        ga_stream stream);
+int ga_prefilter_hot(const ga_prefilter* pf, int64_t threshold, uint64_t* n_hot_dev, ga_stream stream);
+int ga_count_candidates(const ga_reads* reads, int k, const ga_prefilter* pf, int64_t threshold,
+                        void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
+
 /* ---- CountMinSketch: replaces countminsketch.py:34-44 and _make_sketch --------------------- */
 /* cells[row][murmur3(window) % width[row]] += count for every key of the count table
  * (debruijn_graph.py:181-188, 398-405).  lut_dev[256]: symbol code -> byte. */
@@ -163,6 +184,13 @@ int ga_select_solid(const void* table_dev, uint64_t capacity, int key_words, int
 int ga_build_unpaired(const ga_reads* reads, int k, const void* solid_dev, uint64_t solid_capacity,
                       uint64_t* node_stamp_dev, void* edge_table_dev, uint64_t edge_capacity,
                       uint32_t* status_dev, ga_stream stream);
+/* Unpaired with at most 4 symbols (DNA): no edge table.  solid_dev is an id table whose aux words
+ * are 0xFFFFFFFF (ga_table_clear); edge_stamp_dev[4*n_solid] (0xFF filled) takes the first
+ * occurrence of edge (node id, next symbol).  The aux word of a slot caches, per stamp, the
+ * earliest read epoch that already folded it in, so repeat occurrences stop at the slot. */
+int ga_build_unpaired_dna(const ga_reads* reads, int k, void* solid_dev, uint64_t solid_capacity,
+                          uint64_t* node_stamp_dev, uint64_t* edge_stamp_dev, uint32_t* status_dev,
+                          ga_stream stream);
 /* Paired.  query table: key = idA << 32 | idB -> min stamp; query-edge table: key =
  * query_slot(P) << 32 | query_slot(S) -> min occurrence; dh_dev: 256*256*2 uint64 (0xFF filled),
  * the two smallest occurrences of "prefix pair == suffix pair" per (symbol A, symbol B)
@@ -184,6 +212,11 @@ int ga_csr_plan_unpaired(const uint64_t* node_stamp_dev, uint64_t n_solid, const
                          int key_words, int sym_bits, const void* edge_table_dev,
                          uint64_t edge_capacity, ga_stream stream, ga_csr_plan** plan_out,
                          int64_t* n_nodes, int64_t* n_edges);
+int ga_csr_plan_unpaired_dna(const uint64_t* node_stamp_dev, const uint64_t* edge_stamp_dev,
+                             uint64_t n_solid, const void* solid_keys_dev, int key_words, int k,
+                             int sym_bits, const void* solid_dev, uint64_t solid_capacity,
+                             ga_stream stream, ga_csr_plan** plan_out, int64_t* n_nodes,
+                             int64_t* n_edges);
 int ga_csr_plan_paired(const void* solid_dev, uint64_t solid_capacity, const void* solid_keys_dev,
                        uint64_t n_solid, int key_words, int k, int sym_bits,
                        const void* query_table_dev, uint64_t query_capacity,
