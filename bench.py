@@ -54,47 +54,69 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML from a thread (cheap
+    per query); spawning `nvidia-smi -lms` next to a 25 ms timed region stalls the driver for
+    longer than the region itself, so it is only the fallback."""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.index, self.rows, self.stop_flag, self.nvml = index, [], threading.Event(), None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def start(self):
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+        return self
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if self.nvml is None:
+            return
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((sm, reasons))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self.stop_flag.set()
+        if self.nvml is None:
+            return self._smi_once()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            cells = [c.strip() for c in row.split(",")]
-            if len(cells) < 6:
-                continue
-            try:
-                sm.append(float(cells[0]))
-                mx = float(cells[1])
-            except ValueError:
-                continue
-            for name, cell in zip(names, cells[2:6]):
-                if cell.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(r[0] for r in self.rows)
+        seen = set()
+        for _, mask in self.rows:
+            seen |= {name for name, bit in bits.items() if mask & bit}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(seen),
+                "samples": len(sm), "source": "nvml, 20 ms period, during the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index),
+                                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            cells = [c.strip() for c in out.strip().split(",")]
+            return {"sm_mhz": float(cells[0]), "sm_max_mhz": float(cells[1]), "reasons": [cells[2]], "samples": 1,
+                    "source": "nvidia-smi once after the timed region (NVML python module missing)"}
+        except Exception as exc:          # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s" % exc], "samples": 0}
 
 
 def workload_occ(n_reads, read_len, paired, k):
@@ -201,11 +223,13 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # NVML initialised outside the timed region
     for _ in range(args.warmup):
         step_fn()
     barrier()
     launches0 = L.ga_launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     timers = {}
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()

@@ -20,13 +20,12 @@ build_unpaired_kernel(ReadsView rv, int w, const Slot<K>* __restrict__ solid, u6
                       u32* status) {
     const K mask = ga_key_mask<K>(w, rv.sym_bits);
     bool full = false;
-    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
-         r += (u64)gridDim.x * blockDim.x) {
-        u32 len = ga_read_len(rv, r);
-        if (len <= (u32)w) continue;  // fewer than two windows: no edge occurrence
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
+        u32 len = valid ? ga_read_len(rv, r) : 0u;
+        if (len <= (u32)w) len = 0;  // fewer than two windows: no edge occurrence
         const u64 e0 = (rv.first_read + r) * (u64)rv.estride;
         u32 prev = GA_NONE32;
-        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
             u32 id = ga_table_find(solid, solid_cap, key);
             if (pos > 0 && prev != GA_NONE32 && id != GA_NONE32) {
                 const u64 e = e0 + (pos - 1);
@@ -74,16 +73,15 @@ build_unpaired_dna_kernel(ReadsView rv, int w, Slot<K>* solid, u64 solid_cap, u6
                           u64* __restrict__ edge_stamp, u64 reads_per_epoch) {
     const K mask = ga_key_mask<K>(w, rv.sym_bits);
     const u32 smask = (1u << rv.sym_bits) - 1u;
-    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
-         r += (u64)gridDim.x * blockDim.x) {
-        u32 len = ga_read_len(rv, r);
-        if (len <= (u32)w) continue;
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
+        u32 len = valid ? ga_read_len(rv, r) : 0u;
+        if (len <= (u32)w) len = 0;
         const u64 e0 = (rv.first_read + r) * (u64)rv.estride;
         u64 ep64 = r / reads_per_epoch;
         const u32 epoch = ep64 < GA_EPOCHS ? (u32)ep64 : GA_EPOCHS - 1u;
         u64 prev_slot = GA_NONE64;
         u32 prev_id = 0, prev_aux = 0;
-        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
             u32 id, aux;
             u64 slot = ga_table_find_slot(solid, solid_cap, key, id, aux);
             if (pos > 0 && prev_slot != GA_NONE64 && slot != GA_NONE64) {
@@ -133,25 +131,32 @@ build_paired_kernel(ReadsView rv, int w, const Slot<K>* __restrict__ solid, u64 
     const u32 smask = (1u << rv.sym_bits) - 1u;
     const u64 n_pairs = rv.n_reads / 2;
     bool full = false;
-    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n_pairs; p += (u64)gridDim.x * blockDim.x) {
-        u32 len = ga_read_len(rv, 2 * p);
-        if (len <= (u32)w) continue;
-        const u64* wa = ga_read_ptr(rv, 2 * p);
-        const u64* wb = ga_read_ptr(rv, 2 * p + 1);
+    const u32 lane = threadIdx.x & 31u;
+    for (u64 pb = blockIdx.x * (u64)blockDim.x + (threadIdx.x - lane); pb < n_pairs;
+         pb += (u64)gridDim.x * blockDim.x) {
+        const u64 p = pb + lane;
+        const bool valid = p < n_pairs;
+        u32 len = valid ? ga_read_len(rv, 2 * p) : 0u;
+        if (len <= (u32)w) len = 0;
+        const u64* wa = valid ? ga_read_ptr(rv, 2 * p) : rv.words;
+        const u64* wb = valid ? ga_read_ptr(rv, 2 * p + 1) : rv.words;
         const u64 e0 = (rv.first_read + p) * (u64)rv.estride;
+        const u32 max_len = __reduce_max_sync(0xFFFFFFFFu, len);   // warp-uniform walk, see ga_for_each_window
         K ka = 0, kb = 0;
         u32 prev_a = GA_NONE32, prev_b = GA_NONE32;
         u64 prev_q = GA_NONE64;  // query slot of the previous position when it was part of an accepted occurrence
-        for (u32 base = 0; base < len; base += SPW) {
-            u64 word_a = __ldg(wa + base / SPW), word_b = __ldg(wb + base / SPW);
-            u32 lim = len - base < SPW ? len - base : SPW;
+        for (u32 base = 0; base < max_len; base += SPW) {
+            u64 word_a = base < len ? __ldg(wa + base / SPW) : 0ull;
+            u64 word_b = base < len ? __ldg(wb + base / SPW) : 0ull;
+            u32 lim = max_len - base < SPW ? max_len - base : SPW;
             for (u32 j = 0; j < lim; ++j) {
                 ka = ((ka << rv.sym_bits) | (K)(word_a & SMASK)) & mask;
                 kb = ((kb << rv.sym_bits) | (K)(word_b & SMASK)) & mask;
                 word_a >>= SB;
                 word_b >>= SB;
                 u32 i = base + j + 1;
-                if (i < (u32)w) continue;
+                __syncwarp();
+                if (i < (u32)w || i > len) continue;
                 u32 pos = i - (u32)w;
                 u32 ida = ga_table_find(solid, solid_cap, ka);
                 u32 idb = ida == GA_NONE32 ? GA_NONE32 : ga_table_find(solid, solid_cap, kb);

@@ -256,26 +256,40 @@ template <class K> __host__ __device__ __forceinline__ K ga_key_mask(int w, int 
     return (bits >= (int)(8 * sizeof(K))) ? ~(K)0 : (((K)1 << bits) - 1);
 }
 
-// Walk the windows of one read.  SB = storage bits per symbol (2 or 8).  f(pos, key) is called
-// for every window start `pos` (0-based) with the packed key (first symbol most significant).
+// Walk the windows of one read, WARP-UNIFORMLY: all 32 lanes of the warp must call this together
+// (a lane without a read passes len = 0).  Every step re-converges the warp with __syncwarp():
+// the callbacks contain data-dependent probe loops, and without an explicit convergence point the
+// lanes of a warp drift apart for good and each instruction issues for 3-4 lanes instead of 32
+// (profiles/r01: "Avg. Threads Executed").  SB = storage bits per symbol (2 or 8).  f(pos, key) is
+// called for every window start `pos` (0-based) with the packed key (first symbol most significant).
 template <class K, int SB, class F>
 __device__ __forceinline__ void ga_for_each_window(const u64* __restrict__ words, u32 len, int w,
                                                    int sym_bits, K mask, F&& f) {
     constexpr u32 SPW = 64 / SB;
     constexpr u64 SMASK = (1ull << SB) - 1;
+    const u32 max_len = __reduce_max_sync(0xFFFFFFFFu, len);
     K key = 0;
-    for (u32 base = 0; base < len; base += SPW) {
-        u64 word = __ldg(words + base / SPW);
-        u32 lim = len - base < SPW ? len - base : SPW;
+    for (u32 base = 0; base < max_len; base += SPW) {
+        u64 word = base < len ? __ldg(words + base / SPW) : 0ull;
+        const u32 lim = max_len - base < SPW ? max_len - base : SPW;
         for (u32 j = 0; j < lim; ++j) {
             u32 c = (u32)(word & SMASK);
             word >>= SB;
             key = ((key << sym_bits) | (K)c) & mask;
-            u32 i = base + j + 1;
-            if (i >= (u32)w) f(i - (u32)w, key);
+            const u32 i = base + j + 1;
+            __syncwarp();
+            if (i >= (u32)w && i <= len) f(i - (u32)w, key);
         }
     }
 }
+
+// Grid-stride loop over reads in which whole warps stay together: `r` is this lane's read and
+// `valid` says whether it exists.
+#define GA_FOR_EACH_READ_WARP(rv, r, valid)                                                              \
+    for (u64 _rb = blockIdx.x * (u64)blockDim.x + (threadIdx.x & ~31u), r = _rb + (threadIdx.x & 31u),   \
+             valid = r < (rv).n_reads;                                                                    \
+         _rb < (rv).n_reads;                                                                              \
+         _rb += (u64)gridDim.x * blockDim.x, r = _rb + (threadIdx.x & 31u), valid = r < (rv).n_reads)
 
 // ---------------------------------------------------------------------------------------------
 // MurmurHash3_x86_32, seed 0, over the ASCII bytes of a window (countminsketch.py:46-95).

@@ -30,12 +30,11 @@ __global__ void __launch_bounds__(256) count_kernel(ReadsView rv, int w, Slot<K>
                                                     u64 capacity, u32* status) {
     const K mask = ga_key_mask<K>(w, rv.sym_bits);
     bool full = false;
-    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
-         r += (u64)gridDim.x * blockDim.x) {
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
         // windows range over mate 1's length for both mates (debruijn_graph.py:374)
-        u32 len = ga_read_len(rv, rv.paired ? (r & ~1ull) : r);
-        if (len < (u32)w) continue;
-        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32, K key) {
+        u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
+        if (len < (u32)w) len = 0;
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32, K key) {
             u64 s = ga_table_upsert(table, capacity, key);
             if (s == GA_NONE64) full = true;
             else atomicAdd(&table[s].val, 1u);

@@ -30,12 +30,27 @@ struct ga_csr_plan {
 
 namespace {
 
+// The stream-ordered pool gives memory back to the driver at every synchronisation unless told
+// otherwise; re-mapping a few hundred MB per pass costs far more than the kernels.
+static void keep_pool_warm() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 struct Scratch {
     cudaStream_t st;
     std::vector<void*>* keep;   // allocations that outlive the call (owned by the plan)
     std::vector<void*> temp;    // freed when the call ends
     cudaError_t err = cudaSuccess;
     template <class T> T* get(u64 n, bool persistent = false) {
+        keep_pool_warm();
         void* p = nullptr;
         cudaError_t e = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
         if (e != cudaSuccess) {

@@ -15,11 +15,10 @@ template <class K, int SB>
 __global__ void __launch_bounds__(256) prefilter_update_kernel(ReadsView rv, int w, PrefilterView pf) {
     const K mask = ga_key_mask<K>(w, rv.sym_bits);
     const u32 cmask = (1u << pf.cell_bits) - 1u;
-    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
-         r += (u64)gridDim.x * blockDim.x) {
-        u32 len = ga_read_len(rv, rv.paired ? (r & ~1ull) : r);
-        if (len < (u32)w) continue;
-        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32, K key) {
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
+        u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
+        if (len < (u32)w) len = 0;
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32, K key) {
             u64 wi;
             u32 sh;
             u32 v = ga_prefilter_value(pf, ga_key_hash(key), wi, sh);
@@ -49,11 +48,10 @@ count_candidates_kernel(ReadsView rv, int w, PrefilterView pf, Slot<K>* __restri
                         u32* status) {
     const K mask = ga_key_mask<K>(w, rv.sym_bits);
     bool full = false;
-    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < rv.n_reads;
-         r += (u64)gridDim.x * blockDim.x) {
-        u32 len = ga_read_len(rv, rv.paired ? (r & ~1ull) : r);
-        if (len < (u32)w) continue;
-        ga_for_each_window<K, SB>(ga_read_ptr(rv, r), len, w, rv.sym_bits, mask, [&](u32, K key) {
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
+        u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
+        if (len < (u32)w) len = 0;
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32, K key) {
             u64 wi;
             u32 sh;
             if (ga_prefilter_value(pf, ga_key_hash(key), wi, sh) < pf.limit) return;

@@ -22,6 +22,22 @@ _DNA = b"ACGT"
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
 
+import os as _os
+import time as _time
+_TRACE = int(_os.environ.get("GA_TRACE", "0") or 0)
+_last = [0.0]
+
+
+def _mark(name):
+    """GA_TRACE=1: print host wall time between stages (with a device sync) -- debugging aid."""
+    if _TRACE:
+        if _TRACE == 1:
+            torch.cuda.synchronize()
+        now = _time.perf_counter()
+        print("  [trace] %-28s %8.3f ms" % (name, (now - _last[0]) * 1e3))
+        _last[0] = _time.perf_counter()
+
+
 def _timed(name):
     """Context manager recording a CUDA-event pair around a kernel launch when TIMERS is set."""
     class _Span:
@@ -333,7 +349,9 @@ class KmerCounts:
         L = gn.lib()
         dev = _dev()
         bits = 4 if threshold + 1 <= 15 else 8
+        _mark("enter candidates")
         free, _ = torch.cuda.mem_get_info()
+        _mark("mem_get_info")
         n_cells = max(1 << 16, min(self.n_occ, int(free * 0.25) * 8 // bits))
         words = torch.zeros((n_cells * bits + 31) // 32, dtype=torch.int32, device=dev)
         pf = gn.GaPrefilter()
@@ -341,9 +359,11 @@ class KmerCounts:
         status = self.reads.status
         with _timed("prefilter"):
             gn.check(L.ga_prefilter_update(C.byref(self.reads.struct()), self.k, C.byref(pf), threshold, _stream()))
+        _mark("prefilter zero+update")
         n_hot = torch.zeros(1, dtype=torch.int64, device=dev)
         gn.check(L.ga_prefilter_hot(C.byref(pf), threshold, gn.ptr(n_hot), _stream()))
         hot = int(n_hot.item())
+        _mark("prefilter_hot")
         limit = max(1024, int(free * 0.5) // self.slot_bytes)
         cap = min(limit, max(1024, int(hot * 2.2) + 1024))
         while True:
@@ -356,6 +376,7 @@ class KmerCounts:
             out = torch.zeros(4, dtype=torch.int64, device=dev)
             gn.check(L.ga_table_summary(gn.ptr(table), cap, self.key_words, int(threshold), gn.ptr(out), _stream()))
             st = _check_status(status)
+            _mark("clear+count_candidates+summary")
             if st & gn.ST_BAD_SYMBOL:
                 raise ValueError("read symbol outside the detected alphabet")
             if not st & gn.ST_TABLE_FULL:
@@ -535,6 +556,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
     else:
         solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
+    _mark("select solid")
     if n_solid == 0 or reads.n_reads == 0:
         return graph
     solid_cap = int(1.7 * n_solid) + 64
@@ -544,6 +566,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, _stream()))
     gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap,
                                    gn.ptr(status), _stream()))
+    _mark("id table")
     n_nodes, n_edges, attr = C.c_int64(), C.c_int64(), C.c_int64()
     plan = C.c_void_p()
     dna4 = (not reads.paired) and alphabet.sym_bits <= 2
@@ -554,10 +577,12 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         with _timed("build"):
             gn.check(L.ga_build_unpaired_dna(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap,
                                              gn.ptr(node_stamp), gn.ptr(edge_stamp), gn.ptr(status), _stream()))
+        _mark("fill stamps + build_dna")
         gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
                                             kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),
                                             C.byref(plan), C.byref(n_nodes), C.byref(n_edges)))
         attr.value = n_edges.value
+        _mark("csr plan dna")
         if _check_status(status) & gn.ST_TABLE_FULL:
             raise gn.GaError("id table overflow")
     free, _ = torch.cuda.mem_get_info()
@@ -608,6 +633,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
                                gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
         torch.cuda.current_stream().synchronize()
+        _mark("csr emit")
     finally:
         L.ga_csr_plan_free(plan)
     graph.n_nodes, graph.n_edges, graph.num_edges_attr = nn, ne, attr.value
