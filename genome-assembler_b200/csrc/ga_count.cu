@@ -154,6 +154,15 @@ __global__ void lookup_kernel(const Slot<K>* __restrict__ table, u64 capacity, c
     }
 }
 
+// owner rank of a key for the hash-partitioned exchange: independent of the slot hash's top bits
+template <class K>
+__global__ void key_owner_kernel(const K* __restrict__ keys, u64 n, u32 n_parts, int* __restrict__ owner) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 h = ga_key_hash(keys[i]);
+        owner[i] = (int)__umul64hi((h << 32) | (h >> 32), (u64)n_parts);
+    }
+}
+
 int check_table_args(const char* fn, const void* table, u64 capacity, int key_words) {
     if (!table || capacity == 0 || (key_words != 1 && key_words != 2)) {
         ga_set_error("%s: bad table arguments (capacity=%llu key_words=%d)", fn, capacity, key_words);
@@ -234,6 +243,20 @@ extern "C" int ga_table_insert_ids(const void* keys_dev, uint64_t n, int key_wor
     else
         insert_ids_kernel<u128><<<grid, 256, 0, st>>>((const u128*)keys_dev, n, id_base, (Slot<u128>*)table_dev, capacity, status_dev);
     GA_LAUNCH_CHECK("insert_ids");
+    return GA_OK;
+}
+
+extern "C" int ga_key_owner(const void* keys_dev, uint64_t n, int key_words, uint32_t n_parts, int32_t* owner_dev,
+                            ga_stream stream) {
+    if ((key_words != 1 && key_words != 2) || n_parts == 0 || (n && (!keys_dev || !owner_dev))) {
+        ga_set_error("ga_key_owner: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    if (n == 0) return GA_OK;
+    unsigned grid = ga_grid(n, 256);
+    if (key_words == 1) key_owner_kernel<u64><<<grid, 256, 0, (cudaStream_t)stream>>>((const u64*)keys_dev, n, n_parts, owner_dev);
+    else key_owner_kernel<u128><<<grid, 256, 0, (cudaStream_t)stream>>>((const u128*)keys_dev, n, n_parts, owner_dev);
+    GA_LAUNCH_CHECK("key_owner");
     return GA_OK;
 }
 

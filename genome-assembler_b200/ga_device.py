@@ -651,6 +651,41 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     return graph
 
 
+def emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_cap, kw, k, alphabet, to_host):
+    """CSR from per-node edge stamps (unpaired, <= 4 symbols); used by the multi-GPU path on rank 0."""
+    L = gn.lib()
+    dev = node_stamp.device
+    n_nodes, n_edges, plan = C.c_int64(), C.c_int64(), C.c_void_p()
+    gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys), kw, k,
+                                        alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(), C.byref(plan),
+                                        C.byref(n_nodes), C.byref(n_edges)))
+    try:
+        nn, ne = n_nodes.value, n_edges.value
+        rowptr = torch.empty(nn + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+        indeg = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        branching = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        last_sym = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        keys_a = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
+        gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
+                               gn.ptr(last_sym), gn.ptr(keys_a), None, _stream()))
+        torch.cuda.current_stream().synchronize()
+    finally:
+        L.ga_csr_plan_free(plan)
+    graph.n_nodes, graph.n_edges, graph.num_edges_attr = nn, ne, ne
+    if not to_host:
+        graph.device = dict(rowptr=rowptr, col=col, indeg=indeg, branching=branching, last_sym=last_sym,
+                            keys_a=keys_a, keys_b=None)
+        return graph
+    graph.rowptr = rowptr.cpu().numpy()
+    graph.col = col[:ne].cpu().numpy()
+    graph.indeg = indeg[:nn].cpu().numpy()
+    graph.branching = branching[:nn].cpu().numpy()
+    graph.last_char = alphabet.inv[last_sym[:nn].cpu().numpy()]
+    graph.keys_a = keys_a[:nn].cpu().numpy().view(np.uint64)
+    return graph
+
+
 # ----------------------------------------------------------------------------------- whole path
 def device_step(reads: DeviceReads, k: int, threshold: int, timers=None):
     """One pass of the hot path over device-resident packed reads; the CSR stays on the device."""

@@ -58,6 +58,7 @@ SIGNATURES = {
     "ga_table_clear": (_i32, [_vp, _u64, _i32, _vp]),
     "ga_count_kmers": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp]),
     "ga_count_keys": (_i32, [_vp, _vp, _u64, _i32, _vp, _u64, _vp, _vp]),
+    "ga_key_owner": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),
     "ga_table_summary": (_i32, [_vp, _u64, _i32, _i64, _vp, _vp]),
     "ga_table_export": (_i32, [_vp, _u64, _i32, _i64, _vp, _vp, _vp, _vp]),
     "ga_table_lookup": (_i32, [_vp, _u64, _i32, _vp, _u64, _vp, _vp]),

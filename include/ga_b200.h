@@ -125,6 +125,9 @@ int ga_count_kmers(const ga_reads* reads, int k, void* table_dev, uint64_t capac
 /* add `amounts_dev[i]` (NULL: 1) for explicit packed keys (multi-GPU owner side; dict upload) */
 int ga_count_keys(const void* keys_dev, const uint32_t* amounts_dev, uint64_t n, int key_words,
                   void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
+/* owner_dev[i] = rank in [0, n_parts) that owns keys_dev[i] in the hash-partitioned exchange */
+int ga_key_owner(const void* keys_dev, uint64_t n, int key_words, uint32_t n_parts, int32_t* owner_dev,
+                 ga_stream stream);
 /* out4_dev = { distinct keys, keys with count > threshold, sum of counts, max count } */
 int ga_table_summary(const void* table_dev, uint64_t capacity, int key_words, int64_t threshold,
                      uint64_t* out4_dev, ga_stream stream);

@@ -1,0 +1,49 @@
+"""Run under torchrun on N GPUs: the sharded build must equal the single-GPU build bit for bit.
+Rank 0 also builds the whole read set alone and compares every CSR array."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "genome-assembler_b200")]
+import numpy as np
+import torch
+import torch.distributed as dist
+import ga_native as gn
+import ga_device as gd
+import ga_multi
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    L = gn.lib()
+    ok = True
+    for genome_size, n_reads, read_len, k, F in ((200000, 60000, 100, 31, 3), (50000, 30011, 150, 41, 2)):
+        stride = (read_len + 31) // 32
+        genome = torch.empty(genome_size, dtype=torch.uint8, device=dev)
+        gn.check(L.ga_gen_genome(gn.ptr(genome), genome_size, 5, None))
+        lo, hi = n_reads * rank // world, n_reads * (rank + 1) // world
+        words = torch.empty(max(1, (hi - lo) * stride), dtype=torch.int64, device=dev)
+        gn.check(L.ga_gen_reads(gn.ptr(genome), genome_size, lo, hi - lo, read_len, 5, 100, gn.ptr(words), stride, 0, 0, None))
+        shard = gd.DeviceReads.from_packed(words, hi - lo, read_len, False, first_read=lo, estride=read_len)
+        got = ga_multi.sharded_step(shard, k, F, to_host=True)
+        if rank == 0:
+            allw = torch.empty(n_reads * stride, dtype=torch.int64, device=dev)
+            gn.check(L.ga_gen_reads(gn.ptr(genome), genome_size, 0, n_reads, read_len, 5, 100, gn.ptr(allw), stride, 0, 0, None))
+            whole = gd.DeviceReads.from_packed(allw, n_reads, read_len, False, estride=read_len)
+            want = gd.build_graph(gd.KmerCounts(k, whole), whole, F, to_host=True)
+            same = all(np.array_equal(getattr(got, f), getattr(want, f))
+                       for f in ("rowptr", "col", "indeg", "branching", "last_char", "keys_a"))
+            print("multi_check world=%d k=%d: nodes %d/%d edges %d/%d identical=%s" %
+                  (world, k, got.n_nodes, want.n_nodes, got.n_edges, want.n_edges, same), flush=True)
+            ok = ok and same and got.n_nodes > 0
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""Host-side logic of the multi-GPU path on the CPU: world_size-2 gloo processes exercise the
+tensor-moving helpers of ga_multi (variable all-gather, hash-owner all-to-all, unsigned
+min all-reduce).  The kernels themselves are covered by the -m gpu tests."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, results):
+    sys.path[:0] = [os.path.join(ROOT, "genome-assembler_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ga_multi
+    try:
+        # variable all-gather: rank r contributes r+2 rows
+        local = torch.arange((rank + 2) * 2, dtype=torch.int64).reshape(rank + 2, 2) + 100 * rank
+        cat, sizes = ga_multi.all_gather_var(local)
+        want = torch.cat([torch.arange((r + 2) * 2, dtype=torch.int64).reshape(r + 2, 2) + 100 * r for r in range(world)])
+        assert sizes == [r + 2 for r in range(world)] and torch.equal(cat, want)
+        # empty contribution from one rank
+        cat, sizes = ga_multi.all_gather_var(local[:0] if rank == 0 else local)
+        assert sizes[0] == 0 and cat.shape[0] == sum(sizes)
+
+        # hash-owner exchange: keys 0..19 on each rank (+1000*rank), owner = key % world
+        keys = torch.arange(20, dtype=torch.int64) + 1000 * rank
+        counts = (torch.arange(20, dtype=torch.int32) + 1) * (rank + 1)
+        owner = (keys % world).to(torch.int32)
+        got_keys, got_counts = ga_multi.exchange_by_owner(owner, [keys.reshape(-1, 1), counts])
+        assert torch.all(got_keys[:, 0] % world == rank)
+        assert got_keys.shape[0] == got_counts.shape[0] == 20        # 10 from each of 2 ranks
+        total = torch.tensor([int(got_counts.sum())], dtype=torch.int64)
+        dist.all_reduce(total)
+        assert int(total) == sum((i + 1) * (r + 1) for i in range(20) for r in range(world))
+        # (key, count) rows stay paired
+        for kk, cc in zip(got_keys[:, 0].tolist(), got_counts.tolist()):
+            src = kk // 1000
+            assert cc == ((kk % 1000) + 1) * (src + 1)
+
+        # unsigned minimum with all-ones meaning "no stamp"
+        stamps = torch.full((6,), -1, dtype=torch.int64)
+        if rank == 0:
+            stamps[0], stamps[1], stamps[3] = 7, 1 << 40, 5
+        else:
+            stamps[0], stamps[2], stamps[3] = 3, 9, 6
+        ga_multi.all_reduce_min_u64(stamps)
+        assert stamps.tolist() == [3, 1 << 40, 9, 5, -1, -1]
+        results[rank] = "ok"
+    except Exception as exc:      # noqa: BLE001
+        results[rank] = repr(exc)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_rank_helpers_gloo():
+    world = 2
+    port = 29600 + os.getpid() % 300
+    with mp.Manager() as manager:
+        results = manager.dict()
+        mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: "ok", 1: "ok"}
