@@ -112,6 +112,115 @@ build_unpaired_dna_kernel(ReadsView rv, int w, Slot<K>* solid, u64 solid_cap, u6
     }
 }
 
+// ---- two-phase build: what is still unstamped after a prefix of the reads ---------------------
+__device__ __forceinline__ void bloom_bits(u64 h, u64 n_words, u64& word, u32& bits) {
+    word = ga_slot_of(h, n_words);
+    bits = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)) | (1u << ((h >> 10) & 31u));
+}
+
+template <class K>
+__global__ void unstamped_scan_kernel(const Slot<K>* __restrict__ solid, u64 solid_cap, const K* __restrict__ keys,
+                                      u64 n_solid, const u64* __restrict__ edge_stamp, int w, int sym_bits,
+                                      u8* __restrict__ mask_out, u64* n_open) {
+    const K mask = ga_key_mask<K>(w, sym_bits);
+    const u32 n_sym = 1u << sym_bits;
+    u64 mine = 0;
+    for (u64 id = blockIdx.x * (u64)blockDim.x + threadIdx.x; id < n_solid; id += (u64)gridDim.x * blockDim.x) {
+        const K key = keys[id];
+        u32 open = 0;
+        for (u32 c = 0; c < n_sym; ++c) {
+            if (edge_stamp[4 * id + c] != GA_NONE64) continue;
+            K succ = ((key << sym_bits) | (K)c) & mask;
+            if (ga_table_find(solid, solid_cap, succ) != GA_NONE32) open |= 1u << c;
+        }
+        mask_out[id] = (u8)open;
+        mine += open != 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_open, mine);
+}
+
+template <class K>
+__global__ void unstamped_table_kernel(const K* __restrict__ keys, const u8* __restrict__ open_mask, u64 n_solid,
+                                       Slot<K>* __restrict__ table, u64 capacity, u32* __restrict__ bloom,
+                                       u64 bloom_words, u32* status) {
+    bool full = false;
+    for (u64 id = blockIdx.x * (u64)blockDim.x + threadIdx.x; id < n_solid; id += (u64)gridDim.x * blockDim.x) {
+        u32 open = open_mask[id];
+        if (!open) continue;
+        const K key = keys[id];
+        u64 s = ga_table_upsert(table, capacity, key);
+        if (s == GA_NONE64) {
+            full = true;
+            continue;
+        }
+        table[s].val = (u32)id;
+        table[s].aux = open;
+        u64 word;
+        u32 bits;
+        bloom_bits(ga_key_hash(key), bloom_words, word, bits);
+        atomicOr(bloom + word, bits);
+    }
+    if (full) atomicOr(status, GA_ST_TABLE_FULL);
+}
+
+// Remaining reads: an occurrence matters only if its prefix node still has an open edge through the
+// next symbol.  One Bloom word per window; hits (about 1 in 100) go to the open-node table.
+template <class K, int SB>
+__global__ void __launch_bounds__(256)
+build_dna_tail_kernel(ReadsView rv, int w, const u32* __restrict__ bloom, u64 bloom_words,
+                      const Slot<K>* __restrict__ open_table, u64 open_cap, const Slot<K>* __restrict__ solid,
+                      u64 solid_cap, u64* __restrict__ node_stamp, u64* __restrict__ edge_stamp) {
+    const K mask = ga_key_mask<K>(w, rv.sym_bits);
+    const u32 smask = (1u << rv.sym_bits) - 1u;
+    GA_FOR_EACH_READ_WARP(rv, r, valid) {
+        u32 len = valid ? ga_read_len(rv, r) : 0u;
+        if (len <= (u32)w) len = 0;
+        const u64 e0 = (rv.first_read + r) * (u64)rv.estride;
+        bool prev_hit = false;
+        K prev_key = 0;
+        ga_for_each_window<K, SB>(valid ? ga_read_ptr(rv, r) : rv.words, len, w, rv.sym_bits, mask, [&](u32 pos, K key) {
+            if (prev_hit) {   // the previous window may be an open node: is its edge through my last symbol open?
+                K pk;
+                u32 id, open;
+                u64 s = ga_slot_of(ga_key_hash(prev_key), open_cap);
+                for (u64 probes = 0; probes < open_cap; ++probes) {
+                    const Slot<K>* slot = open_table + s;
+                    uint4 raw = __ldg(reinterpret_cast<const uint4*>(slot));
+                    if (sizeof(K) == 8) {
+                        pk = (K)(((u64)raw.y << 32) | raw.x);
+                        id = raw.z;
+                        open = raw.w;
+                    } else {
+                        uint4 raw2 = __ldg(reinterpret_cast<const uint4*>(slot) + 1);
+                        pk = (K)(((u128)(((u64)raw.w << 32) | raw.z) << 64) | (((u64)raw.y << 32) | raw.x));
+                        id = raw2.x;
+                        open = raw2.y;
+                    }
+                    if (pk == prev_key) {
+                        const u32 sym = (u32)key & smask;
+                        if ((open >> sym) & 1u) {
+                            const u64 e = e0 + (pos - 1);
+                            u32 succ = ga_table_find(solid, solid_cap, key);   // solid by construction of the mask
+                            atomicMin(edge_stamp + 4ull * id + sym, e);
+                            atomicMin(node_stamp + id, 2 * e);
+                            if (succ != GA_NONE32) atomicMin(node_stamp + succ, 2 * e + 1);
+                        }
+                        break;
+                    }
+                    if (pk == ga_empty_key<K>()) break;
+                    if (++s == open_cap) s = 0;
+                }
+            }
+            u64 word;
+            u32 bits;
+            bloom_bits(ga_key_hash(key), bloom_words, word, bits);
+            prev_hit = (__ldg(bloom + word) & bits) == bits;
+            prev_key = key;
+        });
+    }
+}
+
 // Keep the two smallest values ever offered (all values distinct): m[0] <= m[1].
 __device__ __forceinline__ void two_min(u64* m, u64 v) {
     u64 old = atomicMin(m, v);
@@ -247,6 +356,81 @@ extern "C" int ga_build_unpaired_dna(const ga_reads* reads, int k, void* solid_d
     else GA_BUILD(u128, 8);
 #undef GA_BUILD
     GA_LAUNCH_CHECK("build_unpaired_dna");
+    return GA_OK;
+}
+
+extern "C" int ga_unstamped_scan(const void* solid_dev, uint64_t solid_capacity, const void* solid_keys_dev,
+                                 uint64_t n_solid, int key_words, const uint64_t* edge_stamp_dev, int k,
+                                 int sym_bits, uint8_t* mask_out_dev, uint64_t* n_open_dev, ga_stream stream) {
+    if (!solid_dev || !solid_keys_dev || !edge_stamp_dev || !mask_out_dev || !n_open_dev || sym_bits > 2 ||
+        (key_words != 1 && key_words != 2) || solid_capacity == 0) {
+        ga_set_error("ga_unstamped_scan: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    if (n_solid == 0) return GA_OK;
+    unsigned grid = ga_grid(n_solid, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (key_words == 1)
+        unstamped_scan_kernel<u64><<<grid, 256, 0, st>>>((const Slot<u64>*)solid_dev, solid_capacity, (const u64*)solid_keys_dev,
+                                                        n_solid, (const u64*)edge_stamp_dev, k - 1, sym_bits, mask_out_dev, (u64*)n_open_dev);
+    else
+        unstamped_scan_kernel<u128><<<grid, 256, 0, st>>>((const Slot<u128>*)solid_dev, solid_capacity, (const u128*)solid_keys_dev,
+                                                         n_solid, (const u64*)edge_stamp_dev, k - 1, sym_bits, mask_out_dev, (u64*)n_open_dev);
+    GA_LAUNCH_CHECK("unstamped_scan");
+    return GA_OK;
+}
+
+extern "C" int ga_unstamped_table_build(const void* solid_keys_dev, const uint8_t* mask_dev, uint64_t n_solid,
+                                        int key_words, void* open_table_dev, uint64_t open_capacity,
+                                        uint32_t* bloom_dev, uint64_t bloom_words, uint32_t* status_dev,
+                                        ga_stream stream) {
+    if (!solid_keys_dev || !mask_dev || !open_table_dev || !bloom_dev || open_capacity == 0 || bloom_words == 0 ||
+        (key_words != 1 && key_words != 2)) {
+        ga_set_error("ga_unstamped_table_build: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    if (n_solid == 0) return GA_OK;
+    unsigned grid = ga_grid(n_solid, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (key_words == 1)
+        unstamped_table_kernel<u64><<<grid, 256, 0, st>>>((const u64*)solid_keys_dev, mask_dev, n_solid, (Slot<u64>*)open_table_dev,
+                                                         open_capacity, bloom_dev, bloom_words, status_dev);
+    else
+        unstamped_table_kernel<u128><<<grid, 256, 0, st>>>((const u128*)solid_keys_dev, mask_dev, n_solid, (Slot<u128>*)open_table_dev,
+                                                          open_capacity, bloom_dev, bloom_words, status_dev);
+    GA_LAUNCH_CHECK("unstamped_table");
+    return GA_OK;
+}
+
+extern "C" int ga_build_unpaired_dna_tail(const ga_reads* reads, int k, const uint32_t* bloom_dev, uint64_t bloom_words,
+                                          const void* open_table_dev, uint64_t open_capacity, const void* solid_dev,
+                                          uint64_t solid_capacity, uint64_t* node_stamp_dev, uint64_t* edge_stamp_dev,
+                                          ga_stream stream) {
+    if (!reads || !bloom_dev || !open_table_dev || !solid_dev || !node_stamp_dev || !edge_stamp_dev ||
+        bloom_words == 0 || open_capacity == 0 || solid_capacity == 0) {
+        ga_set_error("ga_build_unpaired_dna_tail: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    int kw = ga_key_words(k, reads->sym_bits);
+    if (!kw || reads->paired || reads->sym_bits > 2) {
+        ga_set_error("ga_build_unpaired_dna_tail: needs unpaired reads over at most 4 symbols");
+        return GA_ERR_BAD_ARG;
+    }
+    if (reads->n_reads == 0) return GA_OK;
+    ReadsView rv = ga_view(reads);
+    unsigned grid = ga_grid(rv.n_reads, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GA_TAIL(K, SB)                                                                                       \
+    build_dna_tail_kernel<K, SB><<<grid, 256, 0, st>>>(rv, k - 1, bloom_dev, bloom_words,                     \
+                                                      (const Slot<K>*)open_table_dev, open_capacity,         \
+                                                      (const Slot<K>*)solid_dev, solid_capacity,             \
+                                                      (u64*)node_stamp_dev, (u64*)edge_stamp_dev)
+    if (kw == 1 && rv.storage_bits == 2) GA_TAIL(u64, 2);
+    else if (kw == 1) GA_TAIL(u64, 8);
+    else if (rv.storage_bits == 2) GA_TAIL(u128, 2);
+    else GA_TAIL(u128, 8);
+#undef GA_TAIL
+    GA_LAUNCH_CHECK("build_dna_tail");
     return GA_OK;
 }
 

@@ -52,6 +52,13 @@ extern "C" int ga_fill_bytes(void* dev, int value, uint64_t bytes, ga_stream str
 
 extern "C" void ga_free_host(void* p) { free(p); }
 
+// The hot kernels are random 16-byte probes; a DRAM fetch wider than one 32-byte sector is
+// wasted bandwidth for them.  Process-wide hint (cudaLimitMaxL2FetchGranularity).
+extern "C" int ga_set_l2_fetch_granularity(int bytes) {
+    GA_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return GA_OK;
+}
+
 // Walk = pop the last remaining edge of the start node, then keep going while the current node
 // still has edges and was not branching; every step contributes the successor's last symbol.
 extern "C" int ga_traverse_contigs(const int32_t* rowptr, const int32_t* col, const int32_t* indeg,

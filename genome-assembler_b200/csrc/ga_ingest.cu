@@ -68,6 +68,28 @@ __global__ void pack_ragged_kernel(const u8* __restrict__ ascii, const u64* __re
     if (bad) atomicOr(status, GA_ST_BAD_SYMBOL);
 }
 
+// packed uniform reads -> ASCII (inverse of pack_uniform_kernel): one thread per packed word
+template <int SB>
+__global__ void unpack_uniform_kernel(const u64* __restrict__ words, u64 n_reads, u32 len, u32 stride_words,
+                                      const u8* __restrict__ inv_g, u8* __restrict__ ascii) {
+    constexpr u32 SPW = 64 / SB;
+    constexpr u64 SMASK = (1ull << SB) - 1;
+    __shared__ u8 inv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) inv[i] = inv_g[i];
+    __syncthreads();
+    u64 total = n_reads * (u64)stride_words;
+    for (u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+        u64 r = idx / stride_words;
+        u32 first = (u32)(idx % stride_words) * SPW;
+        u64 word = words[idx];
+        u8* dst = ascii + r * (u64)len + first;
+        for (u32 j = 0; j < SPW && first + j < len; ++j) {
+            dst[j] = inv[word & SMASK];
+            word >>= SB;
+        }
+    }
+}
+
 __device__ __forceinline__ u64 splitmix64(u64 x) {
     u64 z = x + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -147,6 +169,24 @@ extern "C" int ga_pack_reads(const uint8_t* ascii_dev, const uint64_t* in_offset
                                                          (const u64*)out_offsets_dev, status_dev);
     }
     GA_LAUNCH_CHECK("pack");
+    return GA_OK;
+}
+
+extern "C" int ga_unpack_reads(const void* words_dev, uint64_t n_reads, uint32_t uniform_len, uint32_t stride_words,
+                               int storage_bits, const uint8_t* inv_lut_dev, uint8_t* ascii_dev, ga_stream stream) {
+    if ((storage_bits != 2 && storage_bits != 8) || !inv_lut_dev) {
+        ga_set_error("ga_unpack_reads: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    u64 total = n_reads * (u64)stride_words;
+    if (total == 0 || uniform_len == 0) return GA_OK;
+    unsigned grid = ga_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (storage_bits == 2)
+        unpack_uniform_kernel<2><<<grid, 256, 0, st>>>((const u64*)words_dev, n_reads, uniform_len, stride_words, inv_lut_dev, ascii_dev);
+    else
+        unpack_uniform_kernel<8><<<grid, 256, 0, st>>>((const u64*)words_dev, n_reads, uniform_len, stride_words, inv_lut_dev, ascii_dev);
+    GA_LAUNCH_CHECK("unpack");
     return GA_OK;
 }
 

@@ -19,6 +19,10 @@ import torch
 import ga_native as gn
 
 _DNA = b"ACGT"
+# two-phase build thresholds (tests lower them to exercise the path on small inputs)
+TWO_PHASE_MIN_TABLE_BYTES = 64 << 20    # id table + stamps beyond this no longer live in the L2
+TWO_PHASE_MIN_READS = 1 << 22
+TWO_PHASE_MIN_STEP = 1 << 20
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
 
@@ -38,8 +42,9 @@ def _mark(name):
         _last[0] = _time.perf_counter()
 
 
-def _timed(name):
-    """Context manager recording a CUDA-event pair around a kernel launch when TIMERS is set."""
+def _timed(name, occurrences=0):
+    """Context manager recording a CUDA-event pair (and the occurrences the launch covers) around a
+    kernel launch when TIMERS is set."""
     class _Span:
         def __enter__(self):
             self.on = TIMERS is not None
@@ -50,7 +55,7 @@ def _timed(name):
         def __exit__(self, *exc):
             if self.on:
                 self.b.record()
-                TIMERS.setdefault(name, []).append((self.a, self.b))
+                TIMERS.setdefault(name, []).append((self.a, self.b, occurrences))
     return _Span()
 
 
@@ -265,6 +270,21 @@ class DeviceReads:
             self._struct = s
         return self._struct
 
+    def struct_range(self, r0: int, r1: int) -> gn.GaReads:
+        """Descriptor of reads [r0, r1) of this (unpaired) set; stamps keep their global index."""
+        base = self.struct()
+        s = gn.GaReads()
+        for name, _ in gn.GaReads._fields_:
+            setattr(s, name, getattr(base, name))
+        s.n_reads = r1 - r0
+        s.first_read = self.first_read + r0
+        if self.offsets is None:
+            s.words = self.words.data_ptr() + r0 * self.stride_words * 8
+        else:
+            s.offsets = self.offsets.data_ptr() + r0 * 8
+            s.lengths = self.lengths.data_ptr() + r0 * 4
+        return s
+
     def key_words(self, k: int) -> int:
         kw = gn.lib().ga_key_words(k, self.alphabet.sym_bits)
         if kw == 0:
@@ -325,7 +345,7 @@ class KmerCounts:
             self.capacity = cap
             self.reads.status.zero_()
             gn.check(L.ga_table_clear(gn.ptr(self._table), cap, self.key_words, _stream()))
-            with _timed("count"):
+            with _timed("count_full", self.n_occ):
                 gn.check(L.ga_count_kmers(C.byref(self.reads.struct()), self.k, gn.ptr(self._table), cap,
                                           gn.ptr(self.reads.status), _stream()))
             st = _check_status(self.reads.status)
@@ -357,7 +377,7 @@ class KmerCounts:
         pf = gn.GaPrefilter()
         pf.words, pf.n_cells, pf.cell_bits = gn.ptr(words), n_cells, bits
         status = self.reads.status
-        with _timed("prefilter"):
+        with _timed("prefilter", self.n_occ):
             gn.check(L.ga_prefilter_update(C.byref(self.reads.struct()), self.k, C.byref(pf), threshold, _stream()))
         _mark("prefilter zero+update")
         n_hot = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -370,7 +390,7 @@ class KmerCounts:
             table = torch.empty(cap * self.slot_bytes, dtype=torch.uint8, device=dev)
             status.zero_()
             gn.check(L.ga_table_clear(gn.ptr(table), cap, self.key_words, _stream()))
-            with _timed("count"):
+            with _timed("count", self.n_occ):
                 gn.check(L.ga_count_candidates(C.byref(self.reads.struct()), self.k, C.byref(pf), threshold,
                                                gn.ptr(table), cap, gn.ptr(status), _stream()))
             out = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -574,9 +594,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         # <= 4 symbols: per-node edge stamps, epoch-tagged slots (ga_build_unpaired_dna)
         node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
         edge_stamp = torch.full((4 * n_solid,), -1, dtype=torch.int64, device=dev)
-        with _timed("build"):
-            gn.check(L.ga_build_unpaired_dna(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap,
-                                             gn.ptr(node_stamp), gn.ptr(edge_stamp), gn.ptr(status), _stream()))
+        build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status)
         _mark("fill stamps + build_dna")
         gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
                                             kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),
@@ -649,6 +667,53 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     graph.keys_a = keys_a[:nn].cpu().numpy().view(np.uint64)
     graph.keys_b = keys_b[:nn].cpu().numpy().view(np.uint64) if reads.paired else None
     return graph
+
+
+def build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status):
+    """Stamps of an unpaired read set over <= 4 symbols (ga_build_unpaired_dna).  When the id table is
+    far bigger than the L2, only a prefix of the reads goes through it: what is still unstamped
+    afterwards is small, and the rest of the reads is checked against a Bloom filter of it
+    (ga_build_unpaired_dna_tail).  Same stamps either way."""
+    L = gn.lib()
+    dev = node_stamp.device
+    n = reads.n_reads
+    per_read = max(reads.max_len - (k - 1) + 1, 0) if reads.lens is None else 0
+
+    def run(r0, r1):
+        with _timed("build", (r1 - r0) * per_read):
+            gn.check(L.ga_build_unpaired_dna(C.byref(reads.struct_range(r0, r1)), k, gn.ptr(solid), solid_cap,
+                                             gn.ptr(node_stamp), gn.ptr(edge_stamp), gn.ptr(status), _stream()))
+
+    big = n_solid * 27 > TWO_PHASE_MIN_TABLE_BYTES and n >= TWO_PHASE_MIN_READS
+    if not big:
+        run(0, n)
+        return
+    done, step = 0, max(TWO_PHASE_MIN_STEP, n // 20)
+    while True:
+        hi = min(n, done + step)
+        run(done, hi)
+        done = hi
+        if done >= n:
+            return
+        mask = torch.empty(n_solid, dtype=torch.uint8, device=dev)
+        n_open = torch.zeros(1, dtype=torch.int64, device=dev)
+        gn.check(L.ga_unstamped_scan(gn.ptr(solid), solid_cap, gn.ptr(solid_keys), n_solid, kw, gn.ptr(edge_stamp), k,
+                                     reads.alphabet.sym_bits, gn.ptr(mask), gn.ptr(n_open), _stream()))
+        opened = int(n_open.item())
+        if opened <= max(TWO_PHASE_MIN_STEP, n_solid // 4) and opened <= (24 << 20):
+            break
+        step *= 2
+    open_cap = 2 * opened + 64
+    open_table = torch.empty(open_cap * L.ga_slot_bytes(kw), dtype=torch.uint8, device=dev)
+    bloom_words = max(1024, opened // 2)
+    bloom = torch.zeros(bloom_words, dtype=torch.int32, device=dev)
+    gn.check(L.ga_table_clear(gn.ptr(open_table), open_cap, kw, _stream()))
+    gn.check(L.ga_unstamped_table_build(gn.ptr(solid_keys), gn.ptr(mask), n_solid, kw, gn.ptr(open_table), open_cap,
+                                        gn.ptr(bloom), bloom_words, gn.ptr(status), _stream()))
+    with _timed("build_tail", (n - done) * per_read):
+        gn.check(L.ga_build_unpaired_dna_tail(C.byref(reads.struct_range(done, n)), k, gn.ptr(bloom), bloom_words,
+                                              gn.ptr(open_table), open_cap, gn.ptr(solid), solid_cap,
+                                              gn.ptr(node_stamp), gn.ptr(edge_stamp), _stream()))
 
 
 def emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_cap, kw, k, alphabet, to_host):

@@ -102,7 +102,8 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
     cells = torch.zeros(n_cells, dtype=torch.uint8, device=dev)
     pf = gn.GaPrefilter()
     pf.words, pf.n_cells, pf.cell_bits = gn.ptr(cells), n_cells, 8
-    with gd._timed("prefilter"):
+    n_occ_local = reads.windows_total(k)
+    with gd._timed("prefilter", n_occ_local):
         gn.check(L.ga_prefilter_update(C.byref(reads.struct()), k, C.byref(pf), threshold, stream()))
     cells.clamp_(max=threshold + 1)
     dist.all_reduce(cells)
@@ -115,7 +116,7 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
         table = torch.empty(cap * slot_bytes, dtype=torch.uint8, device=dev)
         status.zero_()
         gn.check(L.ga_table_clear(gn.ptr(table), cap, kw, stream()))
-        with gd._timed("count"):
+        with gd._timed("count", n_occ_local):
             gn.check(L.ga_count_candidates(C.byref(reads.struct()), k, C.byref(pf), threshold, gn.ptr(table), cap,
                                            gn.ptr(status), stream()))
         out4 = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -165,9 +166,7 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
     # 5. stamps of the local shard, then the global minimum
     stamps = torch.full((5 * n_solid,), -1, dtype=torch.int64, device=dev)
     node_stamp, edge_stamp = stamps[:n_solid], stamps[n_solid:]
-    with gd._timed("build"):
-        gn.check(L.ga_build_unpaired_dna(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap, gn.ptr(node_stamp),
-                                         gn.ptr(edge_stamp), gn.ptr(status), stream()))
+    gd.build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status)
     all_reduce_min_u64(stamps)
     if gd._check_status(status) & (gn.ST_TABLE_FULL | gn.ST_BAD_SYMBOL):
         raise gn.GaError("table overflow or bad symbol in the sharded build")

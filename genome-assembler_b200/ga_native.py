@@ -49,10 +49,12 @@ SIGNATURES = {
     "ga_last_error": (C.c_char_p, []),
     "ga_device_count": (_i32, []),
     "ga_launch_count": (_u64, []),
+    "ga_set_l2_fetch_granularity": (_i32, [_i32]),
     "ga_fill_bytes": (_i32, [_vp, _i32, _u64, _vp]),
     "ga_key_words": (_i32, [_i32, _i32]),
     "ga_slot_bytes": (_i32, [_i32]),
     "ga_pack_reads": (_i32, [_vp, _vp, _u64, _u32, _vp, _i32, _vp, _vp, _u32, _vp, _vp]),
+    "ga_unpack_reads": (_i32, [_vp, _u64, _u32, _u32, _i32, _vp, _vp, _vp]),
     "ga_gen_genome": (_i32, [_vp, _u64, _u64, _vp]),
     "ga_gen_reads": (_i32, [_vp, _u64, _u64, _u64, _u32, _u64, _u32, _vp, _u32, _i32, _u32, _vp]),
     "ga_table_clear": (_i32, [_vp, _u64, _i32, _vp]),
@@ -73,6 +75,9 @@ SIGNATURES = {
     "ga_select_solid": (_i32, [_vp, _u64, _i32, _i32, _i32, _i64, _PS, _vp, _vp, _vp, _vp, _vp]),
     "ga_build_unpaired": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
     "ga_build_unpaired_dna": (_i32, [_PR, _i32, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "ga_unstamped_scan": (_i32, [_vp, _u64, _vp, _u64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ga_unstamped_table_build": (_i32, [_vp, _vp, _u64, _i32, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "ga_build_unpaired_dna_tail": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "ga_build_paired": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "ga_csr_plan_unpaired": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _u64, _vp,
                                     C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
@@ -116,10 +121,19 @@ def check(rc: int) -> None:
         raise GaError("libga_b200 error %d: %s" % (rc, last_error()))
 
 
+_tuned = False
+
+
 def require_gpu() -> None:
+    global _tuned
     if lib().ga_device_count() < 1:
         raise GaError("no CUDA device visible: the k-mer counting / graph build path runs on "
                       "the GPU only (no CPU fallback)")
+    if not _tuned:
+        _tuned = True
+        gran = int(os.environ.get("GA_L2_FETCH", "0"))   # measured on B200: no effect (profiles/r01)
+        if gran in (32, 64, 128):
+            lib().ga_set_l2_fetch_granularity(gran)
 
 
 def ptr(tensor) -> int:

@@ -89,6 +89,7 @@ int ga_version(void);
 const char* ga_last_error(void);
 int ga_device_count(void);                 /* number of CUDA devices, 0 without a GPU */
 uint64_t ga_launch_count(void);            /* kernels of this library launched so far (process-wide) */
+int ga_set_l2_fetch_granularity(int bytes); /* 32, 64 or 128: DRAM bytes fetched per L2 miss (hint) */
 int ga_fill_bytes(void* dev, int value, uint64_t bytes, ga_stream stream);
 
 /* key geometry: 1 word (64-bit keys) when (k-1)*sym_bits <= 63, 2 words when <= 127,
@@ -105,6 +106,11 @@ int ga_pack_reads(const uint8_t* ascii_dev, const uint64_t* in_offsets_dev, uint
                   uint32_t uniform_len, const uint8_t* lut_dev, int storage_bits, void* words_dev,
                   const uint64_t* out_offsets_dev, uint32_t stride_words, uint32_t* status_dev,
                   ga_stream stream);
+
+/* Inverse of ga_pack_reads for uniform-length reads: packed words -> n_reads*uniform_len bytes.
+ * inv_lut_dev[256]: symbol code -> byte. */
+int ga_unpack_reads(const void* words_dev, uint64_t n_reads, uint32_t uniform_len, uint32_t stride_words,
+                    int storage_bits, const uint8_t* inv_lut_dev, uint8_t* ascii_dev, ga_stream stream);
 
 /* Synthetic reads on the device (our replacement for generate_reads.py:42-74 where it cannot
  * produce the shape: any length, per-base substitutions, seeded; arithmetic documented in
@@ -194,6 +200,25 @@ int ga_build_unpaired(const ga_reads* reads, int k, const void* solid_dev, uint6
 int ga_build_unpaired_dna(const ga_reads* reads, int k, void* solid_dev, uint64_t solid_capacity,
                           uint64_t* node_stamp_dev, uint64_t* edge_stamp_dev, uint32_t* status_dev,
                           ga_stream stream);
+/* Two-phase variant for read sets whose id table does not fit the L2: after ga_build_unpaired_dna
+ * has run over a PREFIX of the reads, almost every node and edge already holds its final (earliest)
+ * stamp.  ga_unstamped_scan finds what is still open: mask_out_dev[id] = bit c set iff the
+ * successor of node id through symbol c is solid and edge (id, c) has no stamp yet (*n_open_dev =
+ * number of nodes with a non-zero mask; zeroed by the caller).  ga_unstamped_table_build puts
+ * those nodes in a small table (key -> id, mask) fronted by a blocked Bloom filter
+ * (bloom_dev: uint32 words, zero-filled).  ga_build_unpaired_dna_tail then walks the remaining
+ * reads: one Bloom probe (L2 resident) per window, and only the rare hits touch the tables. */
+int ga_unstamped_scan(const void* solid_dev, uint64_t solid_capacity, const void* solid_keys_dev,
+                      uint64_t n_solid, int key_words, const uint64_t* edge_stamp_dev, int k, int sym_bits,
+                      uint8_t* mask_out_dev, uint64_t* n_open_dev, ga_stream stream);
+int ga_unstamped_table_build(const void* solid_keys_dev, const uint8_t* mask_dev, uint64_t n_solid,
+                             int key_words, void* open_table_dev, uint64_t open_capacity,
+                             uint32_t* bloom_dev, uint64_t bloom_words, uint32_t* status_dev,
+                             ga_stream stream);
+int ga_build_unpaired_dna_tail(const ga_reads* reads, int k, const uint32_t* bloom_dev, uint64_t bloom_words,
+                               const void* open_table_dev, uint64_t open_capacity, const void* solid_dev,
+                               uint64_t solid_capacity, uint64_t* node_stamp_dev, uint64_t* edge_stamp_dev,
+                               ga_stream stream);
 /* Paired.  query table: key = idA << 32 | idB -> min stamp; query-edge table: key =
  * query_slot(P) << 32 | query_slot(S) -> min occurrence; dh_dev: 256*256*2 uint64 (0xFF filled),
  * the two smallest occurrences of "prefix pair == suffix pair" per (symbol A, symbol B)

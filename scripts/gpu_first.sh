@@ -7,5 +7,5 @@ timeout 1500 python -m pytest tests -m gpu -q --tb=short --durations=15 -p no:ca
     > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
+timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
 echo "bench exit $?"; cat gpurun_out/bench_c2.json; tail -5 gpurun_out/bench_c2.err

@@ -200,6 +200,16 @@ def test_against_c_oracle_random_dna():
             want.close()
 
 
+@pytest.mark.parametrize("name", ["nd-unpaired", "nd-unpaired-s1", "nd-unpaired-k41", "two-circles", "toy-unpaired"])
+def test_two_phase_build_matches_golden(name, monkeypatch):
+    """Prefix + Bloom-filtered tail (the route C4-sized inputs take) gives the same graph."""
+    import ga_device as gd
+    monkeypatch.setattr(gd, "TWO_PHASE_MIN_TABLE_BYTES", 0)
+    monkeypatch.setattr(gd, "TWO_PHASE_MIN_READS", 1)
+    monkeypatch.setattr(gd, "TWO_PHASE_MIN_STEP", 1)
+    check_against_gold(name, check_counts=False)
+
+
 def test_deterministic_across_runs():
     gold = GOLDEN["cases"]["nd-paired-jitter2"]
     reads = reads_for(gold["recipe"])
