@@ -68,6 +68,9 @@ SIGNATURES = {
     "ga_prefilter_update": (_i32, [_PR, _i32, _PF, _i64, _vp]),
     "ga_prefilter_hot": (_i32, [_PF, _i64, _vp, _vp]),
     "ga_count_candidates": (_i32, [_PR, _i32, _PF, _i64, _vp, _u64, _vp, _vp]),
+    "ga_partition_kmers": (_i32, [_PR, _i32, _u32, _vp, _u64, _vp, _vp, _vp]),
+    "ga_prefilter_update_keys": (_i32, [_vp, _u64, _PF, _i64, _vp]),
+    "ga_count_candidates_keys": (_i32, [_vp, _u64, _PF, _i64, _vp, _u64, _vp, _vp]),
     "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
     "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
     "ga_sketch_estimate_bytes": (_i32, [_vp, _vp, _u64, _PS, _vp, _vp]),

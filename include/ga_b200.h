@@ -160,6 +160,20 @@ int ga_prefilter_hot(const ga_prefilter* pf, int64_t threshold, uint64_t* n_hot_
 int ga_count_candidates(const ga_reads* reads, int k, const ga_prefilter* pf, int64_t threshold,
                         void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
 
+/* The same two passes over a hash-partitioned copy of the occurrence stream (64-bit keys), for read
+ * sets whose sketch and candidate table exceed the L2: ga_partition_kmers writes every window key
+ * into bucket floor(hash * n_parts / 2^64) (bucket b occupies items_dev[b*part_capacity ..],
+ * cursors_dev[b] = keys written, zeroed by the caller; GA_STATUS_TABLE_FULL if a bucket
+ * overflowed); the *_keys passes then take one bucket (or any key array) at a time. */
+int ga_partition_kmers(const ga_reads* reads, int k, uint32_t n_parts, uint64_t* items_dev,
+                       uint64_t part_capacity, uint64_t* cursors_dev, uint32_t* status_dev,
+                       ga_stream stream);
+int ga_prefilter_update_keys(const uint64_t* keys_dev, uint64_t n, const ga_prefilter* pf,
+                             int64_t threshold, ga_stream stream);
+int ga_count_candidates_keys(const uint64_t* keys_dev, uint64_t n, const ga_prefilter* pf,
+                             int64_t threshold, void* table_dev, uint64_t capacity,
+                             uint32_t* status_dev, ga_stream stream);
+
 /* ---- CountMinSketch: replaces countminsketch.py:34-44 and _make_sketch --------------------- */
 /* cells[row][murmur3(window) % width[row]] += count for every key of the count table
  * (debruijn_graph.py:181-188, 398-405).  lut_dev[256]: symbol code -> byte. */
