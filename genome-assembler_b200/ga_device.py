@@ -23,6 +23,11 @@ _DNA = b"ACGT"
 TWO_PHASE_MIN_TABLE_BYTES = 64 << 20    # id table + stamps beyond this no longer live in the L2
 TWO_PHASE_MIN_READS = 1 << 22
 TWO_PHASE_MIN_STEP = 1 << 20
+# bucketed (super-k-mer) count + build, csrc/ga_superkmer.cu: unpaired DNA, 64-bit keys
+SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
+SUPERKMER_TARGET = 16384                # windows per bucket aimed for
+SUPERKMER_TABLE_SLOTS = 16384           # shared-memory table slots per bucket (tests shrink it to force spills)
+SUPERKMER_MAX_SOLID = 1024              # solid windows per bucket held in shared memory
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
 
@@ -489,6 +494,114 @@ def sketch_struct(cells: torch.Tensor, widths) -> gn.GaSketch:
     return s
 
 
+# ----------------------------------------------------------------------------------- buckets
+def superkmer_supported(reads: "DeviceReads", k: int, threshold: int) -> bool:
+    """The bucketed path covers unpaired 2-bit reads whose windows fit 62 bits."""
+    if reads.paired or reads.alphabet.storage_bits != 2 or not 2 <= k <= 32:
+        return False
+    if not 0 <= threshold <= 60000:
+        return False
+    return (reads.first_read + reads.n_reads) * max(reads.estride, 1) < (1 << 47)
+
+
+def _record_groups(reads: "DeviceReads", w: int) -> int:
+    """Upper bound on the extra records caused by cutting runs at 32-window groups."""
+    if reads.lens is None:
+        return reads.n_reads * max(-(-max(reads.max_len - w + 1, 0) // 32), 0)
+    win = np.maximum(reads.lens - w + 1, 0)
+    return int((-(-win // 32)).sum())
+
+
+def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
+    """reads -> (solid keys (n, 1) int64, n, candidate edge stamps int64[4n]) through the bucketed
+    pipeline of csrc/ga_superkmer.cu: scatter records to level-1 buckets, split into final buckets,
+    count + stamp per bucket in shared memory.  Exact: same solid set and stamps as counting every
+    window in one table (debruijn_graph.py:144-152, 113-142)."""
+    L = gn.lib()
+    dev = _dev()
+    w = k - 1
+    n_occ = reads.windows_total(k)
+    m = L.ga_sk_minimizer_len(k)
+    per_window = w - m + 1
+    bits = 0
+    while bits < 20 and (n_occ >> bits) > SUPERKMER_TARGET:
+        bits += 1
+    l2_bits = min(10, bits)
+    l1_bits = bits - l2_bits
+    n_l1, n_buckets = 1 << l1_bits, 1 << bits
+    status = reads.status
+    est = int(n_occ * 2.0 / (per_window + 1)) + _record_groups(reads, w)
+    cap1 = int(est / n_l1 * 1.15) + 4096
+    while True:
+        rec_bases = torch.empty(n_l1 * cap1 * 2, dtype=torch.int64, device=dev)
+        rec_meta = torch.empty(n_l1 * cap1, dtype=torch.int64, device=dev)
+        cursors1 = torch.zeros(n_l1, dtype=torch.int64, device=dev)
+        hist = torch.zeros(n_buckets, dtype=torch.int32, device=dev)
+        status.zero_()
+        with _timed("sk_scatter1", n_occ):
+            gn.check(L.ga_sk_scatter_reads(C.byref(reads.struct()), k, l1_bits, l2_bits, gn.ptr(rec_bases),
+                                           gn.ptr(rec_meta), cap1, gn.ptr(cursors1), gn.ptr(hist), gn.ptr(status),
+                                           _stream()))
+        offsets = torch.empty(n_buckets + 1, dtype=torch.int64, device=dev)
+        cursors2 = torch.empty(n_buckets, dtype=torch.int64, device=dev)
+        gn.check(L.ga_sk_offsets(gn.ptr(hist), n_buckets, gn.ptr(offsets), gn.ptr(cursors2), _stream()))
+        total = int(offsets[n_buckets].item())
+        if not _check_status(status) & gn.ST_TABLE_FULL:
+            break
+        cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
+        del rec_bases, rec_meta
+    _mark("sk scatter reads")
+    bases = torch.empty(max(total, 1) * 2, dtype=torch.int64, device=dev)
+    meta = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    with _timed("sk_scatter2", n_occ):
+        gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits, l2_bits,
+                                         gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), _stream()))
+    del rec_bases, rec_meta
+    _mark("sk scatter buckets")
+    free, _ = torch.cuda.mem_get_info()
+    out_cap = max(1 << 16, min(n_occ // 16 + 1024, int(free * 0.5) // 40))
+    spill_cap = 1 << 16
+    while True:
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        spill_list = torch.empty(spill_cap, dtype=torch.int32, device=dev)
+        solid_keys = torch.empty((out_cap, 1), dtype=torch.int64, device=dev)
+        edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
+        status.zero_()
+        with _timed("sk_bucket", n_occ):
+            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_buckets, k, int(threshold),
+                                         SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
+                                         gn.ptr(edge_stamp), out_cap, gn.ptr(counters), gn.ptr(spill_list), spill_cap,
+                                         gn.ptr(status), _stream()))
+        _, n_solid, n_spill, _ = (int(v) for v in counters.cpu().tolist())
+        if n_spill > spill_cap:
+            spill_cap = n_spill
+            continue
+        if n_spill:
+            ids = spill_list[:n_spill].long()
+            records = int((offsets[ids + 1] - offsets[ids]).max().item())
+            slots = 256
+            while slots < 2 * 32 * records:
+                slots <<= 1
+            per_cta = int(L.ga_sk_spill_scratch_bytes(slots))
+            free, _ = torch.cuda.mem_get_info()
+            n_ctas = max(1, min(n_spill, 148, int(free * 0.4) // per_cta))
+            scratch = torch.empty(n_ctas * per_cta, dtype=torch.uint8, device=dev)
+            with _timed("sk_bucket_spill"):
+                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), gn.ptr(spill_list),
+                                                   n_spill, k, int(threshold), slots, gn.ptr(scratch), n_ctas,
+                                                   gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
+                                                   gn.ptr(status), _stream()))
+            n_solid = int(counters[1].item())
+            del scratch
+        if _check_status(status) & gn.ST_TABLE_FULL:
+            raise gn.GaError("bucketed count: a spilled bucket overflowed its scratch table")
+        if n_solid <= out_cap:
+            break
+        out_cap = n_solid
+    _mark("sk bucket pass")
+    return solid_keys, n_solid, edge_stamp
+
+
 # ----------------------------------------------------------------------------------- build
 class BuiltGraph:
     """The CSR contract of SURVEY App. C.3 on the host."""
@@ -572,7 +685,12 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     k, w, kw = counts.k, counts.w, counts.key_words
     alphabet = reads.alphabet
     graph = BuiltGraph(reads.paired, w, alphabet, kw)
-    if keep_fn is not None:
+    bucketed = (keep_fn is None and sketch is None and counts._table is None and not counts._cand and
+                counts.n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(reads, k, threshold))
+    edge_stamp = None
+    if bucketed:
+        solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold)
+    elif keep_fn is not None:
         solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
     else:
         solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
@@ -593,8 +711,13 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     if dna4:
         # <= 4 symbols: per-node edge stamps, epoch-tagged slots (ga_build_unpaired_dna)
         node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
-        edge_stamp = torch.full((4 * n_solid,), -1, dtype=torch.int64, device=dev)
-        build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status)
+        if bucketed:
+            with _timed("sk_resolve"):
+                gn.check(L.ga_sk_resolve(gn.ptr(solid_keys), n_solid, k, gn.ptr(solid), solid_cap, gn.ptr(edge_stamp),
+                                         gn.ptr(node_stamp), _stream()))
+        else:
+            edge_stamp = torch.full((4 * n_solid,), -1, dtype=torch.int64, device=dev)
+            build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status)
         _mark("fill stamps + build_dna")
         gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
                                             kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),

@@ -174,6 +174,54 @@ int ga_count_candidates_keys(const uint64_t* keys_dev, uint64_t n, const ga_pref
                              int64_t threshold, void* table_dev, uint64_t capacity,
                              uint32_t* status_dev, ga_stream stream);
 
+/* ---- bucketed count + build (unpaired DNA reads, 64-bit keys): replaces BOTH hot loops,
+ *      _count_kmers (debruijn_graph.py:144-152) and _build_graph (:113-142), without one random
+ *      global-memory access per occurrence (csrc/ga_superkmer.cu) ------------------ */
+/* m-mer length used to pick a window's bucket for --kmer_length k */
+int ga_sk_minimizer_len(int k);
+/* Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases in
+ * rec_bases_dev + one meta word in rec_meta_dev) and scatter them to 2^l1_bits level-1 buckets of
+ * l1_capacity records each (bucket b at index b*l1_capacity; l1_cursors_dev[b] = records written,
+ * zeroed by the caller).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) counts records per
+ * final bucket.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed, retry with a larger capacity. */
+int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* rec_bases_dev,
+                        uint64_t* rec_meta_dev, uint64_t l1_capacity, uint64_t* l1_cursors_dev,
+                        uint32_t* hist_dev, uint32_t* status_dev, ga_stream stream);
+/* offsets_dev[n_buckets+1] = exclusive prefix sum of hist_dev; cursors_dev[n_buckets] = a copy */
+int ga_sk_offsets(const uint32_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
+                  uint64_t* cursors_dev, ga_stream stream);
+/* level-1 buckets -> final buckets, densely packed at offsets_dev (cursors_dev is consumed) */
+int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
+                          const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
+                          void* out_bases_dev, uint64_t* out_meta_dev, ga_stream stream);
+/* One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots; every
+ * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
+ * stamps (edge_stamp_out_dev[4*i + c] = smallest occurrence ordinal of "window i followed by symbol
+ * c", all-ones if never).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
+ * windows found (may exceed out_capacity: nothing is written beyond it, the caller retries with
+ * that many), [2] buckets that did not fit and were listed in spill_list_dev. */
+int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                      uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
+                      uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                      uint64_t out_capacity, uint64_t* counters_dev, uint32_t* spill_list_dev,
+                      uint64_t spill_capacity, uint32_t* status_dev, ga_stream stream);
+/* The listed buckets again with tables in global scratch (n_ctas slices of
+ * ga_sk_spill_scratch_bytes(table_slots) bytes; table_slots >= twice the windows of the largest). */
+uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots);
+int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                            const uint32_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                            uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
+                            uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                            uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
+                            ga_stream stream);
+/* Candidate stamps -> the reference's graph: clears edge_stamp_dev[4*i + c] when the successor of
+ * window i through c is not solid (solid_dev: id table over solid_keys_dev, id = index) and folds
+ * 2e / 2e+1 into node_stamp_dev[n_solid] (0xFF filled by the caller).  The arrays then feed
+ * ga_csr_plan_unpaired_dna. */
+int ga_sk_resolve(const uint64_t* solid_keys_dev, uint64_t n_solid, int k, const void* solid_dev,
+                  uint64_t solid_capacity, uint64_t* edge_stamp_dev, uint64_t* node_stamp_dev,
+                  ga_stream stream);
+
 /* ---- CountMinSketch: replaces countminsketch.py:34-44 and _make_sketch --------------------- */
 /* cells[row][murmur3(window) % width[row]] += count for every key of the count table
  * (debruijn_graph.py:181-188, 398-405).  lut_dev[256]: symbol code -> byte. */
