@@ -55,10 +55,9 @@ __device__ __forceinline__ u64 meta_ordinal(u64 meta) { return meta >> 16; }
 
 // ------------------------------------------------------------------------------------------------
 // 1. reads -> records in level-1 buckets
-constexpr int S1_THREADS = 256;
+constexpr int S1_THREADS = 512;
 constexpr int S1_WARPS = S1_THREADS / 32;
-constexpr u32 S1_STAGE = 3072;                 // records staged per CTA between flushes
-constexpr u32 S1_MARGIN = S1_WARPS * 128;      // most records one round can add
+constexpr u32 S1_STAGE = 3072;                 // records staged per CTA between flushes (>= S1_WARPS * 128)
 constexpr u32 S1_MAXB = 1024;                  // level-1 buckets
 
 struct S1Shared {
@@ -68,19 +67,19 @@ struct S1Shared {
     u64 gbase[S1_MAXB];
     u32 hist[S1_MAXB];
     u64 words[S1_WARPS][8];
-    u32 count;
+    u32 desc[S1_WARPS][128];       // records of the current chunk: position | (windows-1) << 7 | bucket << 12
+    u32 wcount[S1_WARPS];
 };
 
-__device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n_l1, ulonglong2* __restrict__ out_bases,
+__device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n, u32 n_l1, ulonglong2* __restrict__ out_bases,
                                          u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors,
                                          bool& overflow) {
     __syncthreads();
-    const u32 n = sm.count;
     for (u32 p = threadIdx.x; p < n_l1; p += S1_THREADS) {
         const u32 c = sm.hist[p];
         u64 base = 0;
         if (c) {
-            base = atomicAdd(&cursors[p], (u64)c);
+            base = atomicAdd((unsigned long long*)&cursors[p], (unsigned long long)c);
             if (base + c > cap1) {
                 overflow = true;
                 base = GA_NONE64;      // dropped: the host retries with larger buckets
@@ -100,15 +99,14 @@ __device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n_l1, ulonglong2* __r
         out_meta[dst] = sm.meta[i];
     }
     __syncthreads();
-    if (threadIdx.x == 0) sm.count = 0;
-    __syncthreads();
 }
 
-// One warp per read and round; lanes own window positions lane, lane+32, lane+64, lane+96 of the
-// current 128-window chunk.
+// One warp per read and round.  Lane l owns the four consecutive window positions 4l..4l+3 of the
+// current 128-window chunk, so the sliding minimum over a window's m-mers needs the lane's own
+// values plus whole-lane minima of up to three following lanes and a prefix of one more.
 __global__ void __launch_bounds__(S1_THREADS)
 sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ulonglong2* __restrict__ out_bases,
-                        u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors, u32* __restrict__ ghist,
+                        u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors, u64* __restrict__ ghist,
                         u32* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sm = *reinterpret_cast<S1Shared*>(smem_raw);
@@ -116,12 +114,11 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
     const u32 n_l1 = 1u << l1_bits;
     const int bits = l1_bits + l2_bits;
     const u32 n = (u32)(w - m + 1);                       // m-mers per window, 1..16
-    u32 P = 1;
-    while (P * 2 <= n) P *= 2;
     const u32 mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const u32 lt_mask = (1u << lane) - 1u;
     bool overflow = false;
+    u32 staged = 0;                                       // records in the stage; identical in every thread
     for (u32 p = threadIdx.x; p < n_l1; p += S1_THREADS) sm.hist[p] = 0;
-    if (threadIdx.x == 0) sm.count = 0;
     __syncthreads();
 
     const u64 n_tiles = (rv.n_reads + S1_WARPS - 1) / S1_WARPS;
@@ -137,87 +134,145 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
         for (u32 c = 0;; ++c) {
             const bool more = c < nch;
             if (!__syncthreads_or(more)) break;
+            u32 mycount = 0;
+            const u32 base_word = c * 4u;
+            const u64* sw = sm.words[warp];
+            auto get64 = [&](u32 pos) -> u64 {           // 32 symbols from symbol `pos` on, symbol 0 in the low bits
+                const u32 wi = (pos >> 5) - base_word, sh = (pos & 31u) * 2u;
+                const u64 lo = sw[wi], hi = sw[wi + 1];
+                return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+            };
             if (more) {
-                const u32 base_word = c * 4u;
                 if (lane < 8u) {
                     const u32 wi = base_word + lane;
                     sm.words[warp][lane] = wi < n_words ? __ldg(rp + wi) : 0ull;
                 }
                 __syncwarp();
-                const u64* sw = sm.words[warp];
-                auto get64 = [&](u32 pos) -> u64 {       // 32 symbols from symbol `pos` on, symbol 0 in the low bits
-                    const u32 wi = (pos >> 5) - base_word, sh = (pos & 31u) * 2u;
-                    const u64 lo = sw[wi], hi = sw[wi + 1];
-                    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-                };
-                u32 v[5];
+                // m-mer hashes: v[t] at position 4*lane + t, ov[t] at 128 + 4*lane + t (lanes 0..3 matter)
+                const u32 q0 = c * 128u + 4u * lane;
+                u32 v[4], ov[4];
+                {
+                    const u64 x = get64(q0);
+                    const u64 y = lane < 4u ? get64(q0 + 128u) : 0ull;
 #pragma unroll
-                for (int t = 0; t < 5; ++t) {
-                    const u32 q = c * 128u + 32u * t + lane;
-                    v[t] = q + (u32)m <= len ? sk_hash32((u32)get64(q) & mmask) : 0xFFFFFFFFu;
-                }
-                auto shifted = [&](u32 a, u32 b, u32 s) -> u32 {
-                    const u32 src = (lane + s) & 31u;
-                    const u32 x = __shfl_sync(FULL, a, src), y = __shfl_sync(FULL, b, src);
-                    return lane + s < 32u ? x : y;
-                };
-                for (u32 s = 1; s < P; s <<= 1) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) v[t] = min(v[t], shifted(v[t], v[t + 1], s));
-                    v[4] = min(v[4], shifted(v[4], 0xFFFFFFFFu, s));
-                }
-                if (n > P) {
-                    const u32 s = n - P;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) v[t] = min(v[t], shifted(v[t], v[t + 1], s));
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const u32 p = c * 128u + 32u * t + lane;
-                    const bool vw = p < nwt;
-                    // the minimum of n hashes crowds near zero: hash it again before taking bucket bits
-                    const u32 b = bits ? sk_hash32(v[t] ^ 0x5bd1e995u) >> (32 - bits) : 0u;
-                    const u32 prevb = __shfl_up_sync(FULL, b, 1);
-                    const bool start = vw && (lane == 0u || b != prevb);
-                    const u32 flags = __ballot_sync(FULL, start);
-                    const u32 nvalid = __popc(__ballot_sync(FULL, vw));
-                    if (flags == 0u) continue;
-                    u32 base = 0;
-                    if (lane == 0u) base = atomicAdd(&sm.count, (u32)__popc(flags));
-                    base = __shfl_sync(FULL, base, 0);
-                    if (start) {
-                        const u32 higher = flags & ~((2u << lane) - 1u);
-                        const u32 nxt = higher ? (u32)__ffs(higher) - 1u : 32u;
-                        const u32 nwin = min(nxt, nvalid) - lane;
-                        const u32 idx = base + __popc(flags & ((1u << lane) - 1u));
-                        const u64 hi = sk_rev2(get64(p)), lo = sk_rev2(get64(p + 32u));
-                        const u32 has_next = p + nwin - 1u + (u32)w < len ? 1u : 0u;
-                        const u32 b1 = b >> l2_bits, b2 = b & ((1u << l2_bits) - 1u);
-                        const u32 rank = atomicAdd(&sm.hist[b1], 1u);
-                        atomicAdd(&ghist[b], 1u);
-                        sm.bases[idx] = make_ulonglong2(hi, lo);
-                        sm.meta[idx] = ((e_read + p) << 16) | ((u64)b2 << 6) | ((u64)has_next << 5) | (u64)(nwin - 1u);
-                        sm.br[idx] = (b1 << 16) | rank;
+                    for (int t = 0; t < 4; ++t) {
+                        v[t] = q0 + t + (u32)m <= len ? sk_hash32((u32)(x >> (2 * t)) & mmask) : 0xFFFFFFFFu;
+                        ov[t] = (lane < 4u && q0 + 128u + t + (u32)m <= len) ? sk_hash32((u32)(y >> (2 * t)) & mmask)
+                                                                             : 0xFFFFFFFFu;
                     }
                 }
+                auto fetch = [&](u32 a, u32 b, u32 d) -> u32 {      // value of lane + d, continuing into the overflow lanes
+                    const u32 src = (lane + d) & 31u;
+                    const u32 x = __shfl_sync(FULL, a, src), y = __shfl_sync(FULL, b, src);
+                    return lane + d < 32u ? x : y;
+                };
+                const u32 m4 = min(min(v[0], v[1]), min(v[2], v[3]));
+                const u32 m4o = min(min(ov[0], ov[1]), min(ov[2], ov[3]));
+                const u32 c1 = fetch(m4, m4o, 1), c2 = min(c1, fetch(m4, m4o, 2)), c3 = min(c2, fetch(m4, m4o, 3));
+                const u32 p1 = v[0], p2 = min(v[0], v[1]), p3 = min(p2, v[2]);          // prefix minima
+                const u32 p1o = ov[0], p2o = min(ov[0], ov[1]), p3o = min(p2o, ov[2]);
+                u32 bkt[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const u32 end = (u32)t + n;              // m-mer positions t .. end-1 relative to 4*lane
+                    u32 res = v[t];
+#pragma unroll
+                    for (int u = t + 1; u < 4; ++u)
+                        if ((u32)u < end) res = min(res, v[u]);
+                    if (end > 4u) {
+                        const u32 f = (end - 4u) >> 2, rem = (end - 4u) & 3u;
+                        if (f >= 1u) res = min(res, f == 1u ? c1 : (f == 2u ? c2 : c3));
+                        if (rem) {
+                            const u32 a = rem == 1u ? p1 : (rem == 2u ? p2 : p3);
+                            const u32 b = rem == 1u ? p1o : (rem == 2u ? p2o : p3o);
+                            res = min(res, fetch(a, b, f + 1u));
+                        }
+                    }
+                    // the minimum of n hashes crowds near zero: hash it again before taking bucket bits
+                    bkt[t] = bits ? sk_hash32(res ^ 0x5bd1e995u) >> (32 - bits) : 0u;
+                }
+                // record starts: bucket change, or a multiple of 32 windows (records hold at most 32)
+                const u32 nvalid = min(nwt - c * 128u, 128u);
+                const u32 prev3 = __shfl_up_sync(FULL, bkt[3], 1);
+                bool st[4];
+                u32 F[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const bool vw = 4u * lane + t < nvalid;
+                    const bool change = t == 0 ? ((lane & 7u) == 0u || bkt[0] != prev3) : bkt[t] != bkt[t - 1];
+                    st[t] = vw && change;
+                    F[t] = __ballot_sync(FULL, st[t]);
+                }
+                const u32 any = F[0] | F[1] | F[2] | F[3];
+                const u32 higher = any & ~((2u << lane) - 1u);
+                u32 next_lane = 128u;                        // first start in a later lane
+                if (higher) {
+                    const u32 l2 = (u32)__ffs(higher) - 1u;
+                    const u32 t2 = (F[0] >> l2) & 1u ? 0u : ((F[1] >> l2) & 1u ? 1u : ((F[2] >> l2) & 1u ? 2u : 3u));
+                    next_lane = 4u * l2 + t2;
+                }
+                u32 off = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (st[t]) {
+                        u32 next = next_lane;
+#pragma unroll
+                        for (int u = 3; u > t; --u)
+                            if (st[u]) next = 4u * lane + u;
+                        const u32 prel = 4u * lane + t;
+                        const u32 nwin = min(next, nvalid) - prel;
+                        sm.desc[warp][off + __popc(F[t] & lt_mask)] = prel | ((nwin - 1u) << 7) | (bkt[t] << 12);
+                    }
+                    off += __popc(F[t]);
+                }
+                mycount = off;
             }
+            if (lane == 0u) sm.wcount[warp] = mycount;
             __syncthreads();
-            if (sm.count > S1_STAGE - S1_MARGIN) s1_flush(sm, n_l1, out_bases, out_meta, cap1, cursors, overflow);
+            // deterministic reservation: every thread computes the same prefix over the warps
+            u32 mine = lane < (u32)S1_WARPS ? sm.wcount[lane] : 0u;
+            u32 incl = mine;
+#pragma unroll
+            for (int o = 1; o < S1_WARPS; o <<= 1) {
+                const u32 t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (u32)o) incl += t;
+            }
+            const u32 total = __shfl_sync(FULL, incl, S1_WARPS - 1);
+            const u32 my_base = __shfl_sync(FULL, incl - mine, warp);
+            if (staged + total > S1_STAGE) {
+                s1_flush(sm, staged, n_l1, out_bases, out_meta, cap1, cursors, overflow);
+                staged = 0;
+            }
+            for (u32 l = lane; l < mycount; l += 32u) {
+                const u32 d = sm.desc[warp][l];
+                const u32 prel = d & 127u, nwin = ((d >> 7) & 31u) + 1u, b = d >> 12;
+                const u32 p = c * 128u + prel;
+                const u64 hi = sk_rev2(get64(p)), lo = sk_rev2(get64(p + 32u));
+                const u32 has_next = p + nwin - 1u + (u32)w < len ? 1u : 0u;
+                const u32 b1 = b >> l2_bits, b2 = b & ((1u << l2_bits) - 1u);
+                const u32 rank = atomicAdd(&sm.hist[b1], 1u);
+                atomicAdd((unsigned long long*)&ghist[b], (1ull << 32) | (unsigned long long)nwin);
+                const u32 idx = staged + my_base + l;
+                sm.bases[idx] = make_ulonglong2(hi, lo);
+                sm.meta[idx] = ((e_read + p) << 16) | ((u64)b2 << 6) | ((u64)has_next << 5) | (u64)(nwin - 1u);
+                sm.br[idx] = (b1 << 16) | rank;
+            }
+            staged += total;
         }
     }
-    s1_flush(sm, n_l1, out_bases, out_meta, cap1, cursors, overflow);
+    s1_flush(sm, staged, n_l1, out_bases, out_meta, cap1, cursors, overflow);
     if (overflow) atomicOr(status, GA_ST_TABLE_FULL);
 }
 
 // ------------------------------------------------------------------------------------------------
 // 2. histogram -> offsets; level-1 buckets -> final buckets
-__global__ void __launch_bounds__(1024) sk_offsets_kernel(const u32* __restrict__ hist, u64 n, u64* __restrict__ offsets,
+__global__ void __launch_bounds__(1024) sk_offsets_kernel(const u64* __restrict__ hist, u64 n, u64* __restrict__ offsets,
                                                           u64* __restrict__ cursors) {
     __shared__ u64 part[1024];
     const u64 span = (n + 1023) / 1024;
     const u64 lo = min(n, threadIdx.x * span), hi = min(n, lo + span);
     u64 sum = 0;
-    for (u64 i = lo; i < hi; ++i) sum += hist[i];
+    for (u64 i = lo; i < hi; ++i) sum += hist[i] >> 32;
     part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -234,7 +289,7 @@ __global__ void __launch_bounds__(1024) sk_offsets_kernel(const u32* __restrict_
     for (u64 i = lo; i < hi; ++i) {
         offsets[i] = run;
         cursors[i] = run;
-        run += hist[i];
+        run += hist[i] >> 32;
     }
 }
 
@@ -292,34 +347,97 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
 
 // ------------------------------------------------------------------------------------------------
 // 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps
+//
+// Work is flattened per warp: each lane loads one record, the warp prefix-sums the window counts and
+// then walks the windows of its 32 records 32 at a time, so every lane probes an independent window
+// (full lanes, no serial key roll, balanced warps).  Table, counters and stamps live in shared
+// memory and are addressed with explicit ld/atom.shared.
 constexpr int SB_THREADS = 1024;
 constexpr u32 SB_MAX_SLOTS = 16384;
-constexpr u32 SB_MAX_SOLID = 1024;
+constexpr u32 SB_POOL_BYTES = 212992;          // 208 KB of dynamic shared memory: table + solid keys + stamps
 constexpr u32 SB_PROBE_MAX = 192;
 
 __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
-    u64 h = key * 0x9E3779B97F4A7C15ull;
-    h ^= h >> 29;
-    h *= 0xBF58476D1CE4E5B9ull;
-    return (u32)(h >> 36);
+    u32 h = (u32)key * 0x9E3779B1u ^ (u32)(key >> 32) * 0x85EBCA77u;
+    h ^= h >> 15;
+    return h * 0xC2B2AE3Du;                     // use the TOP bits
 }
 
-// counts: SM = true packs two 16-bit counters per word (shared memory is the scarce resource),
-// SM = false (spill path, global scratch) uses one 32-bit word per slot
-template <bool SM> __device__ __forceinline__ u32 cnt_get(const u32* cnt, u32 s) {
-    if (SM) return (((const volatile u32*)cnt)[s >> 1] >> ((s & 1u) * 16u)) & 0xFFFFu;
-    return ((const volatile u32*)cnt)[s];
-}
-template <bool SM> __device__ __forceinline__ void cnt_add(u32* cnt, u32 s) {
-    if (SM) atomicAdd(cnt + (s >> 1), 1u << ((s & 1u) * 16u));
-    else atomicAdd(cnt + s, 1u);
-}
+// ---- table access, shared-memory flavour (byte addresses in the shared window) and global flavour
+struct TabShared {
+    static constexpr bool kPacked = true;       // two 16-bit counters per word
+    u32 keys, cnt, skeys, stamps;               // shared byte addresses
+    __device__ __forceinline__ u64 key_ld(u32 s) const {
+        u64 v;
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(keys + 8u * s));
+        return v;
+    }
+    __device__ __forceinline__ void key_st(u32 s, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(keys + 8u * s), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ u64 key_cas(u32 s, u64 val) const {
+        u64 old;
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(keys + 8u * s), "l"(GA_NONE64), "l"(val) : "memory");
+        return old;
+    }
+    // two 16-bit counters per word
+    __device__ __forceinline__ u32 word_ld(u32 wi) const {
+        u32 v;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(cnt + 4u * wi));
+        return v;
+    }
+    __device__ __forceinline__ void word_st(u32 wi, u32 v) const {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt + 4u * wi), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ u32 cnt_get(u32 s) const { return (word_ld(s >> 1) >> ((s & 1u) * 16u)) & 0xFFFFu; }
+    __device__ __forceinline__ void cnt_add(u32 s) const {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
+    }
+    __device__ __forceinline__ u32 cnt_words(u32 cap) const { return cap >> 1; }
+    __device__ __forceinline__ void skey_st(u32 i, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(skeys + 8u * i), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ u64 skey_ld(u32 i) const {
+        u64 v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(skeys + 8u * i));
+        return v;
+    }
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const {
+        u64 v;
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(stamps + 8u * i));
+        return v;
+    }
+    __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
+        asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
+    }
+};
 
-struct BucketMem {
-    u64* keys;        // [cap]
-    u32* cnt;         // SM: [cap / 2], else [cap]
-    u64* solid_keys;  // [max_solid]
-    u64* stamps;      // [max_solid * 4]
+struct TabGlobal {
+    static constexpr bool kPacked = false;
+    u64* keys;
+    u32* cnt;                                   // one 32-bit counter per slot
+    u64* skeys;
+    u64* stamps;
+    __device__ __forceinline__ u64 key_ld(u32 s) const { return ((volatile u64*)keys)[s]; }
+    __device__ __forceinline__ void key_st(u32 s, u64 v) const { keys[s] = v; }
+    __device__ __forceinline__ u64 key_cas(u32 s, u64 val) const {
+        return atomicCAS((unsigned long long*)(keys + s), GA_NONE64, val);
+    }
+    __device__ __forceinline__ u32 word_ld(u32 wi) const { return ((volatile u32*)cnt)[wi]; }
+    __device__ __forceinline__ void word_st(u32 wi, u32 v) const { cnt[wi] = v; }
+    __device__ __forceinline__ u32 cnt_get(u32 s) const { return word_ld(s); }
+    __device__ __forceinline__ void cnt_add(u32 s) const { atomicAdd(cnt + s, 1u); }
+    __device__ __forceinline__ u32 cnt_words(u32 cap) const { return cap; }
+    __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
+    __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { stamps[i] = v; }
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return ((volatile u64*)stamps)[i]; }
+    __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
+        atomicMin((unsigned long long*)(stamps + i), (unsigned long long)v);
+    }
 };
 
 struct BucketCtl {     // shared-memory control block of one CTA
@@ -327,106 +445,141 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u32 overflow;
     u32 bucket;
     u32 pad;
-    u64 n_windows;
     u64 out_base;
 };
 
-// returns false when the bucket does not fit (cap / max_solid): the caller lists it for the spill path
-template <bool SM>
-__device__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, u64 lo, u64 hi,
-                               int w, u32 threshold, BucketMem mem, u32 cap_limit, u32 max_solid, BucketCtl& ctl,
-                               u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
-                               u64* n_solid_global) {
-    const u32 tid = threadIdx.x, T = blockDim.x;
-    const u64 mask = ga_key_mask<u64>(w, 2);
-    // A. windows in the bucket -> table size
-    u64 nw = 0;
-    for (u64 i = lo + tid; i < hi; i += T) nw += meta_windows(meta[i]);
-    for (int off = 16; off > 0; off >>= 1) nw += __shfl_down_sync(FULL, nw, off);
+__device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
+    const u32 lo = __shfl_sync(FULL, (u32)v, src), hi = __shfl_sync(FULL, (u32)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+
+// One batch = 32 records (one per lane) of the bucket.  f(top64, j, owner fields...) is called once
+// per window with all lanes converged between calls: `top` holds the window's symbols from bit 63
+// down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal and
+// `follows` whether a next symbol exists.  WITH_META = false skips the meta shuffles (count phase).
+template <bool WITH_META, class F>
+__device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 nwin = have ? meta_windows(meta) : 0u;
+    u32 incl = nwin;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 t = __shfl_up_sync(FULL, incl, off);
+        if (lane >= (u32)off) incl += t;
+    }
+    const u32 start = incl - nwin;
+    const u32 total = __shfl_sync(FULL, incl, 31);
+    const u32 le_mask = 0xFFFFFFFFu >> (31u - lane);
+    for (u32 xb = 0; xb < total; xb += 32u) {
+        const u32 before = __popc(__ballot_sync(FULL, start < xb));
+        const u32 bit = (nwin && start >= xb && start < xb + 32u) ? 1u << (start - xb) : 0u;
+        const u32 marks = __reduce_or_sync(FULL, bit);
+        const u32 x = xb + lane;
+        const bool active = x < total;
+        const u32 owner = active ? before + __popc(marks & le_mask) - 1u : 0u;
+        const u32 j = x - __shfl_sync(FULL, start, owner);
+        const u64 ohi = shfl64(rhi, owner), olo = shfl64(rlo, owner);
+        u64 ord = 0;
+        bool follows = false;
+        if (WITH_META) {
+            const u64 om = shfl64(meta, owner);
+            ord = meta_ordinal(om) + j;
+            follows = j + 1u < meta_windows(om) || meta_has_next(om);
+        }
+        if (active) {
+            const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
+            f(top, ord, follows);
+        }
+        __syncwarp();
+    }
+}
+
+// returns false when the bucket does not fit: the caller lists it for the spill path
+template <class Tab>
+__device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
+                                               u64 lo, u64 hi, int w, u32 threshold, const Tab& tab, u32 cap,
+                                               u32 max_solid, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
+                                               u64* __restrict__ edge_stamp_out, u64 out_capacity,
+                                               u64* n_solid_global) {
+    const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
+    const u32 lg = 31u - (u32)__clz(cap);
+    const u32 cmask = cap - 1u;
+    const u32 kshift = 64u - 2u * (u32)w;
+    const u64 nrec = hi - lo;
+    const u64 n_batches = (nrec + 31u) / 32u;
+    // B. clear
+    for (u32 s = tid; s < cap; s += T) tab.key_st(s, GA_NONE64);
+    for (u32 s = tid; s < tab.cnt_words(cap); s += T) tab.word_st(s, 0u);
     if (tid == 0) {
-        ctl.n_windows = 0;
         ctl.n_solid = 0;
         ctl.overflow = 0;
     }
     __syncthreads();
-    if ((tid & 31u) == 0 && nw) atomicAdd((unsigned long long*)&ctl.n_windows, (unsigned long long)nw);
-    __syncthreads();
-    nw = ctl.n_windows;
-    u32 cap = 256;
-    while (cap < cap_limit && (u64)cap < 2 * nw) cap <<= 1;
-    const u32 cmask = cap - 1u;
-    // B. clear
-    for (u32 s = tid; s < cap; s += T) mem.keys[s] = GA_NONE64;
-    for (u32 s = tid; s < (SM ? cap / 2 : cap); s += T) mem.cnt[s] = 0;
-    __syncthreads();
-    volatile u64* vkeys = mem.keys;
     volatile u32* vovf = &ctl.overflow;
     // C. count (saturating just above the threshold: only "count > threshold" is asked)
-    for (u64 i = lo + tid; i < hi && !*vovf; i += T) {
-        const ulonglong2 b = bases[i];
-        const u32 nwin = meta_windows(meta[i]);
-        u64 key = b.x >> (64 - 2 * w);
-        for (u32 j = 0; j < nwin; ++j) {
-            u32 s = sk_slot_hash(key) & cmask;
+    for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
+        const u64 i = lo + bt * 32u + lane;
+        const bool have = i < hi;
+        ulonglong2 b = make_ulonglong2(0, 0);
+        u64 mt = 0;
+        if (have) {
+            b = bases[i];
+            mt = meta[i];
+        }
+        sk_for_each_window<false>(b.x, b.y, mt, have, [&](u64 top, u64, bool) {
+            const u64 key = top >> kshift;
+            u32 s = sk_slot_hash(key) >> (32u - lg);
             u32 probes = 0;
             for (;;) {
-                const u64 cur = vkeys[s];
+                const u64 cur = tab.key_ld(s);
                 if (cur == key) break;
                 if (cur == GA_NONE64) {
-                    const u64 old = atomicCAS((unsigned long long*)(mem.keys + s), GA_NONE64, key);
+                    const u64 old = tab.key_cas(s, key);
                     if (old == GA_NONE64 || old == key) break;
                 }
                 if (++probes > SB_PROBE_MAX) {
-                    s = GA_NONE32;
-                    break;
+                    *vovf = 1u;
+                    return;
                 }
                 s = (s + 1u) & cmask;
             }
-            if (s == GA_NONE32) {
-                *vovf = 1u;
-                break;
-            }
-            if (cnt_get<SM>(mem.cnt, s) <= threshold) cnt_add<SM>(mem.cnt, s);
-            const u32 idx = (u32)w + j;
-            const u64 word = idx < 32u ? b.x : b.y;
-            key = ((key << 2) | ((word >> (62u - 2u * (idx & 31u))) & 3ull)) & mask;
-        }
+            if (tab.cnt_get(s) <= threshold) tab.cnt_add(s);
+        });
     }
     __syncthreads();
     if (ctl.overflow) return false;
-    // D. solid windows: counter word -> solid index + 1 (0 = not solid)
-    if (SM) {
+    // D. solid windows: counter -> solid index + 1 (0 = not solid)
+    if (Tab::kPacked) {
         for (u32 wi = tid; wi < cap / 2; wi += T) {
-            const u32 word = mem.cnt[wi];
-            const u32 c0 = word & 0xFFFFu, c1 = word >> 16;
-            const u32 s0 = c0 > threshold, s1 = c1 > threshold;
+            const u32 word = tab.word_ld(wi);
+            const u32 s0 = (word & 0xFFFFu) > threshold, s1 = (word >> 16) > threshold;
             u32 neu = 0;
             if (s0 + s1) {
                 const u32 base = atomicAdd(&ctl.n_solid, s0 + s1);
                 if (base + s0 + s1 <= max_solid) {
                     if (s0) {
-                        mem.solid_keys[base] = mem.keys[2 * wi];
+                        tab.skey_st(base, tab.key_ld(2 * wi));
                         neu |= base + 1u;
                     }
                     if (s1) {
-                        mem.solid_keys[base + s0] = mem.keys[2 * wi + 1];
+                        tab.skey_st(base + s0, tab.key_ld(2 * wi + 1));
                         neu |= (base + s0 + 1u) << 16;
                     }
                 }
             }
-            mem.cnt[wi] = neu;
+            tab.word_st(wi, neu);
         }
     } else {
         for (u32 s = tid; s < cap; s += T) {
             u32 neu = 0;
-            if (mem.cnt[s] > threshold) {
+            if (tab.word_ld(s) > threshold) {
                 const u32 base = atomicAdd(&ctl.n_solid, 1u);
                 if (base < max_solid) {
-                    mem.solid_keys[base] = mem.keys[s];
+                    tab.skey_st(base, tab.key_ld(s));
                     neu = base + 1u;
                 }
             }
-            mem.cnt[s] = neu;
+            tab.word_st(s, neu);
         }
     }
     __syncthreads();
@@ -434,55 +587,52 @@ __device__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* 
     if (n_solid > max_solid) return false;
     if (n_solid == 0) return true;
     // E. candidate edge stamps: smallest ordinal of "solid window followed by symbol c"
-    for (u32 s = tid; s < 4 * n_solid; s += T) mem.stamps[s] = GA_NONE64;
+    for (u32 s = tid; s < 4 * n_solid; s += T) tab.stamp_st(s, GA_NONE64);
     if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
     __syncthreads();
-    for (u64 i = lo + tid; i < hi; i += T) {
-        const ulonglong2 b = bases[i];
-        const u64 mt = meta[i];
-        const u32 nwin = meta_windows(mt);
-        const u32 nfollow = meta_has_next(mt) ? nwin : nwin - 1u;     // windows that have a next symbol
-        const u64 e0 = meta_ordinal(mt);
-        u64 key = b.x >> (64 - 2 * w);
-        for (u32 j = 0; j < nfollow; ++j) {
-            const u32 idx = (u32)w + j;
-            const u64 word = idx < 32u ? b.x : b.y;
-            const u32 c = (u32)(word >> (62u - 2u * (idx & 31u))) & 3u;
-            u32 s = sk_slot_hash(key) & cmask;
-            u32 probes = 0;                                           // present: counted in C
-            while (vkeys[s] != key && probes++ <= SB_PROBE_MAX) s = (s + 1u) & cmask;
-            const u32 sol = probes <= SB_PROBE_MAX ? cnt_get<SM>(mem.cnt, s) : 0u;
-            if (sol) {
-                u64* p = mem.stamps + 4u * (sol - 1u) + c;
-                const u64 e = e0 + j;
-                if (e < *(volatile u64*)p) atomicMin((unsigned long long*)p, (unsigned long long)e);
-            }
-            key = ((key << 2) | (u64)c) & mask;
+    for (u64 bt = warp; bt < n_batches; bt += W) {
+        const u64 i = lo + bt * 32u + lane;
+        const bool have = i < hi;
+        ulonglong2 b = make_ulonglong2(0, 0);
+        u64 mt = 0;
+        if (have) {
+            b = bases[i];
+            mt = meta[i];
         }
+        sk_for_each_window<true>(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
+            if (!follows) return;
+            const u64 key = top >> kshift;
+            u32 s = sk_slot_hash(key) >> (32u - lg);
+            u32 probes = 0;                                           // present: counted in C
+            while (tab.key_ld(s) != key && probes++ <= SB_PROBE_MAX) s = (s + 1u) & cmask;
+            const u32 sol = probes <= SB_PROBE_MAX ? tab.cnt_get(s) : 0u;
+            if (sol) {
+                const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
+                const u32 at = 4u * (sol - 1u) + c;
+                if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
+            }
+        });
     }
     __syncthreads();
     // F. output
     const u64 base = ctl.out_base;
     if (base + n_solid <= out_capacity) {
-        for (u32 s = tid; s < n_solid; s += T) solid_keys_out[base + s] = mem.solid_keys[s];
-        for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = mem.stamps[s];
+        for (u32 s = tid; s < n_solid; s += T) solid_keys_out[base + s] = tab.skey_ld(s);
+        for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = tab.stamp_ld(s);
     }
     return true;
 }
 
 // counters: [0] next bucket, [1] solid windows so far, [2] buckets listed for the spill path
+// hist: per bucket, records << 32 | windows
 __global__ void __launch_bounds__(SB_THREADS, 1)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
-                 u64 n_buckets, int w, u32 threshold, u32 cap_limit, u32 max_solid, u64* __restrict__ solid_keys_out,
-                 u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters, u32* __restrict__ spill_list,
-                 u64 spill_capacity, u32* status) {
+                 const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit, u32 solid_limit,
+                 u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
+                 u32* __restrict__ spill_list, u64 spill_capacity, u32* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BucketCtl ctl;
-    BucketMem mem;
-    mem.keys = reinterpret_cast<u64*>(smem_raw);
-    mem.solid_keys = mem.keys + cap_limit;
-    mem.stamps = mem.solid_keys + max_solid;
-    mem.cnt = reinterpret_cast<u32*>(mem.stamps + 4 * (size_t)max_solid);
+    const u32 pool = (u32)__cvta_generic_to_shared(smem_raw);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) ctl.bucket = (u32)min((u64)atomicAdd((unsigned long long*)&counters[0], 1ull), n_buckets);
@@ -491,8 +641,19 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         if (b >= n_buckets) break;
         const u64 lo = offsets[b], hi = offsets[b + 1];
         if (lo == hi) continue;
-        const bool ok = sk_bucket_body<true>(bases, meta, lo, hi, w, threshold, mem, cap_limit, max_solid, ctl,
-                                             solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+        const u64 nw = hist[b] & 0xFFFFFFFFull;
+        u32 cap = 256;
+        while (cap < cap_limit && (u64)cap < 2 * nw) cap <<= 1;
+        // table first (8 B keys + 2 B counters per slot), the rest of the pool holds solid keys + 4 stamps
+        TabShared tab;
+        tab.keys = pool;
+        tab.cnt = pool + 8u * cap;
+        tab.skeys = pool + 10u * cap;
+        u32 max_solid = (SB_POOL_BYTES - 10u * cap) / 40u;
+        if (max_solid > solid_limit) max_solid = solid_limit;
+        tab.stamps = tab.skeys + 8u * max_solid;
+        const bool ok = sk_bucket_body(bases, meta, lo, hi, w, threshold, tab, cap, max_solid, ctl, solid_keys_out,
+                                       edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) {
             const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
             if (at < spill_capacity) spill_list[at] = (u32)b;
@@ -502,7 +663,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
 }
 
 // spill path: the same body over global scratch (one slice per CTA), for buckets whose distinct or
-// solid windows exceed the shared-memory table
+// solid windows exceed the shared-memory pool
 __global__ void __launch_bounds__(SB_THREADS, 1)
 sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                        const u64* __restrict__ offsets, const u32* __restrict__ spill_list, u64 n_spill, int w,
@@ -510,18 +671,18 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
                        u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
                        u64* counters, u32* status) {
     __shared__ BucketCtl ctl;
-    BucketMem mem;
+    TabGlobal tab;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
-    mem.keys = reinterpret_cast<u64*>(mine);
-    mem.solid_keys = mem.keys + cap;
-    mem.stamps = mem.solid_keys + cap;
-    mem.cnt = reinterpret_cast<u32*>(mem.stamps + 4 * (size_t)cap);
+    tab.keys = reinterpret_cast<u64*>(mine);
+    tab.skeys = tab.keys + cap;
+    tab.stamps = tab.skeys + cap;
+    tab.cnt = reinterpret_cast<u32*>(tab.stamps + 4 * (size_t)cap);
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
         const u64 b = spill_list[oi];
         const u64 lo = offsets[b], hi = offsets[b + 1];
-        const bool ok = sk_bucket_body<false>(bases, meta, lo, hi, w, threshold, mem, cap, cap, ctl, solid_keys_out,
-                                              edge_stamp_out, out_capacity, counters + 1);
+        const bool ok = sk_bucket_body(bases, meta, lo, hi, w, threshold, tab, cap, cap, ctl, solid_keys_out,
+                                       edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
     }
@@ -551,10 +712,6 @@ sk_resolve_kernel(const u64* __restrict__ keys, u64 n, int w, const Slot<u64>* _
     }
 }
 
-size_t sk_bucket_smem(u32 cap_limit, u32 max_solid) {
-    return (size_t)cap_limit * 8 + (size_t)max_solid * 8 + (size_t)max_solid * 32 + (size_t)cap_limit * 2;
-}
-
 bool is_pow2(u64 v) { return v && !(v & (v - 1)); }
 
 }  // namespace
@@ -571,7 +728,7 @@ extern "C" int ga_sk_minimizer_len(int k) {
 
 extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* rec_bases_dev,
                                    uint64_t* rec_meta_dev, uint64_t l1_capacity, uint64_t* l1_cursors_dev,
-                                   uint32_t* hist_dev, uint32_t* status_dev, ga_stream stream) {
+                                   uint64_t* hist_dev, uint32_t* status_dev, ga_stream stream) {
     if (!reads || !rec_bases_dev || !rec_meta_dev || !l1_cursors_dev || !hist_dev || !status_dev || l1_capacity == 0 ||
         l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10) {
         ga_set_error("ga_sk_scatter_reads: bad arguments (bucket bits must be 0..10 each)");
@@ -598,18 +755,18 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     const unsigned grid = (unsigned)(n_tiles < 148ull * 2 ? n_tiles : 148ull * 2);
     sk_scatter_reads_kernel<<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(
         rv, w, ga_sk_minimizer_len(k), l1_bits, l2_bits, (ulonglong2*)rec_bases_dev, (u64*)rec_meta_dev, l1_capacity,
-        (u64*)l1_cursors_dev, hist_dev, status_dev);
+        (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev);
     GA_LAUNCH_CHECK("sk_scatter_reads");
     return GA_OK;
 }
 
-extern "C" int ga_sk_offsets(const uint32_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
+extern "C" int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
                              uint64_t* cursors_dev, ga_stream stream) {
     if (!hist_dev || !offsets_dev || !cursors_dev || n_buckets == 0) {
         ga_set_error("ga_sk_offsets: bad arguments");
         return GA_ERR_BAD_ARG;
     }
-    sk_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist_dev, n_buckets, (u64*)offsets_dev, (u64*)cursors_dev);
+    sk_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const u64*)hist_dev, n_buckets, (u64*)offsets_dev, (u64*)cursors_dev);
     GA_LAUNCH_CHECK("sk_offsets");
     return GA_OK;
 }
@@ -633,26 +790,31 @@ extern "C" int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* 
 }
 
 extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                                 uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
-                                 uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
-                                 uint64_t out_capacity, uint64_t* counters_dev, uint32_t* spill_list_dev,
-                                 uint64_t spill_capacity, uint32_t* status_dev, ga_stream stream) {
+                                 const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold,
+                                 uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
+                                 uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
+                                 uint32_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
+                                 ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || !meta_dev || !offsets_dev || !solid_keys_out_dev || !edge_stamp_out_dev || !counters_dev ||
-        !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 || threshold > 60000 ||
-        !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS || max_solid == 0 ||
-        max_solid > SB_MAX_SOLID) {
+    if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev || !edge_stamp_out_dev ||
+        !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
+        threshold > 60000 || !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS ||
+        max_solid == 0) {
         ga_set_error("ga_sk_count_build: bad arguments (0 <= threshold <= 60000, table_slots a power of two in "
-                     "256..%u, max_solid 1..%u)", SB_MAX_SLOTS, SB_MAX_SOLID);
+                     "256..%u, max_solid >= 1)", SB_MAX_SLOTS);
         return GA_ERR_BAD_ARG;
     }
-    const size_t smem = sk_bucket_smem(table_slots, max_solid);
-    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;
+    if (!attr_set) {
+        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+        attr_set = true;
+    }
+    if (max_solid > 16000) max_solid = 16000;          // solid index + 1 lives in a 16-bit counter
     const unsigned grid = (unsigned)(n_buckets < 148ull ? n_buckets : 148ull);
-    sk_bucket_kernel<<<grid, SB_THREADS, smem, (cudaStream_t)stream>>>(
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_buckets, w, (u32)threshold,
-        table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity, (u64*)counters_dev,
-        spill_list_dev, spill_capacity, status_dev);
+    sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, (const u64*)hist_dev, n_buckets, w,
+        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
+        (u64*)counters_dev, spill_list_dev, spill_capacity, status_dev);
     GA_LAUNCH_CHECK("sk_bucket");
     return GA_OK;
 }

@@ -27,7 +27,7 @@ TWO_PHASE_MIN_STEP = 1 << 20
 SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
 SUPERKMER_TARGET = 16384                # windows per bucket aimed for
 SUPERKMER_TABLE_SLOTS = 16384           # shared-memory table slots per bucket (tests shrink it to force spills)
-SUPERKMER_MAX_SOLID = 1024              # solid windows per bucket held in shared memory
+SUPERKMER_MAX_SOLID = 16000             # solid windows per bucket (further bounded by the shared-memory pool)
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
 
@@ -536,7 +536,7 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
         rec_bases = torch.empty(n_l1 * cap1 * 2, dtype=torch.int64, device=dev)
         rec_meta = torch.empty(n_l1 * cap1, dtype=torch.int64, device=dev)
         cursors1 = torch.zeros(n_l1, dtype=torch.int64, device=dev)
-        hist = torch.zeros(n_buckets, dtype=torch.int32, device=dev)
+        hist = torch.zeros(n_buckets, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_scatter1", n_occ):
             gn.check(L.ga_sk_scatter_reads(C.byref(reads.struct()), k, l1_bits, l2_bits, gn.ptr(rec_bases),
@@ -559,7 +559,9 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
     del rec_bases, rec_meta
     _mark("sk scatter buckets")
     free, _ = torch.cuda.mem_get_info()
-    out_cap = max(1 << 16, min(n_occ // 16 + 1024, int(free * 0.5) // 40))
+    out_cap = max(1 << 16, n_occ // 16 + 1024)
+    if out_cap * 40 > free * 0.6:
+        out_cap = max(1 << 16, int(free * 0.6) // 40)
     spill_cap = 1 << 16
     while True:
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -568,7 +570,7 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
         edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_bucket", n_occ):
-            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_buckets, k, int(threshold),
+            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), gn.ptr(hist), n_buckets, k, int(threshold),
                                          SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
                                          gn.ptr(edge_stamp), out_cap, gn.ptr(counters), gn.ptr(spill_list), spill_cap,
                                          gn.ptr(status), _stream()))

@@ -182,26 +182,27 @@ int ga_sk_minimizer_len(int k);
 /* Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases in
  * rec_bases_dev + one meta word in rec_meta_dev) and scatter them to 2^l1_bits level-1 buckets of
  * l1_capacity records each (bucket b at index b*l1_capacity; l1_cursors_dev[b] = records written,
- * zeroed by the caller).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) counts records per
- * final bucket.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed, retry with a larger capacity. */
+ * zeroed by the caller).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) accumulates, per final
+ * bucket, records << 32 | windows.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed, retry with a larger capacity. */
 int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* rec_bases_dev,
                         uint64_t* rec_meta_dev, uint64_t l1_capacity, uint64_t* l1_cursors_dev,
-                        uint32_t* hist_dev, uint32_t* status_dev, ga_stream stream);
-/* offsets_dev[n_buckets+1] = exclusive prefix sum of hist_dev; cursors_dev[n_buckets] = a copy */
-int ga_sk_offsets(const uint32_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
+                        uint64_t* hist_dev, uint32_t* status_dev, ga_stream stream);
+/* offsets_dev[n_buckets+1] = exclusive prefix sum of the record counts; cursors_dev[n_buckets] = a copy */
+int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
                   uint64_t* cursors_dev, ga_stream stream);
 /* level-1 buckets -> final buckets, densely packed at offsets_dev (cursors_dev is consumed) */
 int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
                           const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
                           void* out_bases_dev, uint64_t* out_meta_dev, ga_stream stream);
-/* One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots; every
+/* One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
+ * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
  * stamps (edge_stamp_out_dev[4*i + c] = smallest occurrence ordinal of "window i followed by symbol
  * c", all-ones if never).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
  * windows found (may exceed out_capacity: nothing is written beyond it, the caller retries with
  * that many), [2] buckets that did not fit and were listed in spill_list_dev. */
 int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                      uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
+                      const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
                       uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                       uint64_t out_capacity, uint64_t* counters_dev, uint32_t* spill_list_dev,
                       uint64_t spill_capacity, uint32_t* status_dev, ga_stream stream);
