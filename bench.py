@@ -44,7 +44,11 @@ B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
             "prefilter": 1.35,     # sketch cell read-modify-write (4-bit cell, counted as 1 B)
             "count": 16.85,        # cell read 0.5 + key probe 8 + count RMW 8
             "build": 22.35,        # key probe 8 + id/epoch word 4 + edge + node stamp RMW 10
-            "build_tail": 22.35}   # same pass, the reads after the prefix
+            "build_tail": 22.35,   # same pass, the reads after the prefix
+            # bucketed path (csrc/ga_superkmer.cu): the two base reads of the reference's two loops
+            # happen in the scatter, every probe / count / stamp access in the bucket kernel
+            "sk_scatter1": 0.7, "sk_scatter2": 0.0,
+            "sk_bucket": 38.0}     # count probe + RMW 16, build probe + count read 12, stamp RMW 10
 
 
 def hbm_peak():

@@ -363,74 +363,173 @@ __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
     return h * 0xC2B2AE3Du;                     // use the TOP bits
 }
 
-// ---- table access, shared-memory flavour (byte addresses in the shared window) and global flavour
-struct TabShared {
-    static constexpr bool kPacked = true;       // two 16-bit counters per word
+// ---- table access: two shared-memory flavours (byte addresses in the shared window) and a global one.
+// kKind 0: shared, count packed into the key word ((key << 4) | count, count <= 15) -- one 64-bit CAS
+//          inserts a window with count 1, no separate counter traffic; needs 2w + 4 <= 64, threshold <= 13.
+// kKind 1: shared, separate 16-bit counters (two per word).
+// kKind 2: global scratch (spill path), 32-bit counters.
+__device__ __forceinline__ u64 sh_ld64v(u32 a) {
+    u64 v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ u64 sh_ld64(u32 a) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sh_st64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ u32 sh_ld32v(u32 a) {
+    u32 v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sh_st32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 sh_ld16(u32 a) {
+    u16 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sh_st16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((u16)v) : "memory"); }
+__device__ __forceinline__ u64 sh_cas64(u32 a, u64 cmp, u64 val) {
+    u64 old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+
+struct TabSharedBase {
     u32 keys, cnt, skeys, stamps;               // shared byte addresses
-    __device__ __forceinline__ u64 key_ld(u32 s) const {
-        u64 v;
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(keys + 8u * s));
-        return v;
-    }
-    __device__ __forceinline__ void key_st(u32 s, u64 v) const {
-        asm volatile("st.shared.u64 [%0], %1;" ::"r"(keys + 8u * s), "l"(v) : "memory");
-    }
-    __device__ __forceinline__ u64 key_cas(u32 s, u64 val) const {
-        u64 old;
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(keys + 8u * s), "l"(GA_NONE64), "l"(val) : "memory");
-        return old;
-    }
-    // two 16-bit counters per word
-    __device__ __forceinline__ u32 word_ld(u32 wi) const {
-        u32 v;
-        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(cnt + 4u * wi));
-        return v;
-    }
-    __device__ __forceinline__ void word_st(u32 wi, u32 v) const {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt + 4u * wi), "r"(v) : "memory");
-    }
-    __device__ __forceinline__ u32 cnt_get(u32 s) const { return (word_ld(s >> 1) >> ((s & 1u) * 16u)) & 0xFFFFu; }
-    __device__ __forceinline__ void cnt_add(u32 s) const {
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
-    }
-    __device__ __forceinline__ u32 cnt_words(u32 cap) const { return cap >> 1; }
-    __device__ __forceinline__ void skey_st(u32 i, u64 v) const {
-        asm volatile("st.shared.u64 [%0], %1;" ::"r"(skeys + 8u * i), "l"(v) : "memory");
-    }
-    __device__ __forceinline__ u64 skey_ld(u32 i) const {
-        u64 v;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(skeys + 8u * i));
-        return v;
-    }
-    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const {
-        asm volatile("st.shared.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
-    }
-    __device__ __forceinline__ u64 stamp_ld(u32 i) const {
-        u64 v;
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(stamps + 8u * i));
-        return v;
-    }
+    __device__ __forceinline__ void skey_st(u32 i, u64 v) const { sh_st64(skeys + 8u * i, v); }
+    __device__ __forceinline__ u64 skey_ld(u32 i) const { return sh_ld64(skeys + 8u * i); }
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { sh_st64(stamps + 8u * i, v); }
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return sh_ld64v(stamps + 8u * i); }
     __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
         asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
     }
 };
 
+struct TabPacked : TabSharedBase {
+    static constexpr int kKind = 0;
+    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);   // solid indices are written before read
+    }
+    // count one occurrence (saturating above the threshold); false = table full
+    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            const u32 a = keys + 8u * s;
+            u64 cur = sh_ld64v(a);
+            if (cur == GA_NONE64) {
+                cur = sh_cas64(a, GA_NONE64, (key << 4) | 1ull);
+                if (cur == GA_NONE64) return true;
+            }
+            if ((cur >> 4) == key) {
+                while ((u32)(cur & 15ull) <= threshold) {
+                    const u64 old = sh_cas64(a, cur, cur + 1ull);
+                    if (old == cur) break;
+                    cur = old;
+                }
+                return true;
+            }
+            s = (s + 1u) & cmask;
+        }
+        return false;
+    }
+    // phase D for slot s: returns the key when the slot holds a solid window
+    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
+        const u64 cur = sh_ld64(keys + 8u * s);
+        key = cur >> 4;
+        return cur != GA_NONE64 && (u32)(cur & 15ull) > threshold;
+    }
+    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
+    // phase E: solid index + 1 of a counted window, 0 if not solid
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            const u64 cur = sh_ld64(keys + 8u * s);
+            if ((cur >> 4) == key) return (u32)(cur & 15ull) > threshold ? sh_ld16(cnt + 2u * s) : 0u;
+            s = (s + 1u) & cmask;
+        }
+        return 0u;
+    }
+};
+
+struct TabShared : TabSharedBase {
+    static constexpr int kKind = 1;
+    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);
+        for (u32 s = tid; s < cap / 2; s += T) sh_st32(cnt + 4u * s, 0u);
+    }
+    __device__ __forceinline__ u32 cnt_get(u32 s) const { return (sh_ld32v(cnt + 4u * (s >> 1)) >> ((s & 1u) * 16u)) & 0xFFFFu; }
+    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            const u32 a = keys + 8u * s;
+            u64 cur = sh_ld64v(a);
+            if (cur == GA_NONE64) cur = sh_cas64(a, GA_NONE64, key);
+            if (cur == GA_NONE64 || cur == key) {
+                if (cnt_get(s) <= threshold)
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
+                return true;
+            }
+            s = (s + 1u) & cmask;
+        }
+        return false;
+    }
+    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
+        key = sh_ld64(keys + 8u * s);
+        return cnt_get(s) > threshold;
+    }
+    // counters become solid indices: all of them are rewritten in phase D (0 = not solid)
+    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            if (sh_ld64(keys + 8u * s) == key) return sh_ld16(cnt + 2u * s);
+            s = (s + 1u) & cmask;
+        }
+        return 0u;
+    }
+};
+
 struct TabGlobal {
-    static constexpr bool kPacked = false;
+    static constexpr int kKind = 2;
     u64* keys;
     u32* cnt;                                   // one 32-bit counter per slot
     u64* skeys;
     u64* stamps;
-    __device__ __forceinline__ u64 key_ld(u32 s) const { return ((volatile u64*)keys)[s]; }
-    __device__ __forceinline__ void key_st(u32 s, u64 v) const { keys[s] = v; }
-    __device__ __forceinline__ u64 key_cas(u32 s, u64 val) const {
-        return atomicCAS((unsigned long long*)(keys + s), GA_NONE64, val);
+    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T) {
+            keys[s] = GA_NONE64;
+            cnt[s] = 0u;
+        }
     }
-    __device__ __forceinline__ u32 word_ld(u32 wi) const { return ((volatile u32*)cnt)[wi]; }
-    __device__ __forceinline__ void word_st(u32 wi, u32 v) const { cnt[wi] = v; }
-    __device__ __forceinline__ u32 cnt_get(u32 s) const { return word_ld(s); }
-    __device__ __forceinline__ void cnt_add(u32 s) const { atomicAdd(cnt + s, 1u); }
-    __device__ __forceinline__ u32 cnt_words(u32 cap) const { return cap; }
+    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            u64 cur = ((volatile u64*)keys)[s];
+            if (cur == GA_NONE64) cur = atomicCAS((unsigned long long*)(keys + s), GA_NONE64, key);
+            if (cur == GA_NONE64 || cur == key) {
+                if (((volatile u32*)cnt)[s] <= threshold) atomicAdd(cnt + s, 1u);
+                return true;
+            }
+            s = (s + 1u) & cmask;
+        }
+        return false;
+    }
+    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
+        key = keys[s];
+        return cnt[s] > threshold;
+    }
+    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { cnt[s] = idx1; }
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32) const {
+        u32 s = sk_slot_hash(key) >> (32u - lg);
+        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+            if (keys[s] == key) return cnt[s];
+            s = (s + 1u) & cmask;
+        }
+        return 0u;
+    }
     __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
     __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
     __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { stamps[i] = v; }
@@ -508,8 +607,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u64 nrec = hi - lo;
     const u64 n_batches = (nrec + 31u) / 32u;
     // B. clear
-    for (u32 s = tid; s < cap; s += T) tab.key_st(s, GA_NONE64);
-    for (u32 s = tid; s < tab.cnt_words(cap); s += T) tab.word_st(s, 0u);
+    tab.clear(cap, tid, T);
     if (tid == 0) {
         ctl.n_solid = 0;
         ctl.overflow = 0;
@@ -527,60 +625,23 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             mt = meta[i];
         }
         sk_for_each_window<false>(b.x, b.y, mt, have, [&](u64 top, u64, bool) {
-            const u64 key = top >> kshift;
-            u32 s = sk_slot_hash(key) >> (32u - lg);
-            u32 probes = 0;
-            for (;;) {
-                const u64 cur = tab.key_ld(s);
-                if (cur == key) break;
-                if (cur == GA_NONE64) {
-                    const u64 old = tab.key_cas(s, key);
-                    if (old == GA_NONE64 || old == key) break;
-                }
-                if (++probes > SB_PROBE_MAX) {
-                    *vovf = 1u;
-                    return;
-                }
-                s = (s + 1u) & cmask;
-            }
-            if (tab.cnt_get(s) <= threshold) tab.cnt_add(s);
+            if (!tab.count(top >> kshift, lg, cmask, threshold)) *vovf = 1u;
         });
     }
     __syncthreads();
     if (ctl.overflow) return false;
-    // D. solid windows: counter -> solid index + 1 (0 = not solid)
-    if (Tab::kPacked) {
-        for (u32 wi = tid; wi < cap / 2; wi += T) {
-            const u32 word = tab.word_ld(wi);
-            const u32 s0 = (word & 0xFFFFu) > threshold, s1 = (word >> 16) > threshold;
-            u32 neu = 0;
-            if (s0 + s1) {
-                const u32 base = atomicAdd(&ctl.n_solid, s0 + s1);
-                if (base + s0 + s1 <= max_solid) {
-                    if (s0) {
-                        tab.skey_st(base, tab.key_ld(2 * wi));
-                        neu |= base + 1u;
-                    }
-                    if (s1) {
-                        tab.skey_st(base + s0, tab.key_ld(2 * wi + 1));
-                        neu |= (base + s0 + 1u) << 16;
-                    }
-                }
+    // D. solid windows get an index; every slot learns its index + 1 (0 = not solid)
+    for (u32 s = tid; s < cap; s += T) {
+        u64 key;
+        u32 idx1 = 0;
+        if (tab.solid_at(s, threshold, key)) {
+            const u32 base = atomicAdd(&ctl.n_solid, 1u);
+            if (base < max_solid) {
+                tab.skey_st(base, key);
+                idx1 = base + 1u;
             }
-            tab.word_st(wi, neu);
         }
-    } else {
-        for (u32 s = tid; s < cap; s += T) {
-            u32 neu = 0;
-            if (tab.word_ld(s) > threshold) {
-                const u32 base = atomicAdd(&ctl.n_solid, 1u);
-                if (base < max_solid) {
-                    tab.skey_st(base, tab.key_ld(s));
-                    neu = base + 1u;
-                }
-            }
-            tab.word_st(s, neu);
-        }
+        if (Tab::kKind != 0 || idx1) tab.set_solid_index(s, idx1);
     }
     __syncthreads();
     const u32 n_solid = ctl.n_solid;
@@ -601,14 +662,9 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         }
         sk_for_each_window<true>(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
             if (!follows) return;
-            const u64 key = top >> kshift;
-            u32 s = sk_slot_hash(key) >> (32u - lg);
-            u32 probes = 0;                                           // present: counted in C
-            while (tab.key_ld(s) != key && probes++ <= SB_PROBE_MAX) s = (s + 1u) & cmask;
-            const u32 sol = probes <= SB_PROBE_MAX ? tab.cnt_get(s) : 0u;
+            const u32 sol = tab.solid_of(top >> kshift, lg, cmask, threshold);
             if (sol) {
-                const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
-                const u32 at = 4u * (sol - 1u) + c;
+                const u32 at = 4u * (sol - 1u) + ((u32)(top >> (kshift - 2u)) & 3u);
                 if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
             }
         });
@@ -625,6 +681,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
 
 // counters: [0] next bucket, [1] solid windows so far, [2] buckets listed for the spill path
 // hist: per bucket, records << 32 | windows
+template <class Tab>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
                  const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit, u32 solid_limit,
@@ -645,7 +702,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         u32 cap = 256;
         while (cap < cap_limit && (u64)cap < 2 * nw) cap <<= 1;
         // table first (8 B keys + 2 B counters per slot), the rest of the pool holds solid keys + 4 stamps
-        TabShared tab;
+        Tab tab;
         tab.keys = pool;
         tab.cnt = pool + 8u * cap;
         tab.skeys = pool + 10u * cap;
@@ -806,15 +863,22 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
     }
     static bool attr_set = false;
     if (!attr_set) {
-        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<TabPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<TabShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
         attr_set = true;
     }
-    if (max_solid > 16000) max_solid = 16000;          // solid index + 1 lives in a 16-bit counter
+    if (max_solid > 16000) max_solid = 16000;          // solid index + 1 lives in 16 bits
     const unsigned grid = (unsigned)(n_buckets < 148ull ? n_buckets : 148ull);
-    sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, (const u64*)hist_dev, n_buckets, w,
-        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, spill_list_dev, spill_capacity, status_dev);
+    // count rides in the key word; (key << 4 | 15) is kept free so that it can never look like an empty slot
+    const bool packed = 2 * w + 4 <= 64 && threshold <= 13;
+#define GA_SK_BUCKET(TAB)                                                                                          \
+    sk_bucket_kernel<TAB><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                              \
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, (const u64*)hist_dev, n_buckets, w, \
+        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity, \
+        (u64*)counters_dev, spill_list_dev, spill_capacity, status_dev)
+    if (packed) GA_SK_BUCKET(TabPacked);
+    else GA_SK_BUCKET(TabShared);
+#undef GA_SK_BUCKET
     GA_LAUNCH_CHECK("sk_bucket");
     return GA_OK;
 }

@@ -544,7 +544,8 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
                                            _stream()))
         offsets = torch.empty(n_buckets + 1, dtype=torch.int64, device=dev)
         cursors2 = torch.empty(n_buckets, dtype=torch.int64, device=dev)
-        gn.check(L.ga_sk_offsets(gn.ptr(hist), n_buckets, gn.ptr(offsets), gn.ptr(cursors2), _stream()))
+        with _timed("sk_offsets"):
+            gn.check(L.ga_sk_offsets(gn.ptr(hist), n_buckets, gn.ptr(offsets), gn.ptr(cursors2), _stream()))
         total = int(offsets[n_buckets].item())
         if not _check_status(status) & gn.ST_TABLE_FULL:
             break
@@ -703,9 +704,10 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     solid = torch.empty(solid_cap * counts.slot_bytes, dtype=torch.uint8, device=dev)
     status = reads.status
     status.zero_()
-    gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, _stream()))
-    gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap,
-                                   gn.ptr(status), _stream()))
+    with _timed("id_table"):
+        gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, _stream()))
+        gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap,
+                                       gn.ptr(status), _stream()))
     _mark("id table")
     n_nodes, n_edges, attr = C.c_int64(), C.c_int64(), C.c_int64()
     plan = C.c_void_p()
@@ -721,9 +723,10 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
             edge_stamp = torch.full((4 * n_solid,), -1, dtype=torch.int64, device=dev)
             build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, edge_stamp, status)
         _mark("fill stamps + build_dna")
-        gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
-                                            kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),
-                                            C.byref(plan), C.byref(n_nodes), C.byref(n_edges)))
+        with _timed("csr_plan"):
+            gn.check(L.ga_csr_plan_unpaired_dna(gn.ptr(node_stamp), gn.ptr(edge_stamp), n_solid, gn.ptr(solid_keys),
+                                                kw, k, alphabet.sym_bits, gn.ptr(solid), solid_cap, _stream(),
+                                                C.byref(plan), C.byref(n_nodes), C.byref(n_edges)))
         attr.value = n_edges.value
         _mark("csr plan dna")
         if _check_status(status) & gn.ST_TABLE_FULL:
@@ -773,8 +776,9 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         last_sym = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
         keys_a = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
         keys_b = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev) if reads.paired else None
-        gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
-                               gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
+        with _timed("csr_emit"):
+            gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
+                                   gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
         torch.cuda.current_stream().synchronize()
         _mark("csr emit")
     finally:
