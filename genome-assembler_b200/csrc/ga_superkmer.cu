@@ -352,10 +352,12 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
 // then walks the windows of its 32 records 32 at a time, so every lane probes an independent window
 // (full lanes, no serial key roll, balanced warps).  Table, counters and stamps live in shared
 // memory and are addressed with explicit ld/atom.shared.
-constexpr int SB_THREADS = 1024;
-constexpr u32 SB_MAX_SLOTS = 16384;
-constexpr u32 SB_POOL_BYTES = 212992;          // 208 KB of dynamic shared memory: table + solid keys + stamps
+constexpr int SB_THREADS = 512;
+constexpr int SB_CTAS_PER_SM = 2;
+constexpr u32 SB_MAX_SLOTS = 8192;
+constexpr u32 SB_POOL_BYTES = 106496;          // 104 KB of dynamic shared memory per CTA: table + solid keys + stamps
 constexpr u32 SB_PROBE_MAX = 192;
+constexpr u32 SB_MAX_SEG = 16;                // sources a bucket can be gathered from (multi-GPU exchange)
 
 __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
     u32 h = (u32)key * 0x9E3779B1u ^ (u32)(key >> 32) * 0x85EBCA77u;
@@ -414,8 +416,8 @@ struct TabPacked : TabSharedBase {
         for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);   // solid indices are written before read
     }
     // count one occurrence (saturating above the threshold); false = table full
-    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u32 a = keys + 8u * s;
             u64 cur = sh_ld64v(a);
@@ -442,9 +444,10 @@ struct TabPacked : TabSharedBase {
         return cur != GA_NONE64 && (u32)(cur & 15ull) > threshold;
     }
     __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
+    __device__ __forceinline__ u32 occupied(u32 s) const { return sh_ld64(keys + 8u * s) != GA_NONE64; }
     // phase E: solid index + 1 of a counted window, 0 if not solid
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32 threshold) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u64 cur = sh_ld64(keys + 8u * s);
             if ((cur >> 4) == key) return (u32)(cur & 15ull) > threshold ? sh_ld16(cnt + 2u * s) : 0u;
@@ -461,8 +464,8 @@ struct TabShared : TabSharedBase {
         for (u32 s = tid; s < cap / 2; s += T) sh_st32(cnt + 4u * s, 0u);
     }
     __device__ __forceinline__ u32 cnt_get(u32 s) const { return (sh_ld32v(cnt + 4u * (s >> 1)) >> ((s & 1u) * 16u)) & 0xFFFFu; }
-    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u32 a = keys + 8u * s;
             u64 cur = sh_ld64v(a);
@@ -482,8 +485,9 @@ struct TabShared : TabSharedBase {
     }
     // counters become solid indices: all of them are rewritten in phase D (0 = not solid)
     __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ u32 occupied(u32 s) const { return sh_ld64(keys + 8u * s) != GA_NONE64; }
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             if (sh_ld64(keys + 8u * s) == key) return sh_ld16(cnt + 2u * s);
             s = (s + 1u) & cmask;
@@ -504,8 +508,8 @@ struct TabGlobal {
             cnt[s] = 0u;
         }
     }
-    __device__ __forceinline__ bool count(u64 key, u32 lg, u32 cmask, u32 threshold) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             u64 cur = ((volatile u64*)keys)[s];
             if (cur == GA_NONE64) cur = atomicCAS((unsigned long long*)(keys + s), GA_NONE64, key);
@@ -522,8 +526,9 @@ struct TabGlobal {
         return cnt[s] > threshold;
     }
     __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { cnt[s] = idx1; }
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 lg, u32 cmask, u32) const {
-        u32 s = sk_slot_hash(key) >> (32u - lg);
+    __device__ __forceinline__ u32 occupied(u32 s) const { return keys[s] != GA_NONE64; }
+    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
+        u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             if (keys[s] == key) return cnt[s];
             s = (s + 1u) & cmask;
@@ -543,8 +548,15 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u32 n_solid;
     u32 overflow;
     u32 bucket;
-    u32 pad;
+    u32 n_distinct;
     u64 out_base;
+    u32 sp;            // pending (parts << 16 | part) items of the current bucket
+    u32 ratio_d;       // running estimates, in 1/4096: distinct windows / windows, solid windows / windows
+    u32 ratio_s;
+    u32 n_seg;
+    u32 stack[40];
+    u64 seg_lo[SB_MAX_SEG];        // the bucket's records: segment s holds [seg_lo[s], +seg_pre[s+1]-seg_pre[s])
+    u64 seg_pre[SB_MAX_SEG + 1];
 };
 
 __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
@@ -596,41 +608,55 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
 // returns false when the bucket does not fit: the caller lists it for the spill path
 template <class Tab>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
-                                               u64 lo, u64 hi, int w, u32 threshold, const Tab& tab, u32 cap,
-                                               u32 max_solid, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
+                                               int w, u32 threshold, const Tab& tab, u32 cap,
+                                               u32 max_solid, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
                                                u64* __restrict__ edge_stamp_out, u64 out_capacity,
                                                u64* n_solid_global) {
     const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
     const u32 lg = 31u - (u32)__clz(cap);
     const u32 cmask = cap - 1u;
     const u32 kshift = 64u - 2u * (u32)w;
-    const u64 nrec = hi - lo;
+    const u32 n_seg = ctl.n_seg;
+    const u64 nrec = ctl.seg_pre[n_seg];
     const u64 n_batches = (nrec + 31u) / 32u;
+    // position of the bucket's idx-th record (segments are few: linear scan)
+    auto locate = [&](u64 idx) -> u64 {
+        u32 sg = 0;
+        while (sg + 1u < n_seg && idx >= ctl.seg_pre[sg + 1]) ++sg;
+        return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
+    };
     // B. clear
     tab.clear(cap, tid, T);
     if (tid == 0) {
         ctl.n_solid = 0;
         ctl.overflow = 0;
+        ctl.n_distinct = 0;
     }
     __syncthreads();
     volatile u32* vovf = &ctl.overflow;
+    const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
     // C. count (saturating just above the threshold: only "count > threshold" is asked)
     for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
-        const u64 i = lo + bt * 32u + lane;
-        const bool have = i < hi;
+        const u64 idx = bt * 32u + lane;
+        const bool have = idx < nrec;
         ulonglong2 b = make_ulonglong2(0, 0);
         u64 mt = 0;
         if (have) {
+            const u64 i = locate(idx);
             b = bases[i];
             mt = meta[i];
         }
         sk_for_each_window<false>(b.x, b.y, mt, have, [&](u64 top, u64, bool) {
-            if (!tab.count(top >> kshift, lg, cmask, threshold)) *vovf = 1u;
+            const u64 key = top >> kshift;
+            const u32 h = sk_slot_hash(key);
+            if (((h >> 3) & pmask) != part) return;
+            if (!tab.count(key, h, lg, cmask, threshold)) *vovf = 1u;
         });
     }
     __syncthreads();
     if (ctl.overflow) return false;
     // D. solid windows get an index; every slot learns its index + 1 (0 = not solid)
+    u32 occupied = 0;
     for (u32 s = tid; s < cap; s += T) {
         u64 key;
         u32 idx1 = 0;
@@ -641,8 +667,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                 idx1 = base + 1u;
             }
         }
+        occupied += tab.occupied(s);
         if (Tab::kKind != 0 || idx1) tab.set_solid_index(s, idx1);
     }
+    for (int off = 16; off > 0; off >>= 1) occupied += __shfl_down_sync(FULL, occupied, off);
+    if (lane == 0 && occupied) atomicAdd(&ctl.n_distinct, occupied);
     __syncthreads();
     const u32 n_solid = ctl.n_solid;
     if (n_solid > max_solid) return false;
@@ -652,17 +681,21 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
     __syncthreads();
     for (u64 bt = warp; bt < n_batches; bt += W) {
-        const u64 i = lo + bt * 32u + lane;
-        const bool have = i < hi;
+        const u64 idx = bt * 32u + lane;
+        const bool have = idx < nrec;
         ulonglong2 b = make_ulonglong2(0, 0);
         u64 mt = 0;
         if (have) {
+            const u64 i = locate(idx);
             b = bases[i];
             mt = meta[i];
         }
         sk_for_each_window<true>(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
             if (!follows) return;
-            const u32 sol = tab.solid_of(top >> kshift, lg, cmask, threshold);
+            const u64 key = top >> kshift;
+            const u32 h = sk_slot_hash(key);
+            if (((h >> 3) & pmask) != part) return;
+            const u32 sol = tab.solid_of(key, h, lg, cmask, threshold);
             if (sol) {
                 const u32 at = 4u * (sol - 1u) + ((u32)(top >> (kshift - 2u)) & 3u);
                 if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
@@ -679,51 +712,110 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     return true;
 }
 
-// counters: [0] next bucket, [1] solid windows so far, [2] buckets listed for the spill path
+// counters: [0] next bucket, [1] solid windows so far, [2] passes listed for the spill path
 // hist: per bucket, records << 32 | windows
+//
+// A bucket is done in `parts` passes (a power of two), pass `part` taking the windows whose hash
+// bits select it, so that the distinct and the solid windows of one pass fit the CTA's pool.  parts
+// comes from running estimates of distinct / windows and solid / windows (the first buckets of a CTA
+// start pessimistic); a pass that still does not fit is split in two; only passes that would need more
+// than 32 parts go to the spill list (entry = bucket | parts << 32 | part << 48).
 template <class Tab>
-__global__ void __launch_bounds__(SB_THREADS, 1)
+__global__ void __launch_bounds__(SB_THREADS, SB_CTAS_PER_SM)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
-                 const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit, u32 solid_limit,
+                 u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
+                 u32 solid_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
-                 u32* __restrict__ spill_list, u64 spill_capacity, u32* status) {
+                 u64* __restrict__ spill_list, u64 spill_capacity, u32* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BucketCtl ctl;
     const u32 pool = (u32)__cvta_generic_to_shared(smem_raw);
+    if (threadIdx.x == 0) {
+        ctl.ratio_d = 4096u;
+        ctl.ratio_s = 1024u;
+    }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) ctl.bucket = (u32)min((u64)atomicAdd((unsigned long long*)&counters[0], 1ull), n_buckets);
         __syncthreads();
         const u64 b = ctl.bucket;
         if (b >= n_buckets) break;
-        const u64 lo = offsets[b], hi = offsets[b + 1];
-        if (lo == hi) continue;
         const u64 nw = hist[b] & 0xFFFFFFFFull;
-        u32 cap = 256;
-        while (cap < cap_limit && (u64)cap < 2 * nw) cap <<= 1;
-        // table first (8 B keys + 2 B counters per slot), the rest of the pool holds solid keys + 4 stamps
-        Tab tab;
-        tab.keys = pool;
-        tab.cnt = pool + 8u * cap;
-        tab.skeys = pool + 10u * cap;
-        u32 max_solid = (SB_POOL_BYTES - 10u * cap) / 40u;
-        if (max_solid > solid_limit) max_solid = solid_limit;
-        tab.stamps = tab.skeys + 8u * max_solid;
-        const bool ok = sk_bucket_body(bases, meta, lo, hi, w, threshold, tab, cap, max_solid, ctl, solid_keys_out,
-                                       edge_stamp_out, out_capacity, counters + 1);
-        if (!ok && threadIdx.x == 0) {
-            const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
-            if (at < spill_capacity) spill_list[at] = (u32)b;
-            else atomicOr(status, GA_ST_TABLE_FULL);
+        if (nw == 0) continue;
+        if (threadIdx.x == 0) {       // segment s of the bucket: offsets[s][b] .. offsets[s][b+1]
+            u64 run = 0;
+            for (u32 sg = 0; sg < n_seg; ++sg) {
+                const u64 lo = offsets[sg * (n_buckets + 1) + b], hi = offsets[sg * (n_buckets + 1) + b + 1];
+                ctl.seg_lo[sg] = lo;
+                ctl.seg_pre[sg] = run;
+                run += hi - lo;
+            }
+            ctl.seg_pre[n_seg] = run;
+            ctl.n_seg = n_seg;
+        }
+        const u64 est_d = (nw * ctl.ratio_d >> 12) * 9u / 8u + 64u, est_s = (nw * ctl.ratio_s >> 12) * 9u / 8u + 16u;
+        const u32 solid_room = min(solid_limit, (SB_POOL_BYTES - 10u * cap_limit) / 40u);
+        if (threadIdx.x == 0) {
+            // passes: expected distinct windows of a pass within 85 % of the largest table, solid ones within
+            // 85 % of what the pool holds next to it (a pass that overflows anyway is split below)
+            u32 parts = 1;
+            while (parts < 32u && (est_d > (u64)parts * (cap_limit * 17u / 20u) || est_s > (u64)parts * (solid_room * 17u / 20u)))
+                parts <<= 1;
+            for (u32 q = 0; q < parts; ++q) ctl.stack[q] = (parts << 16) | (parts - 1u - q);
+            ctl.sp = parts;
+        }
+        for (;;) {
+            __syncthreads();
+            const u32 sp = ctl.sp;
+            if (sp == 0) break;
+            const u32 item = ctl.stack[sp - 1];
+            const u32 rd = ctl.ratio_d, rs = ctl.ratio_s;
+            __syncthreads();
+            const u32 parts = item >> 16, part = item & 0xFFFFu;
+            // table sized for 2.5 x the expected distinct windows of this pass (short probe chains); the rest of the pool
+            // holds solid keys + 4 stamps each
+            const u64 want = ((nw * rd >> 12) / parts + 64u) * 5u / 2u;
+            u32 cap = 256;
+            while (cap < cap_limit && (u64)cap < want) cap <<= 1;
+            Tab tab;
+            tab.keys = pool;
+            tab.cnt = pool + 8u * cap;
+            tab.skeys = pool + 10u * cap;
+            u32 max_solid = (SB_POOL_BYTES - 10u * cap) / 40u;
+            if (max_solid > solid_limit) max_solid = solid_limit;
+            tab.stamps = tab.skeys + 8u * max_solid;
+            const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, max_solid, parts, part, ctl,
+                                           solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+            if (threadIdx.x == 0) {
+                u32 top = sp - 1u;
+                if (ok) {
+                    // running means (weight 1/4) of what the passes actually held
+                    const u32 d = (u32)min((u64)ctl.n_distinct * parts * 4096u / (nw + 1u), 4096ull);
+                    const u32 so = (u32)min((u64)ctl.n_solid * parts * 4096u / (nw + 1u), 4096ull);
+                    ctl.ratio_d = (3u * rd + d + 3u) >> 2;
+                    ctl.ratio_s = (3u * rs + so + 3u) >> 2;
+                } else if (parts < 32u && top + 2u <= 40u) {
+                    ctl.stack[top++] = ((parts * 2u) << 16) | (part + parts);
+                    ctl.stack[top++] = ((parts * 2u) << 16) | part;
+                    ctl.ratio_d = min(4096u, rd + (rd >> 1) + 64u);
+                    ctl.ratio_s = min(4096u, rs + (rs >> 1) + 16u);
+                } else {
+                    const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
+                    if (at < spill_capacity) spill_list[at] = b | ((u64)parts << 32) | ((u64)part << 48);
+                    else atomicOr(status, GA_ST_TABLE_FULL);
+                }
+                ctl.sp = top;
+            }
         }
     }
 }
 
-// spill path: the same body over global scratch (one slice per CTA), for buckets whose distinct or
-// solid windows exceed the shared-memory pool
+// spill path: the same body over global scratch (one slice per CTA), for passes that do not fit the
+// shared-memory pool even after splitting
 __global__ void __launch_bounds__(SB_THREADS, 1)
 sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
-                       const u64* __restrict__ offsets, const u32* __restrict__ spill_list, u64 n_spill, int w,
+                       const u64* __restrict__ offsets, u32 n_seg, u64 n_buckets,
+                       const u64* __restrict__ spill_list, u64 n_spill, int w,
                        u32 threshold, u32 cap, unsigned char* __restrict__ scratch, u64 scratch_per_cta,
                        u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
                        u64* counters, u32* status) {
@@ -736,10 +828,23 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
     tab.cnt = reinterpret_cast<u32*>(tab.stamps + 4 * (size_t)cap);
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
-        const u64 b = spill_list[oi];
-        const u64 lo = offsets[b], hi = offsets[b + 1];
-        const bool ok = sk_bucket_body(bases, meta, lo, hi, w, threshold, tab, cap, cap, ctl, solid_keys_out,
-                                       edge_stamp_out, out_capacity, counters + 1);
+        const u64 entry = spill_list[oi];
+        const u64 b = entry & 0xFFFFFFFFull;
+        const u32 parts = (u32)(entry >> 32) & 0xFFFFu, part = (u32)(entry >> 48);
+        if (threadIdx.x == 0) {
+            u64 run = 0;
+            for (u32 sg = 0; sg < n_seg; ++sg) {
+                const u64 lo = offsets[sg * (n_buckets + 1) + b], hi = offsets[sg * (n_buckets + 1) + b + 1];
+                ctl.seg_lo[sg] = lo;
+                ctl.seg_pre[sg] = run;
+                run += hi - lo;
+            }
+            ctl.seg_pre[n_seg] = run;
+            ctl.n_seg = n_seg;
+        }
+        __syncthreads();
+        const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, cap, parts, part, ctl,
+                                       solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
     }
@@ -847,16 +952,17 @@ extern "C" int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* 
 }
 
 extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                                 const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold,
+                                 uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k,
+                                 int64_t threshold,
                                  uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
                                  uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
-                                 uint32_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
+                                 uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
                                  ga_stream stream) {
     const int w = k - 1;
     if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev || !edge_stamp_out_dev ||
         !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
         threshold > 60000 || !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS ||
-        max_solid == 0) {
+        max_solid == 0 || n_segments == 0 || n_segments > SB_MAX_SEG) {
         ga_set_error("ga_sk_count_build: bad arguments (0 <= threshold <= 60000, table_slots a power of two in "
                      "256..%u, max_solid >= 1)", SB_MAX_SLOTS);
         return GA_ERR_BAD_ARG;
@@ -868,14 +974,15 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
         attr_set = true;
     }
     if (max_solid > 16000) max_solid = 16000;          // solid index + 1 lives in 16 bits
-    const unsigned grid = (unsigned)(n_buckets < 148ull ? n_buckets : 148ull);
+    const unsigned grid = (unsigned)(n_buckets < 148ull * SB_CTAS_PER_SM ? n_buckets : 148ull * SB_CTAS_PER_SM);
     // count rides in the key word; (key << 4 | 15) is kept free so that it can never look like an empty slot
     const bool packed = 2 * w + 4 <= 64 && threshold <= 13;
 #define GA_SK_BUCKET(TAB)                                                                                          \
     sk_bucket_kernel<TAB><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                              \
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, (const u64*)hist_dev, n_buckets, w, \
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,                   \
+        (const u64*)hist_dev, n_buckets, w,                                                                        \
         (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity, \
-        (u64*)counters_dev, spill_list_dev, spill_capacity, status_dev)
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev)
     if (packed) GA_SK_BUCKET(TabPacked);
     else GA_SK_BUCKET(TabShared);
 #undef GA_SK_BUCKET
@@ -889,7 +996,7 @@ extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
 }
 
 extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                                       const uint32_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                                       uint32_t n_segments, uint64_t n_buckets, const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
                                        uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
                                        uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                                        uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
@@ -897,13 +1004,15 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
     const int w = k - 1;
     if (!bases_dev || !meta_dev || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
         !edge_stamp_out_dev || !counters_dev || !status_dev || w < 1 || w > 31 || threshold < 0 ||
-        !is_pow2(table_slots) || table_slots < 256 || n_ctas == 0) {
+        !is_pow2(table_slots) || table_slots < 256 || n_ctas == 0 || n_segments == 0 || n_segments > SB_MAX_SEG ||
+        n_buckets == 0) {
         ga_set_error("ga_sk_count_build_spill: bad arguments");
         return GA_ERR_BAD_ARG;
     }
     if (n_spill == 0) return GA_OK;
     sk_bucket_spill_kernel<<<n_ctas, SB_THREADS, 0, (cudaStream_t)stream>>>(
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, spill_list_dev, n_spill, w,
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments, n_buckets,
+        (const u64*)spill_list_dev, n_spill, w,
         (u32)(threshold > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : threshold), table_slots, (unsigned char*)scratch_dev,
         ga_sk_spill_scratch_bytes(table_slots), (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
         (u64*)counters_dev, status_dev);

@@ -26,7 +26,7 @@ TWO_PHASE_MIN_STEP = 1 << 20
 # bucketed (super-k-mer) count + build, csrc/ga_superkmer.cu: unpaired DNA, 64-bit keys
 SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
 SUPERKMER_TARGET = 16384                # windows per bucket aimed for
-SUPERKMER_TABLE_SLOTS = 16384           # shared-memory table slots per bucket (tests shrink it to force spills)
+SUPERKMER_TABLE_SLOTS = 8192            # shared-memory table slots per bucket (tests shrink it to force spills)
 SUPERKMER_MAX_SOLID = 16000             # solid windows per bucket (further bounded by the shared-memory pool)
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
@@ -512,11 +512,14 @@ def _record_groups(reads: "DeviceReads", w: int) -> int:
     return int((-(-win // 32)).sum())
 
 
-def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
+def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
     """reads -> (solid keys (n, 1) int64, n, candidate edge stamps int64[4n]) through the bucketed
     pipeline of csrc/ga_superkmer.cu: scatter records to level-1 buckets, split into final buckets,
     count + stamp per bucket in shared memory.  Exact: same solid set and stamps as counting every
-    window in one table (debruijn_graph.py:144-152, 113-142)."""
+    window in one table (debruijn_graph.py:144-152, 113-142).
+
+    `feed` (optional) yields read ranges (r0, r1) as they become resident on the device -- the
+    host-buffer entry streams chunks in while earlier chunks are already being scattered."""
     L = gn.lib()
     dev = _dev()
     w = k - 1
@@ -539,15 +542,20 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
         hist = torch.zeros(n_buckets, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_scatter1", n_occ):
-            gn.check(L.ga_sk_scatter_reads(C.byref(reads.struct()), k, l1_bits, l2_bits, gn.ptr(rec_bases),
-                                           gn.ptr(rec_meta), cap1, gn.ptr(cursors1), gn.ptr(hist), gn.ptr(status),
-                                           _stream()))
+            for r0, r1 in (feed if feed is not None else ((0, reads.n_reads),)):
+                gn.check(L.ga_sk_scatter_reads(C.byref(reads.struct_range(r0, r1)), k, l1_bits, l2_bits,
+                                               gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1),
+                                               gn.ptr(hist), gn.ptr(status), _stream()))
+            feed = None                     # a retry finds every read resident
         offsets = torch.empty(n_buckets + 1, dtype=torch.int64, device=dev)
         cursors2 = torch.empty(n_buckets, dtype=torch.int64, device=dev)
         with _timed("sk_offsets"):
             gn.check(L.ga_sk_offsets(gn.ptr(hist), n_buckets, gn.ptr(offsets), gn.ptr(cursors2), _stream()))
         total = int(offsets[n_buckets].item())
-        if not _check_status(status) & gn.ST_TABLE_FULL:
+        st = _check_status(status)
+        if st & gn.ST_BAD_SYMBOL:
+            raise ValueError("read symbol outside the alphabet")
+        if not st & gn.ST_TABLE_FULL:
             break
         cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
         del rec_bases, rec_meta
@@ -566,12 +574,12 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
     spill_cap = 1 << 16
     while True:
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
-        spill_list = torch.empty(spill_cap, dtype=torch.int32, device=dev)
+        spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
         solid_keys = torch.empty((out_cap, 1), dtype=torch.int64, device=dev)
         edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_bucket", n_occ):
-            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), gn.ptr(hist), n_buckets, k, int(threshold),
+            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), 1, gn.ptr(hist), n_buckets, k, int(threshold),
                                          SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
                                          gn.ptr(edge_stamp), out_cap, gn.ptr(counters), gn.ptr(spill_list), spill_cap,
                                          gn.ptr(status), _stream()))
@@ -580,7 +588,7 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
             spill_cap = n_spill
             continue
         if n_spill:
-            ids = spill_list[:n_spill].long()
+            ids = spill_list[:n_spill] & 0xFFFFFFFF
             records = int((offsets[ids + 1] - offsets[ids]).max().item())
             slots = 256
             while slots < 2 * 32 * records:
@@ -590,7 +598,7 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int):
             n_ctas = max(1, min(n_spill, 148, int(free * 0.4) // per_cta))
             scratch = torch.empty(n_ctas * per_cta, dtype=torch.uint8, device=dev)
             with _timed("sk_bucket_spill"):
-                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), gn.ptr(spill_list),
+                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), 1, n_buckets, gn.ptr(spill_list),
                                                    n_spill, k, int(threshold), slots, gn.ptr(scratch), n_ctas,
                                                    gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
                                                    gn.ptr(status), _stream()))
@@ -680,8 +688,16 @@ def _solid_keys_from_flags(counts: KmerCounts, keep_fn):
     return torch.from_numpy(sel.view(np.int64)).to(_dev()), sel.shape[0]
 
 
+def _to_host(tensor: torch.Tensor, n: int) -> torch.Tensor:
+    """First n rows of a device tensor -> pinned host tensor (async; the caller synchronises)."""
+    out = torch.empty((n,) + tuple(tensor.shape[1:]), dtype=tensor.dtype, pin_memory=True)
+    if n:
+        out.copy_(tensor[:n], non_blocking=True)
+    return out
+
+
 def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=None, keep_fn=None,
-                to_host: bool = True):
+                to_host: bool = True, feed=None):
     """count table (+ optional sketch) + reads -> BuiltGraph (or device tensors)."""
     L = gn.lib()
     dev = _dev()
@@ -692,7 +708,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
                 counts.n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(reads, k, threshold))
     edge_stamp = None
     if bucketed:
-        solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold)
+        solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold, feed)
     elif keep_fn is not None:
         solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
     else:
@@ -788,13 +804,15 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         graph.device = dict(rowptr=rowptr, col=col, indeg=indeg, branching=branching, last_sym=last_sym,
                             keys_a=keys_a, keys_b=keys_b)
         return graph
-    graph.rowptr = rowptr.cpu().numpy()
-    graph.col = col[:ne].cpu().numpy()
-    graph.indeg = indeg[:nn].cpu().numpy()
-    graph.branching = branching[:nn].cpu().numpy()
-    graph.last_char = alphabet.inv[last_sym[:nn].cpu().numpy()]
-    graph.keys_a = keys_a[:nn].cpu().numpy().view(np.uint64)
-    graph.keys_b = keys_b[:nn].cpu().numpy().view(np.uint64) if reads.paired else None
+    # D2H through pinned buffers; the code -> byte mapping of the last symbol happens on the device
+    last_char = alphabet.inv_dev[last_sym[:nn].long()] if nn else last_sym[:0]
+    host = [_to_host(rowptr, nn + 1), _to_host(col, ne), _to_host(indeg, nn), _to_host(branching, nn),
+            _to_host(last_char, nn), _to_host(keys_a, nn), _to_host(keys_b, nn) if reads.paired else None]
+    torch.cuda.current_stream().synchronize()
+    graph._pinned = host                       # the numpy views below alias these buffers
+    graph.rowptr, graph.col, graph.indeg, graph.branching, graph.last_char = (t.numpy() for t in host[:5])
+    graph.keys_a = host[5].numpy().view(np.uint64)
+    graph.keys_b = host[6].numpy().view(np.uint64) if reads.paired else None
     return graph
 
 
@@ -892,9 +910,59 @@ def device_step(reads: DeviceReads, k: int, threshold: int, timers=None):
         TIMERS = None
 
 
+_STREAM_CHUNK_BYTES = 256 << 20
+_copy_stream = {}
+
+
+def _stream_in(ascii_pinned: torch.Tensor, reads: DeviceReads, read_len: int):
+    """Generator: copies the reads host -> device chunk by chunk on a side stream (two staging buffers),
+    packs each chunk on the current stream, and yields its read range -- so the consumer's kernels on
+    chunk i overlap the copy of chunk i+1."""
+    L = gn.lib()
+    dev = _dev()
+    n = reads.n_reads
+    per_chunk = max(1, _STREAM_CHUNK_BYTES // max(read_len, 1))
+    side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+    main = torch.cuda.current_stream()
+    stage = [torch.empty(min(n, per_chunk) * read_len, dtype=torch.uint8, device=dev) for _ in range(2)]
+    free = [None, None]
+    lut = reads.alphabet.lut_dev
+    side.wait_stream(main)
+    for i, r0 in enumerate(range(0, n, per_chunk)):
+        r1 = min(n, r0 + per_chunk)
+        buf = stage[i & 1][:(r1 - r0) * read_len]
+        if free[i & 1] is not None:
+            side.wait_event(free[i & 1])
+        with torch.cuda.stream(side):
+            buf.copy_(ascii_pinned[r0 * read_len:r1 * read_len], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        main.wait_event(ready)
+        gn.check(L.ga_pack_reads(gn.ptr(buf), None, r1 - r0, read_len, gn.ptr(lut), reads.alphabet.storage_bits,
+                                 reads.words.data_ptr() + r0 * reads.stride_words * 8, None, reads.stride_words,
+                                 gn.ptr(reads.status), _stream()))
+        free[i & 1] = torch.cuda.Event()
+        free[i & 1].record(main)
+        yield r0, r1
+    for t in stage:
+        t.record_stream(main)
+
+
 def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: bool, k: int, threshold: int):
     """The same from host memory: ASCII reads (pinned) -> H2D -> pack -> count -> filter -> build ->
-    CSR arrays on the host.  This is the call bench.py times as `e2e`."""
+    CSR arrays on the host.  This is the call bench.py times as `e2e`.  Unpaired DNA streams in by
+    chunks so that the copy overlaps the scatter kernel; other inputs copy first."""
+    alphabet = Alphabet(np.zeros(0))
+    spw = 64 // alphabet.storage_bits
+    stride = max(1, -(-int(read_len) // spw))
+    probe = DeviceReads.from_packed(torch.empty(0, dtype=torch.int64, device=_dev()), n_reads, read_len, paired,
+                                    estride=read_len, alphabet=alphabet)
+    n_occ = probe.windows_total(k)
+    if not paired and n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(probe, k, threshold):
+        words = torch.empty(max(1, n_reads * stride), dtype=torch.int64, device=_dev())
+        reads = DeviceReads.from_packed(words, n_reads, read_len, False, estride=read_len, alphabet=alphabet)
+        counts = KmerCounts(k, reads)
+        return build_graph(counts, reads, threshold, to_host=True, feed=_stream_in(ascii_pinned, reads, read_len))
     reads = DeviceReads.from_ascii(ascii_pinned, n_reads, read_len, paired, estride=read_len)
     counts = KmerCounts(k, reads)
     if _check_status(reads.status) & gn.ST_BAD_SYMBOL:

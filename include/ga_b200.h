@@ -194,23 +194,30 @@ int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offset
 int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
                           const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
                           void* out_bases_dev, uint64_t* out_meta_dev, ga_stream stream);
-/* One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
+/* offsets_dev holds n_segments rows of n_buckets+1 positions: the records of bucket b are the union of
+ * [offsets[s][b], offsets[s][b+1]) over the segments s (one segment on a single GPU; after the
+ * multi-GPU exchange, one per source rank, each sorted by bucket).  hist_dev[b] & 0xFFFFFFFF = windows
+ * of bucket b over all segments.
+ * One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
  * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
  * stamps (edge_stamp_out_dev[4*i + c] = smallest occurrence ordinal of "window i followed by symbol
  * c", all-ones if never).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
  * windows found (may exceed out_capacity: nothing is written beyond it, the caller retries with
- * that many), [2] buckets that did not fit and were listed in spill_list_dev. */
+ * that many), [2] passes that did not fit and were listed in spill_list_dev.  A bucket whose distinct
+ * or solid windows exceed the pool is done in 2, 4, ... 32 passes over disjoint hash ranges of its
+ * windows, still in shared memory; only what would need more is listed (entry = bucket | passes << 32
+ * | pass << 48). */
 int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                      const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
+                      uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
                       uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
-                      uint64_t out_capacity, uint64_t* counters_dev, uint32_t* spill_list_dev,
+                      uint64_t out_capacity, uint64_t* counters_dev, uint64_t* spill_list_dev,
                       uint64_t spill_capacity, uint32_t* status_dev, ga_stream stream);
 /* The listed buckets again with tables in global scratch (n_ctas slices of
  * ga_sk_spill_scratch_bytes(table_slots) bytes; table_slots >= twice the windows of the largest). */
 uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots);
 int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                            const uint32_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                            uint32_t n_segments, uint64_t n_buckets, const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
                             uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
                             uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                             uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,

@@ -13,6 +13,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on \
     -k regex:'sk_bucket_kernel|sk_scatter_reads_kernel|sk_scatter_buckets_kernel' -s 3 -c 3 \
     -o gpurun_out/prof_sk -f $CMD > gpurun_out/ncu_full_sk.log 2>&1
 echo "full capture exit $?"
-GA_TRACE=1 python bench.py --workload c2 --steps 2 --warmup 1 --sample-reads 2000 > gpurun_out/trace_c2.log 2>&1
-tail -80 gpurun_out/trace_c2.log | head -70
-ls -la gpurun_out | tail -8
+GA_TRACE=1 python bench.py --workload c4 --steps 2 --warmup 1 --sample-reads 2000 > gpurun_out/trace_c4.log 2>&1
+grep trace gpurun_out/trace_c4.log | tail -40
