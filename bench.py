@@ -273,6 +273,32 @@ def run_gpu_arm(args):
 
     # end to end through the host-buffer entry (ASCII reads in pinned memory -> CSR on the host)
     e2e = None
+    if world > 1 and not paired:
+        import ga_multi
+        ascii_dev = torch.empty(n_local * read_len, dtype=torch.uint8, device=dev)
+        gn.check(L.ga_unpack_reads(gn.ptr(words), n_local, read_len, stride, 2, gn.ptr(reads.alphabet.inv_dev),
+                                   gn.ptr(ascii_dev), None))
+        pinned = torch.empty(ascii_dev.shape, dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(ascii_dev)
+        torch.cuda.synchronize()
+        del ascii_dev
+        for _ in range(max(1, min(args.warmup, 2))):
+            ga_multi.sharded_host_step(pinned, n_local, read_len, lo, k, F)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            graph = ga_multi.sharded_host_step(pinned, n_local, read_len, lo, k, F)
+            if graph is not None:
+                d2h = sum(a.nbytes for a in (graph.rowptr, graph.col, graph.indeg, graph.branching,
+                                             graph.last_char, graph.keys_a))
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": occ_total / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(n_reads * read_len),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
     if world == 1:
         ascii_dev = torch.empty(n_local * mates * read_len, dtype=torch.uint8, device=dev)
         gn.check(L.ga_unpack_reads(gn.ptr(words), n_local * mates, read_len, stride, 2,

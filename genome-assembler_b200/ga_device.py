@@ -512,26 +512,26 @@ def _record_groups(reads: "DeviceReads", w: int) -> int:
     return int((-(-win // 32)).sum())
 
 
-def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
-    """reads -> (solid keys (n, 1) int64, n, candidate edge stamps int64[4n]) through the bucketed
-    pipeline of csrc/ga_superkmer.cu: scatter records to level-1 buckets, split into final buckets,
-    count + stamp per bucket in shared memory.  Exact: same solid set and stamps as counting every
-    window in one table (debruijn_graph.py:144-152, 113-142).
-
-    `feed` (optional) yields read ranges (r0, r1) as they become resident on the device -- the
-    host-buffer entry streams chunks in while earlier chunks are already being scattered."""
-    L = gn.lib()
-    dev = _dev()
-    w = k - 1
-    n_occ = reads.windows_total(k)
-    m = L.ga_sk_minimizer_len(k)
-    per_window = w - m + 1
+def sk_geometry(n_occ: int):
+    """(level-1 bits, level-2 bits) of the bucket id for `n_occ` window occurrences IN TOTAL (all
+    ranks): about SUPERKMER_TARGET windows per bucket, at most 2^20 buckets."""
     bits = 0
     while bits < 20 and (n_occ >> bits) > SUPERKMER_TARGET:
         bits += 1
     l2_bits = min(10, bits)
-    l1_bits = bits - l2_bits
-    n_l1, n_buckets = 1 << l1_bits, 1 << bits
+    return bits - l2_bits, l2_bits
+
+
+def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None):
+    """This rank's reads -> records sorted by bucket: (bases int64[2*total], meta int64[total],
+    offsets int64[n_buckets+1], hist int64[n_buckets] = records << 32 | windows, total).
+    ga_sk_scatter_reads + ga_sk_offsets + ga_sk_scatter_buckets."""
+    L = gn.lib()
+    dev = _dev()
+    w = k - 1
+    n_occ = reads.windows_total(k)
+    per_window = w - L.ga_sk_minimizer_len(k) + 1
+    n_l1, n_buckets = 1 << l1_bits, 1 << (l1_bits + l2_bits)
     status = reads.status
     est = int(n_occ * 2.0 / (per_window + 1)) + _record_groups(reads, w)
     cap1 = int(est / n_l1 * 1.15) + 4096
@@ -567,6 +567,17 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
                                          gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), _stream()))
     del rec_bases, rec_meta
     _mark("sk scatter buckets")
+    return bases, meta, offsets, hist, total
+
+
+def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, k: int, threshold: int,
+                   n_occ: int, status):
+    """Bucket-sorted records -> (solid keys (cap, 1) int64, n_solid, candidate edge stamps int64[4*cap]).
+    offsets: n_segments rows of n_buckets+1 record positions (one row on a single GPU, one per source
+    rank after the multi-GPU exchange); hist[b] & 0xFFFFFFFF = windows of bucket b over all segments.
+    ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
+    L = gn.lib()
+    dev = bases.device
     free, _ = torch.cuda.mem_get_info()
     out_cap = max(1 << 16, n_occ // 16 + 1024)
     if out_cap * 40 > free * 0.6:
@@ -579,29 +590,28 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
         edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_bucket", n_occ):
-            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), 1, gn.ptr(hist), n_buckets, k, int(threshold),
-                                         SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
-                                         gn.ptr(edge_stamp), out_cap, gn.ptr(counters), gn.ptr(spill_list), spill_cap,
-                                         gn.ptr(status), _stream()))
+            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
+                                         n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
+                                         gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
+                                         gn.ptr(spill_list), spill_cap, gn.ptr(status), _stream()))
         _, n_solid, n_spill, _ = (int(v) for v in counters.cpu().tolist())
         if n_spill > spill_cap:
             spill_cap = n_spill
             continue
         if n_spill:
-            ids = spill_list[:n_spill] & 0xFFFFFFFF
-            records = int((offsets[ids + 1] - offsets[ids]).max().item())
+            windows = int((hist[spill_list[:n_spill] & 0xFFFFFFFF] & 0xFFFFFFFF).max().item())
             slots = 256
-            while slots < 2 * 32 * records:
+            while slots < 2 * windows:
                 slots <<= 1
             per_cta = int(L.ga_sk_spill_scratch_bytes(slots))
             free, _ = torch.cuda.mem_get_info()
             n_ctas = max(1, min(n_spill, 148, int(free * 0.4) // per_cta))
             scratch = torch.empty(n_ctas * per_cta, dtype=torch.uint8, device=dev)
             with _timed("sk_bucket_spill"):
-                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), 1, n_buckets, gn.ptr(spill_list),
-                                                   n_spill, k, int(threshold), slots, gn.ptr(scratch), n_ctas,
-                                                   gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
-                                                   gn.ptr(status), _stream()))
+                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, n_buckets,
+                                                   gn.ptr(spill_list), n_spill, k, int(threshold), slots,
+                                                   gn.ptr(scratch), n_ctas, gn.ptr(solid_keys), gn.ptr(edge_stamp),
+                                                   out_cap, gn.ptr(counters), gn.ptr(status), _stream()))
             n_solid = int(counters[1].item())
             del scratch
         if _check_status(status) & gn.ST_TABLE_FULL:
@@ -611,6 +621,43 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
         out_cap = n_solid
     _mark("sk bucket pass")
     return solid_keys, n_solid, edge_stamp
+
+
+def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
+    """reads -> (solid keys (n, 1) int64, n, candidate edge stamps int64[4n]) through the bucketed
+    pipeline of csrc/ga_superkmer.cu: scatter records to level-1 buckets, split into final buckets,
+    count + stamp per bucket in shared memory.  Exact: same solid set and stamps as counting every
+    window in one table (debruijn_graph.py:144-152, 113-142).
+
+    `feed` (optional) yields read ranges (r0, r1) as they become resident on the device -- the
+    host-buffer entry streams chunks in while earlier chunks are already being scattered."""
+    n_occ = reads.windows_total(k)
+    l1_bits, l2_bits = sk_geometry(n_occ)
+    bases, meta, offsets, hist, _ = sk_scatter_local(reads, k, l1_bits, l2_bits, feed)
+    return sk_bucket_pass(bases, meta, offsets, 1, hist, 1 << (l1_bits + l2_bits), k, threshold, n_occ, reads.status)
+
+
+def resolve_and_emit(graph, solid_keys, n_solid: int, edge_stamp, k: int, alphabet, status, to_host: bool):
+    """Solid keys + candidate edge stamps (the output of the bucket pass) -> CSR: id table over the
+    solid keys, ga_sk_resolve, then the shared DNA CSR emission."""
+    L = gn.lib()
+    dev = solid_keys.device
+    kw = 1
+    solid_cap = int(1.7 * n_solid) + 64
+    solid = torch.empty(solid_cap * L.ga_slot_bytes(kw), dtype=torch.uint8, device=dev)
+    status.zero_()
+    with _timed("id_table"):
+        gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, _stream()))
+        gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap, gn.ptr(status),
+                                       _stream()))
+    node_stamp = torch.full((n_solid,), -1, dtype=torch.int64, device=dev)
+    with _timed("sk_resolve"):
+        gn.check(L.ga_sk_resolve(gn.ptr(solid_keys), n_solid, k, gn.ptr(solid), solid_cap, gn.ptr(edge_stamp),
+                                 gn.ptr(node_stamp), _stream()))
+    out = emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_cap, kw, k, alphabet, to_host)
+    if _check_status(status) & gn.ST_TABLE_FULL:
+        raise gn.GaError("id table overflow")
+    return out
 
 
 # ----------------------------------------------------------------------------------- build
@@ -889,12 +936,13 @@ def emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_c
         graph.device = dict(rowptr=rowptr, col=col, indeg=indeg, branching=branching, last_sym=last_sym,
                             keys_a=keys_a, keys_b=None)
         return graph
-    graph.rowptr = rowptr.cpu().numpy()
-    graph.col = col[:ne].cpu().numpy()
-    graph.indeg = indeg[:nn].cpu().numpy()
-    graph.branching = branching[:nn].cpu().numpy()
-    graph.last_char = alphabet.inv[last_sym[:nn].cpu().numpy()]
-    graph.keys_a = keys_a[:nn].cpu().numpy().view(np.uint64)
+    last_char = alphabet.inv_dev[last_sym[:nn].long()] if nn else last_sym[:0]
+    host = [_to_host(rowptr, nn + 1), _to_host(col, ne), _to_host(indeg, nn), _to_host(branching, nn),
+            _to_host(last_char, nn), _to_host(keys_a, nn)]
+    torch.cuda.current_stream().synchronize()
+    graph._pinned = host
+    graph.rowptr, graph.col, graph.indeg, graph.branching, graph.last_char = (t.numpy() for t in host[:5])
+    graph.keys_a = host[5].numpy().view(np.uint64)
     return graph
 
 

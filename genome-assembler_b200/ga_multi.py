@@ -12,8 +12,19 @@ Per pass (every exchange is a torch.distributed collective over NCCL 
      arrays; an all-reduce(min) makes them global;
   6. rank 0 emits the CSR.  Stamps depend only on global read indices, so the graph is
      bit-identical for 1, 2, 4 or 8 GPUs.
-The helpers that only move tensors (`exchange_by_owner`, `all_gather_var`) are device-agnostic
-and are covered on the CPU with the gloo backend (tests/test_multi_host.py).
+The helpers that only move tensors (`exchange_by_owner`, `all_gather_var`, `exchange_ranges`,
+`gather_rows`) are device-agnostic and are covered on the CPU with the gloo backend
+(tests/test_multi_host.py).
+
+Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_buckets`, csrc/ga_superkmer.cu):
+  1. each rank cuts its read shard into super-k-mer records sorted by bucket (the bucket of a window
+     depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
+  2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
+     records of that range (one `all_to_all_single` per record array, plus the per-bucket histograms);
+  3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
+     segment per source rank;
+  4. solid keys + candidate edge stamps are gathered on rank 0, which resolves them into the CSR.
+Ordinals are global (read index * stride + position), so the graph is bit-identical for any rank count.
 """
 from __future__ import annotations
 
@@ -56,6 +67,29 @@ def exchange_by_owner(owner: torch.Tensor, payloads, group=None):
     return received
 
 
+def exchange_ranges(src: torch.Tensor, send_rows, group=None):
+    """All-to-all of contiguous row ranges: the first send_rows[0] rows of `src` go to rank 0, the next
+    send_rows[1] to rank 1, ...  Returns (received rows, rows received from each rank)."""
+    world = dist.get_world_size(group)
+    send = torch.tensor(list(send_rows), dtype=torch.int64, device=src.device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_rows = [int(x) for x in recv.tolist()]
+    dst = torch.empty((sum(recv_rows),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    dist.all_to_all_single(dst, src.contiguous(), output_split_sizes=recv_rows,
+                           input_split_sizes=[int(x) for x in send_rows], group=group)
+    assert len(recv_rows) == world
+    return dst, recv_rows
+
+
+def gather_rows(local: torch.Tensor, dst: int = 0, group=None):
+    """Rows of every rank concatenated on rank `dst` (rank order); other ranks get an empty tensor."""
+    world = dist.get_world_size(group)
+    send_rows = [local.shape[0] if g == dst else 0 for g in range(world)]
+    out, _ = exchange_ranges(local, send_rows, group)
+    return out
+
+
 _SIGN = -(1 << 63)
 
 
@@ -68,7 +102,7 @@ def all_reduce_min_u64(stamps: torch.Tensor, group=None):
     return stamps
 
 
-def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = False):
+def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = False, feed=None):
     """One pass of the hot path over this rank's read shard; returns the graph on rank 0 (a
     BuiltGraph whose CSR stays on the device unless to_host) and None elsewhere."""
     import ga_native as gn
@@ -79,9 +113,69 @@ def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = Fal
         raise NotImplementedError("multi-GPU pre-filter needs 0 <= threshold and (threshold+1)*ranks <= 255")
     gd.TIMERS = timers
     try:
+        if gd.superkmer_supported(reads, k, threshold) and USE_BUCKETS:
+            return _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed)
+        if feed is not None:
+            for _ in feed:      # the table route walks resident reads: drain the stream first
+                pass
         return _sharded_step(reads, k, threshold, to_host, gn, gd)
     finally:
         gd.TIMERS = None
+
+
+USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
+
+
+def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
+    dev = reads.words.device
+    world, rank = dist.get_world_size(), dist.get_rank()
+    occ = torch.tensor([reads.windows_total(k)], dtype=torch.int64, device=dev)
+    dist.all_reduce(occ)
+    n_occ = int(occ.item())
+    l1_bits, l2_bits = gd.sk_geometry(n_occ)
+    n_buckets = 1 << (l1_bits + l2_bits)
+    # 1. local records sorted by bucket
+    bases, meta, offsets, hist, total = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed)
+    # 2. rank g owns buckets [bounds[g], bounds[g+1])
+    bounds = [g * n_buckets // world for g in range(world + 1)]
+    cut = offsets[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
+    send_rows = [int(cut[g + 1] - cut[g]) for g in range(world)]
+    with gd._timed("exchange"):
+        got_bases, recv_rows = exchange_ranges(bases.view(-1, 2)[:total], send_rows)
+        got_meta, _ = exchange_ranges(meta[:total], send_rows)
+        got_hist, _ = exchange_ranges(hist, [bounds[g + 1] - bounds[g] for g in range(world)])
+    del bases, meta
+    mine = bounds[rank + 1] - bounds[rank]
+    graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
+    if mine:
+        # 3. one segment per source rank: positions from the per-source record counts
+        per_source = got_hist.view(world, mine)
+        seg_offsets = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
+        seg_offsets[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
+        starts = [0]
+        for rows in recv_rows[:-1]:
+            starts.append(starts[-1] + rows)
+        seg_offsets += torch.tensor(starts, dtype=torch.int64, device=dev).view(world, 1)
+        summed = per_source.sum(dim=0).contiguous()
+        n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
+        solid_keys, n_solid, edge_stamp = gd.sk_bucket_pass(
+            got_bases.contiguous().view(-1), got_meta.contiguous(), seg_offsets.contiguous(), world, summed, mine,
+            k, threshold, max(n_occ_mine, 1), reads.status)
+    else:
+        solid_keys = torch.zeros((0, 1), dtype=torch.int64, device=dev)
+        edge_stamp = torch.zeros(0, dtype=torch.int64, device=dev)
+        n_solid = 0
+    # 4. everything solid meets on rank 0
+    with gd._timed("gather"):
+        all_keys = gather_rows(solid_keys[:n_solid])
+        all_stamps = gather_rows(edge_stamp[:4 * n_solid].view(-1, 4))
+    if rank != 0:
+        return None
+    n_all = all_keys.shape[0]
+    if n_all == 0:
+        return graph
+    return gd.resolve_and_emit(graph, all_keys.contiguous(), n_all, all_stamps.contiguous().view(-1), k, reads.alphabet,
+                               reads.status, to_host)
 
 
 def _sharded_step(reads, k, threshold, to_host, gn, gd):
@@ -175,3 +269,17 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
     # 6. CSR on rank 0
     return gd.emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_cap, kw, k, reads.alphabet,
                         to_host)
+
+
+def sharded_host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, first_read: int, k: int,
+                      threshold: int):
+    """Host-buffer entry of the sharded build: this rank's reads as ASCII in pinned host memory ->
+    (streamed H2D + pack overlapped with the scatter) -> exchange -> CSR arrays on rank 0's host."""
+    import numpy as np
+    import ga_device as gd
+    alphabet = gd.Alphabet(np.zeros(0))
+    stride = max(1, -(-int(read_len) // 32))
+    words = torch.empty(max(1, n_reads * stride), dtype=torch.int64, device=gd._dev())
+    reads = gd.DeviceReads.from_packed(words, n_reads, read_len, False, first_read=first_read, estride=read_len,
+                                       alphabet=alphabet)
+    return sharded_step(reads, k, threshold, to_host=True, feed=gd._stream_in(ascii_pinned, reads, read_len))

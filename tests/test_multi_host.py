@@ -42,6 +42,21 @@ def _worker(rank, world, port, results):
             src = kk // 1000
             assert cc == ((kk % 1000) + 1) * (src + 1)
 
+        # contiguous range exchange: rank r sends r+1 rows to rank 0 and 2 rows to rank 1
+        rows = torch.arange((rank + 1 + 2) * 3, dtype=torch.int64).reshape(-1, 3) + 1000 * rank
+        got, recv_rows = ga_multi.exchange_ranges(rows, [rank + 1, 2])
+        if rank == 0:
+            assert recv_rows == [1, 2] and got[:, 0].tolist() == [0, 1000, 1003]
+        else:
+            assert recv_rows == [2, 2] and got[:, 0].tolist() == [3, 6, 1006, 1009]
+        # gather on rank 0 (rank 1 contributes nothing the second time)
+        cat = ga_multi.gather_rows(rows[:rank + 1])
+        assert cat.shape[0] == (3 if rank == 0 else 0)
+        if rank == 0:
+            assert cat[:, 0].tolist() == [0, 1000, 1003]
+        cat = ga_multi.gather_rows(rows[:0] if rank == 1 else rows[:2])
+        assert cat.shape[0] == (2 if rank == 0 else 0)
+
         # unsigned minimum with all-ones meaning "no stamp"
         stamps = torch.full((6,), -1, dtype=torch.int64)
         if rank == 0:
