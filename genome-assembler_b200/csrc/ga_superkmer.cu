@@ -104,6 +104,8 @@ __device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n, u32 n_l1, ulonglon
 // One warp per read and round.  Lane l owns the four consecutive window positions 4l..4l+3 of the
 // current 128-window chunk, so the sliding minimum over a window's m-mers needs the lane's own
 // values plus whole-lane minima of up to three following lanes and a prefix of one more.
+// NMM: m-mers per window when known at compile time (16 for k >= 27, the common case), 0 = runtime.
+template <int NMM>
 __global__ void __launch_bounds__(S1_THREADS)
 sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ulonglong2* __restrict__ out_bases,
                         u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors, u64* __restrict__ ghist,
@@ -113,7 +115,7 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u32 n_l1 = 1u << l1_bits;
     const int bits = l1_bits + l2_bits;
-    const u32 n = (u32)(w - m + 1);                       // m-mers per window, 1..16
+    const u32 n = NMM ? (u32)NMM : (u32)(w - m + 1);      // m-mers per window, 1..16
     const u32 mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
     const u32 lt_mask = (1u << lane) - 1u;
     bool overflow = false;
@@ -266,13 +268,34 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
 
 // ------------------------------------------------------------------------------------------------
 // 2. histogram -> offsets; level-1 buckets -> final buckets
-__global__ void __launch_bounds__(1024) sk_offsets_kernel(const u64* __restrict__ hist, u64 n, u64* __restrict__ offsets,
-                                                          u64* __restrict__ cursors) {
-    __shared__ u64 part[1024];
-    const u64 span = (n + 1023) / 1024;
-    const u64 lo = min(n, threadIdx.x * span), hi = min(n, lo + span);
+// exclusive prefix sum of the per-bucket record counts, three small kernels: per-tile sums, a scan of
+// the tile sums (one CTA), per-tile scan + write
+constexpr u32 OFF_TILE = 2048;      // buckets per CTA (256 threads x 8)
+
+__global__ void __launch_bounds__(256) sk_offsets_tile_sums_kernel(const u64* __restrict__ hist, u64 n, u64* __restrict__ tile_sum) {
+    __shared__ u64 part[8];
+    const u64 base = (u64)blockIdx.x * OFF_TILE;
     u64 sum = 0;
-    for (u64 i = lo; i < hi; ++i) sum += hist[i] >> 32;
+    for (u32 j = 0; j < 8; ++j) {
+        const u64 i = base + j * 256u + threadIdx.x;
+        if (i < n) sum += hist[i] >> 32;
+    }
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(FULL, sum, off);
+    if ((threadIdx.x & 31u) == 0) part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 t = 0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) sk_offsets_scan_tiles_kernel(u64* __restrict__ tile_sum, u64 n_tiles, u64* __restrict__ total_out) {
+    __shared__ u64 part[1024];
+    const u64 span = (n_tiles + 1023) / 1024;
+    const u64 lo = min(n_tiles, threadIdx.x * span), hi = min(n_tiles, lo + span);
+    u64 sum = 0;
+    for (u64 i = lo; i < hi; ++i) sum += tile_sum[i];
     part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -282,14 +305,53 @@ __global__ void __launch_bounds__(1024) sk_offsets_kernel(const u64* __restrict_
             part[i] = run;
             run += t;
         }
-        offsets[n] = run;
+        *total_out = run;
     }
     __syncthreads();
     u64 run = part[threadIdx.x];
     for (u64 i = lo; i < hi; ++i) {
-        offsets[i] = run;
-        cursors[i] = run;
-        run += hist[i] >> 32;
+        const u64 t = tile_sum[i];
+        tile_sum[i] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(256) sk_offsets_write_kernel(const u64* __restrict__ hist, u64 n, const u64* __restrict__ tile_base,
+                                                               u64* __restrict__ offsets, u64* __restrict__ cursors) {
+    __shared__ u64 warp_base[8];
+    const u64 first = (u64)blockIdx.x * OFF_TILE + (u64)threadIdx.x * 8u;     // 8 consecutive buckets per thread
+    u64 v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = first + j < n ? hist[first + j] >> 32 : 0ull;
+        sum += v[j];
+    }
+    const u32 lane = threadIdx.x & 31u;
+    u64 incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u64 t = __shfl_up_sync(FULL, incl, off);
+        if (lane >= (u32)off) incl += t;
+    }
+    if (lane == 31u) warp_base[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = tile_base[blockIdx.x];
+        for (int i = 0; i < 8; ++i) {
+            const u64 t = warp_base[i];
+            warp_base[i] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    u64 run = warp_base[threadIdx.x >> 5] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (first + j < n) {
+            offsets[first + j] = run;
+            cursors[first + j] = run;
+        }
+        run += v[j];
     }
 }
 
@@ -909,15 +971,22 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     ReadsView rv = ga_view(reads);
     static bool attr_set = false;
     if (!attr_set) {
-        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(S1Shared)));
+        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(S1Shared)));
         attr_set = true;
     }
     const u64 n_tiles = (rv.n_reads + S1_WARPS - 1) / S1_WARPS;
     const unsigned grid = (unsigned)(n_tiles < 148ull * 2 ? n_tiles : 148ull * 2);
-    sk_scatter_reads_kernel<<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(
-        rv, w, ga_sk_minimizer_len(k), l1_bits, l2_bits, (ulonglong2*)rec_bases_dev, (u64*)rec_meta_dev, l1_capacity,
-        (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev);
+    const int m = ga_sk_minimizer_len(k);
+#define GA_SK_SCATTER(NMM)                                                                                          \
+    sk_scatter_reads_kernel<NMM><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(                      \
+        rv, w, m, l1_bits, l2_bits, (ulonglong2*)rec_bases_dev, (u64*)rec_meta_dev, l1_capacity, (u64*)l1_cursors_dev, \
+        (u64*)hist_dev, status_dev)
+    if (w - m + 1 == 16) GA_SK_SCATTER(16);
+    else GA_SK_SCATTER(0);
+#undef GA_SK_SCATTER
     GA_LAUNCH_CHECK("sk_scatter_reads");
     return GA_OK;
 }
@@ -928,7 +997,16 @@ extern "C" int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint6
         ga_set_error("ga_sk_offsets: bad arguments");
         return GA_ERR_BAD_ARG;
     }
-    sk_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const u64*)hist_dev, n_buckets, (u64*)offsets_dev, (u64*)cursors_dev);
+    const u64 n_tiles = (n_buckets + OFF_TILE - 1) / OFF_TILE;
+    cudaStream_t st = (cudaStream_t)stream;
+    u64* tiles = nullptr;
+    GA_CUDA(cudaMallocAsync((void**)&tiles, n_tiles * sizeof(u64), st));
+    sk_offsets_tile_sums_kernel<<<(unsigned)n_tiles, 256, 0, st>>>((const u64*)hist_dev, n_buckets, tiles);
+    sk_offsets_scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, (u64*)offsets_dev + n_buckets);
+    sk_offsets_write_kernel<<<(unsigned)n_tiles, 256, 0, st>>>((const u64*)hist_dev, n_buckets, tiles, (u64*)offsets_dev,
+                                                               (u64*)cursors_dev);
+    ga_note_launches(2);
+    GA_CUDA(cudaFreeAsync(tiles, st));
     GA_LAUNCH_CHECK("sk_offsets");
     return GA_OK;
 }

@@ -43,7 +43,7 @@ def _mark(name):
         if _TRACE == 1:
             torch.cuda.synchronize()
         now = _time.perf_counter()
-        print("  [trace] %-28s %8.3f ms" % (name, (now - _last[0]) * 1e3))
+        print("  [trace r%s] %-28s %8.3f ms" % (_os.environ.get("RANK", "0"), name, (now - _last[0]) * 1e3), flush=True)
         _last[0] = _time.perf_counter()
 
 
@@ -70,6 +70,36 @@ def _stream():
 
 def _dev():
     return torch.device("cuda", torch.cuda.current_device())
+
+
+# Persistent device workspace for the large intermediates of the bucketed path (records, bucket-sorted
+# records, solid keys + stamps, id table).  They are tens of GB at BASELINE config C4; allocating them
+# anew every call makes the caching allocator release and re-acquire segments next to the 180 GB limit,
+# which costs more than some of the kernels.  A buffer is reused by the next call on the same device and
+# only ever grows.  All users run on the current stream, so reuse is stream-ordered.
+_WORKSPACE = {}
+
+
+def workspace(name: str, shape, dtype) -> torch.Tensor:
+    dev = _dev()
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = 1
+    for x in shape:
+        n *= x
+    need = max(n, 1) * torch.empty(0, dtype=dtype).element_size()
+    key = (dev.index, name)
+    buf = _WORKSPACE.get(key)
+    if buf is None or buf.numel() < need:
+        _WORKSPACE.pop(key, None)
+        buf = None                                       # drop the old buffer before growing
+        buf = torch.empty(need + need // 16 + 512, dtype=torch.uint8, device=dev)
+        _WORKSPACE[key] = buf
+    return buf[:n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(shape)
+
+
+def release_workspace():
+    """Give the persistent workspace back to the allocator."""
+    _WORKSPACE.clear()
 
 
 # ----------------------------------------------------------------------------------- alphabet
@@ -534,10 +564,10 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
     n_l1, n_buckets = 1 << l1_bits, 1 << (l1_bits + l2_bits)
     status = reads.status
     est = int(n_occ * 2.0 / (per_window + 1)) + _record_groups(reads, w)
-    cap1 = int(est / n_l1 * 1.15) + 4096
+    cap1 = int(est / n_l1 * 1.08) + 4096
     while True:
-        rec_bases = torch.empty(n_l1 * cap1 * 2, dtype=torch.int64, device=dev)
-        rec_meta = torch.empty(n_l1 * cap1, dtype=torch.int64, device=dev)
+        rec_bases = workspace("sk_l1_bases", n_l1 * cap1 * 2, torch.int64)
+        rec_meta = workspace("sk_l1_meta", n_l1 * cap1, torch.int64)
         cursors1 = torch.zeros(n_l1, dtype=torch.int64, device=dev)
         hist = torch.zeros(n_buckets, dtype=torch.int64, device=dev)
         status.zero_()
@@ -558,14 +588,12 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
         if not st & gn.ST_TABLE_FULL:
             break
         cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
-        del rec_bases, rec_meta
     _mark("sk scatter reads")
-    bases = torch.empty(max(total, 1) * 2, dtype=torch.int64, device=dev)
-    meta = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    bases = workspace("sk_bases", max(total, 1) * 2, torch.int64)
+    meta = workspace("sk_meta", max(total, 1), torch.int64)
     with _timed("sk_scatter2", n_occ):
         gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits, l2_bits,
                                          gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), _stream()))
-    del rec_bases, rec_meta
     _mark("sk scatter buckets")
     return bases, meta, offsets, hist, total
 
@@ -578,16 +606,14 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
     L = gn.lib()
     dev = bases.device
-    free, _ = torch.cuda.mem_get_info()
-    out_cap = max(1 << 16, n_occ // 16 + 1024)
-    if out_cap * 40 > free * 0.6:
-        out_cap = max(1 << 16, int(free * 0.6) // 40)
+    # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
+    out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16
     while True:
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
-        solid_keys = torch.empty((out_cap, 1), dtype=torch.int64, device=dev)
-        edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
+        solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
+        edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64)
         status.zero_()
         with _timed("sk_bucket", n_occ):
             gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),

@@ -67,15 +67,21 @@ def exchange_by_owner(owner: torch.Tensor, payloads, group=None):
     return received
 
 
-def exchange_ranges(src: torch.Tensor, send_rows, group=None):
+def exchange_ranges(src: torch.Tensor, send_rows, group=None, ws_name=None):
     """All-to-all of contiguous row ranges: the first send_rows[0] rows of `src` go to rank 0, the next
-    send_rows[1] to rank 1, ...  Returns (received rows, rows received from each rank)."""
+    send_rows[1] to rank 1, ...  Returns (received rows, rows received from each rank).  ws_name: take the
+    receive buffer from ga_device's persistent workspace instead of the allocator."""
     world = dist.get_world_size(group)
     send = torch.tensor(list(send_rows), dtype=torch.int64, device=src.device)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     recv_rows = [int(x) for x in recv.tolist()]
-    dst = torch.empty((sum(recv_rows),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    shape = (sum(recv_rows),) + tuple(src.shape[1:])
+    if ws_name is not None:
+        import ga_device as gd
+        dst = gd.workspace(ws_name, shape, src.dtype)
+    else:
+        dst = torch.empty(shape, dtype=src.dtype, device=src.device)
     dist.all_to_all_single(dst, src.contiguous(), output_split_sizes=recv_rows,
                            input_split_sizes=[int(x) for x in send_rows], group=group)
     assert len(recv_rows) == world
@@ -140,11 +146,13 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     bounds = [g * n_buckets // world for g in range(world + 1)]
     cut = offsets[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
     send_rows = [int(cut[g + 1] - cut[g]) for g in range(world)]
+    gd._mark("multi: cut")
     with gd._timed("exchange"):
-        got_bases, recv_rows = exchange_ranges(bases.view(-1, 2)[:total], send_rows)
-        got_meta, _ = exchange_ranges(meta[:total], send_rows)
+        got_bases, recv_rows = exchange_ranges(bases.view(-1, 2)[:total], send_rows, ws_name="sk_recv_bases")
+        got_meta, _ = exchange_ranges(meta[:total], send_rows, ws_name="sk_recv_meta")
         got_hist, _ = exchange_ranges(hist, [bounds[g + 1] - bounds[g] for g in range(world)])
     del bases, meta
+    gd._mark("multi: exchange")
     mine = bounds[rank + 1] - bounds[rank]
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
     if mine:
@@ -166,9 +174,11 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
         edge_stamp = torch.zeros(0, dtype=torch.int64, device=dev)
         n_solid = 0
     # 4. everything solid meets on rank 0
+    gd._mark("multi: bucket pass")
     with gd._timed("gather"):
         all_keys = gather_rows(solid_keys[:n_solid])
         all_stamps = gather_rows(edge_stamp[:4 * n_solid].view(-1, 4))
+    gd._mark("multi: gather")
     if rank != 0:
         return None
     n_all = all_keys.shape[0]
