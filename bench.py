@@ -65,6 +65,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.nvml = index, [], threading.Event(), None
+        self.period = float(os.environ.get("GA_CLOCK_PERIOD", "0.1"))   # seconds between NVML samples
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -93,7 +94,7 @@ class ClockSampler:
                 self.rows.append((sm, reasons))
             except Exception:
                 pass
-            self.stop_flag.wait(0.02)
+            self.stop_flag.wait(self.period)
 
     def stop(self):
         self.stop_flag.set()
@@ -110,7 +111,7 @@ class ClockSampler:
         for _, mask in self.rows:
             seen |= {name for name, bit in bits.items() if mask & bit}
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(seen),
-                "samples": len(sm), "source": "nvml, 20 ms period, during the timed region"}
+                "samples": len(sm), "source": "nvml, %d ms period, during the timed region" % int(self.period * 1e3)}
 
     def _smi_once(self):
         try:
@@ -255,6 +256,11 @@ def run_gpu_arm(args):
 
     # dominant-kernel roofline from the per-launch CUDA events recorded inside the timed steps
     # per kernel: total ms per step, launches per step, occurrences per launch (rank 0's shard)
+    marks = timers.pop("_marks", [])
+    stage_ms = {}
+    for (_, ev0), (name, ev1) in zip(marks, marks[1:]):
+        if name != "step begin":
+            stage_ms[name] = stage_ms.get(name, 0.0) + ev0.elapsed_time(ev1) / args.steps
     kernel_ms = {name: sum(a.elapsed_time(b) for a, b, _ in spans) / args.steps for name, spans in timers.items()}
     dominant = max(kernel_ms, key=kernel_ms.get)
     spans = timers[dominant]
@@ -265,7 +271,7 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms_per_step": kernel_ms, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
+                "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": stage_ms, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_occurrence": B_KERNEL.get(dominant, B_TOTAL),
                 "whole_path": {"achieved": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9,
                                "frac": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -287,7 +293,9 @@ def run_gpu_arm(args):
         barrier()
         t0 = time.perf_counter()
         d2h = 0
+        graph = None
         for _ in range(args.steps):
+            graph = None      # drop the previous result first: its pinned CSR buffers are then reused
             graph = ga_multi.sharded_host_step(pinned, n_local, read_len, lo, k, F)
             if graph is not None:
                 d2h = sum(a.nbytes for a in (graph.rowptr, graph.col, graph.indeg, graph.branching,
@@ -312,7 +320,9 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d2h = 0
+        graph = None
         for _ in range(args.steps):
+            graph = None      # drop the previous result first: its pinned CSR buffers are then reused
             graph = gd.host_step(pinned, n_local * mates, read_len, paired, k, F)
             d2h = sum(a.nbytes for a in (graph.rowptr, graph.col, graph.indeg, graph.branching,
                                          graph.last_char, graph.keys_a))

@@ -38,7 +38,13 @@ _last = [0.0]
 
 
 def _mark(name):
-    """GA_TRACE=1: print host wall time between stages (with a device sync) -- debugging aid."""
+    """Stage boundary.  With TIMERS set (bench.py) a CUDA event is recorded, so the GPU-timeline length of
+    every stage -- kernels AND the idle gaps in between -- can be reported.  GA_TRACE=1 additionally
+    prints host wall time between stages (with a device sync) -- debugging aid."""
+    if TIMERS is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TIMERS.setdefault("_marks", []).append((name, ev))
     if _TRACE:
         if _TRACE == 1:
             torch.cuda.synchronize()
@@ -978,8 +984,11 @@ def device_step(reads: DeviceReads, k: int, threshold: int, timers=None):
     global TIMERS
     TIMERS = timers
     try:
+        _mark("step begin")
         counts = KmerCounts(k, reads)
-        return build_graph(counts, reads, threshold, to_host=False)
+        out = build_graph(counts, reads, threshold, to_host=False)
+        _mark("step end")
+        return out
     finally:
         TIMERS = None
 
