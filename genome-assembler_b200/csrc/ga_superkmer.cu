@@ -419,6 +419,7 @@ constexpr int SB_CTAS_PER_SM = 2;
 constexpr u32 SB_MAX_SLOTS = 8192;
 constexpr u32 SB_POOL_BYTES = 106496;          // 104 KB of dynamic shared memory per CTA: table + solid keys + stamps
 constexpr u32 SB_PROBE_MAX = 192;
+constexpr u32 SB_MAX_FLAGS = 6144;             // records of a bucket that can carry a "walk again" flag
 constexpr u32 SB_MAX_SEG = 16;                // sources a bucket can be gathered from (multi-GPU exchange)
 
 __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
@@ -449,11 +450,6 @@ __device__ __forceinline__ u32 sh_ld32v(u32 a) {
     return v;
 }
 __device__ __forceinline__ void sh_st32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ u32 sh_ld16(u32 a) {
-    u16 v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ void sh_st16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((u16)v) : "memory"); }
 __device__ __forceinline__ u64 sh_cas64(u32 a, u64 cmp, u64 val) {
     u64 old;
@@ -461,8 +457,17 @@ __device__ __forceinline__ u64 sh_cas64(u32 a, u64 cmp, u64 val) {
     return old;
 }
 
+// Result of counting one occurrence of a window.
+enum : u32 {
+    CS_SOLID_BEFORE = 0,   // its count was above the threshold already
+    CS_BECAME_SOLID = 1,   // this occurrence took it above the threshold: the caller gives it a solid index
+    CS_NOT_YET = 2,        // still at or below the threshold after this occurrence
+    CS_TABLE_FULL = 3,
+    CS_INSERTED = 4        // OR-ed in when the occurrence created the entry (distinct-window statistics)
+};
+
 struct TabSharedBase {
-    u32 keys, cnt, skeys, stamps;               // shared byte addresses
+    u32 keys, cnt, sidx, flags, skeys, stamps;  // shared byte addresses
     __device__ __forceinline__ void skey_st(u32 i, u64 v) const { sh_st64(skeys + 8u * i, v); }
     __device__ __forceinline__ u64 skey_ld(u32 i) const { return sh_ld64(skeys + 8u * i); }
     __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { sh_st64(stamps + 8u * i, v); }
@@ -470,49 +475,66 @@ struct TabSharedBase {
     __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
         asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
     }
+    // solid index + 1 of a slot (0: none yet); published after the slot's stamps are initialised
+    __device__ __forceinline__ u32 sidx_ld(u32 s) const {
+        u16 v;
+        asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(sidx + 2u * s));
+        return v;
+    }
+    __device__ __forceinline__ void sidx_st(u32 s, u32 idx1) const { sh_st16(sidx + 2u * s, idx1); }
+    // per-record "walk me again" flags (bytes)
+    __device__ __forceinline__ void flag_set(u32 i) const {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(flags + i), "r"(1u) : "memory");
+    }
+    __device__ __forceinline__ u32 flag_ld(u32 i) const {
+        u32 v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(flags + i));
+        return v;
+    }
+    __device__ __forceinline__ void clear_aux(u32 cap, u32 n_flags, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap / 2; s += T) sh_st32(sidx + 4u * s, 0u);
+        for (u32 s = tid; s < (n_flags + 3u) / 4u; s += T) sh_st32(flags + 4u * s, 0u);
+    }
 };
 
 struct TabPacked : TabSharedBase {
-    static constexpr int kKind = 0;
+    static constexpr u32 kSlotBytes = 10;       // key word + solid index
     __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);   // solid indices are written before read
+        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);
     }
-    // count one occurrence (saturating above the threshold); false = table full
-    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+    // count one occurrence (saturating just above the threshold)
+    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u32 a = keys + 8u * s;
             u64 cur = sh_ld64v(a);
             if (cur == GA_NONE64) {
                 cur = sh_cas64(a, GA_NONE64, (key << 4) | 1ull);
-                if (cur == GA_NONE64) return true;
+                if (cur == GA_NONE64) {
+                    slot = s;
+                    return (threshold == 0u ? CS_BECAME_SOLID : CS_NOT_YET) | CS_INSERTED;
+                }
             }
             if ((cur >> 4) == key) {
-                while ((u32)(cur & 15ull) <= threshold) {
+                slot = s;
+                for (;;) {
+                    const u32 c0 = (u32)(cur & 15ull);
+                    if (c0 > threshold) return CS_SOLID_BEFORE;
                     const u64 old = sh_cas64(a, cur, cur + 1ull);
-                    if (old == cur) break;
+                    if (old == cur) return c0 == threshold ? CS_BECAME_SOLID : CS_NOT_YET;
                     cur = old;
                 }
-                return true;
             }
             s = (s + 1u) & cmask;
         }
-        return false;
+        return CS_TABLE_FULL;
     }
-    // phase D for slot s: returns the key when the slot holds a solid window
-    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
-        const u64 cur = sh_ld64(keys + 8u * s);
-        key = cur >> 4;
-        return cur != GA_NONE64 && (u32)(cur & 15ull) > threshold;
-    }
-    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
-    __device__ __forceinline__ u32 occupied(u32 s) const { return sh_ld64(keys + 8u * s) != GA_NONE64; }
-    // phase E: solid index + 1 of a counted window, 0 if not solid
+    // second walk: solid index + 1 of a counted window, 0 if not solid
     __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u64 cur = sh_ld64(keys + 8u * s);
-            if ((cur >> 4) == key) return (u32)(cur & 15ull) > threshold ? sh_ld16(cnt + 2u * s) : 0u;
+            if ((cur >> 4) == key) return (u32)(cur & 15ull) > threshold ? sidx_ld(s) : 0u;
             s = (s + 1u) & cmask;
         }
         return 0u;
@@ -520,38 +542,41 @@ struct TabPacked : TabSharedBase {
 };
 
 struct TabShared : TabSharedBase {
-    static constexpr int kKind = 1;
+    static constexpr u32 kSlotBytes = 12;       // key + 16-bit counter + solid index
     __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
         for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);
         for (u32 s = tid; s < cap / 2; s += T) sh_st32(cnt + 4u * s, 0u);
     }
     __device__ __forceinline__ u32 cnt_get(u32 s) const { return (sh_ld32v(cnt + 4u * (s >> 1)) >> ((s & 1u) * 16u)) & 0xFFFFu; }
-    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             const u32 a = keys + 8u * s;
             u64 cur = sh_ld64v(a);
-            if (cur == GA_NONE64) cur = sh_cas64(a, GA_NONE64, key);
-            if (cur == GA_NONE64 || cur == key) {
-                if (cnt_get(s) <= threshold)
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
-                return true;
+            u32 ins = 0;
+            if (cur == GA_NONE64) {
+                cur = sh_cas64(a, GA_NONE64, key);
+                if (cur == GA_NONE64) {
+                    cur = key;
+                    ins = CS_INSERTED;
+                }
+            }
+            if (cur == key) {
+                slot = s;
+                if (cnt_get(s) > threshold) return CS_SOLID_BEFORE | ins;
+                u32 old;
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
+                old = (old >> ((s & 1u) * 16u)) & 0xFFFFu;
+                return (old == threshold ? CS_BECAME_SOLID : (old > threshold ? CS_SOLID_BEFORE : CS_NOT_YET)) | ins;
             }
             s = (s + 1u) & cmask;
         }
-        return false;
+        return CS_TABLE_FULL;
     }
-    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
-        key = sh_ld64(keys + 8u * s);
-        return cnt_get(s) > threshold;
-    }
-    // counters become solid indices: all of them are rewritten in phase D (0 = not solid)
-    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { sh_st16(cnt + 2u * s, idx1); }
-    __device__ __forceinline__ u32 occupied(u32 s) const { return sh_ld64(keys + 8u * s) != GA_NONE64; }
     __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            if (sh_ld64(keys + 8u * s) == key) return sh_ld16(cnt + 2u * s);
+            if (sh_ld64(keys + 8u * s) == key) return sidx_ld(s);
             s = (s + 1u) & cmask;
         }
         return 0u;
@@ -559,9 +584,9 @@ struct TabShared : TabSharedBase {
 };
 
 struct TabGlobal {
-    static constexpr int kKind = 2;
     u64* keys;
     u32* cnt;                                   // one 32-bit counter per slot
+    u32* sidx;                                  // solid index + 1 per slot
     u64* skeys;
     u64* stamps;
     __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
@@ -570,33 +595,43 @@ struct TabGlobal {
             cnt[s] = 0u;
         }
     }
-    __device__ __forceinline__ bool count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
+    __device__ __forceinline__ void clear_aux(u32 cap, u32, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T) sidx[s] = 0u;
+    }
+    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
             u64 cur = ((volatile u64*)keys)[s];
-            if (cur == GA_NONE64) cur = atomicCAS((unsigned long long*)(keys + s), GA_NONE64, key);
-            if (cur == GA_NONE64 || cur == key) {
-                if (((volatile u32*)cnt)[s] <= threshold) atomicAdd(cnt + s, 1u);
-                return true;
+            u32 ins = 0;
+            if (cur == GA_NONE64) {
+                cur = atomicCAS((unsigned long long*)(keys + s), GA_NONE64, key);
+                if (cur == GA_NONE64) {
+                    cur = key;
+                    ins = CS_INSERTED;
+                }
+            }
+            if (cur == key) {
+                slot = s;
+                if (((volatile u32*)cnt)[s] > threshold) return CS_SOLID_BEFORE | ins;
+                const u32 old = atomicAdd(cnt + s, 1u);
+                return (old == threshold ? CS_BECAME_SOLID : (old > threshold ? CS_SOLID_BEFORE : CS_NOT_YET)) | ins;
             }
             s = (s + 1u) & cmask;
         }
-        return false;
+        return CS_TABLE_FULL;
     }
-    __device__ __forceinline__ bool solid_at(u32 s, u32 threshold, u64& key) const {
-        key = keys[s];
-        return cnt[s] > threshold;
-    }
-    __device__ __forceinline__ void set_solid_index(u32 s, u32 idx1) const { cnt[s] = idx1; }
-    __device__ __forceinline__ u32 occupied(u32 s) const { return keys[s] != GA_NONE64; }
     __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
         u32 s = h >> (32u - lg);
         for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            if (keys[s] == key) return cnt[s];
+            if (keys[s] == key) return ((volatile u32*)sidx)[s];
             s = (s + 1u) & cmask;
         }
         return 0u;
     }
+    __device__ __forceinline__ u32 sidx_ld(u32 s) const { return ((volatile u32*)sidx)[s]; }
+    __device__ __forceinline__ void sidx_st(u32 s, u32 idx1) const { ((volatile u32*)sidx)[s] = idx1; }
+    __device__ __forceinline__ void flag_set(u32) const {}
+    __device__ __forceinline__ u32 flag_ld(u32) const { return 1u; }
     __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
     __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
     __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { stamps[i] = v; }
@@ -626,11 +661,11 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
     return ((u64)hi << 32) | lo;
 }
 
-// One batch = 32 records (one per lane) of the bucket.  f(top64, j, owner fields...) is called once
-// per window with all lanes converged between calls: `top` holds the window's symbols from bit 63
-// down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal and
-// `follows` whether a next symbol exists.  WITH_META = false skips the meta shuffles (count phase).
-template <bool WITH_META, class F>
+// One batch = up to 32 records, one per lane, held by lanes 0..n-1.  f(top, ord, follows, owner) is called once per
+// window with all lanes converged between calls: `top` holds the window's symbols from bit 63 down
+// (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
+// whether a next symbol exists, `owner` the lane whose record it belongs to.
+template <class F>
 __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
     const u32 nwin = have ? meta_windows(meta) : 0u;
@@ -652,16 +687,10 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
         const u32 owner = active ? before + __popc(marks & le_mask) - 1u : 0u;
         const u32 j = x - __shfl_sync(FULL, start, owner);
         const u64 ohi = shfl64(rhi, owner), olo = shfl64(rlo, owner);
-        u64 ord = 0;
-        bool follows = false;
-        if (WITH_META) {
-            const u64 om = shfl64(meta, owner);
-            ord = meta_ordinal(om) + j;
-            follows = j + 1u < meta_windows(om) || meta_has_next(om);
-        }
+        const u64 om = shfl64(meta, owner);
         if (active) {
             const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-            f(top, ord, follows);
+            f(top, meta_ordinal(om) + j, j + 1u < meta_windows(om) || meta_has_next(om), owner);
         }
         __syncwarp();
     }
@@ -671,7 +700,7 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
 template <class Tab>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                int w, u32 threshold, const Tab& tab, u32 cap,
-                                               u32 max_solid, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
+                                               u32 max_solid, bool flag_all, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
                                                u64* __restrict__ edge_stamp_out, u64 out_capacity,
                                                u64* n_solid_global) {
     const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
@@ -688,7 +717,9 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
     };
     // B. clear
+    const u32 n_flags = flag_all ? 0u : (u32)nrec;
     tab.clear(cap, tid, T);
+    tab.clear_aux(cap, n_flags, tid, T);
     if (tid == 0) {
         ctl.n_solid = 0;
         ctl.overflow = 0;
@@ -697,7 +728,16 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     __syncthreads();
     volatile u32* vovf = &ctl.overflow;
     const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
-    // C. count (saturating just above the threshold: only "count > threshold" is asked)
+    // smallest ordinal of "solid window `sol` followed by symbol c"
+    auto stamp = [&](u32 sol, u64 top, u64 ord) {
+        const u32 at = 4u * (sol - 1u) + ((u32)(top >> (kshift - 2u)) & 3u);
+        if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
+    };
+    // C. count (saturating just above the threshold: only "count > threshold" is asked).  A window that
+    //    is solid by the time it is visited takes its edge stamp right away; the occurrence that makes a
+    //    window solid gives it its solid index and stamp slots; records with an occurrence that could
+    //    not be stamped yet are flagged for the second walk.
+    u32 inserted = 0;
     for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
         const u64 idx = bt * 32u + lane;
         const bool have = idx < nrec;
@@ -708,60 +748,67 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             b = bases[i];
             mt = meta[i];
         }
-        sk_for_each_window<false>(b.x, b.y, mt, have, [&](u64 top, u64, bool) {
+        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
-            if (!tab.count(key, h, lg, cmask, threshold)) *vovf = 1u;
+            u32 slot = 0;
+            const u32 st = tab.count(key, h, lg, cmask, threshold, slot);
+            inserted += st >> 2;
+            const u32 state = st & 3u;
+            if (state == CS_TABLE_FULL) {
+                *vovf = 1u;
+                return;
+            }
+            u32 sol = 0;
+            if (state == CS_BECAME_SOLID) {
+                const u32 at = atomicAdd(&ctl.n_solid, 1u);
+                if (at >= max_solid) {
+                    *vovf = 1u;
+                    return;
+                }
+                tab.skey_st(at, key);
+                for (u32 c = 0; c < 4u; ++c) tab.stamp_st(4u * at + c, GA_NONE64);
+                __threadfence_block();
+                tab.sidx_st(slot, at + 1u);
+                sol = at + 1u;
+            } else if (state == CS_SOLID_BEFORE) {
+                sol = tab.sidx_ld(slot);          // 0: its index is still being published
+            }
+            if (!follows) return;
+            if (sol) stamp(sol, top, ord);
+            else if (!flag_all) tab.flag_set((u32)(bt * 32u) + owner);
         });
     }
+    for (int off = 16; off > 0; off >>= 1) inserted += __shfl_down_sync(FULL, inserted, off);
+    if (lane == 0 && inserted) atomicAdd(&ctl.n_distinct, inserted);
     __syncthreads();
     if (ctl.overflow) return false;
-    // D. solid windows get an index; every slot learns its index + 1 (0 = not solid)
-    u32 occupied = 0;
-    for (u32 s = tid; s < cap; s += T) {
-        u64 key;
-        u32 idx1 = 0;
-        if (tab.solid_at(s, threshold, key)) {
-            const u32 base = atomicAdd(&ctl.n_solid, 1u);
-            if (base < max_solid) {
-                tab.skey_st(base, key);
-                idx1 = base + 1u;
-            }
-        }
-        occupied += tab.occupied(s);
-        if (Tab::kKind != 0 || idx1) tab.set_solid_index(s, idx1);
-    }
-    for (int off = 16; off > 0; off >>= 1) occupied += __shfl_down_sync(FULL, occupied, off);
-    if (lane == 0 && occupied) atomicAdd(&ctl.n_distinct, occupied);
-    __syncthreads();
     const u32 n_solid = ctl.n_solid;
-    if (n_solid > max_solid) return false;
     if (n_solid == 0) return true;
-    // E. candidate edge stamps: smallest ordinal of "solid window followed by symbol c"
-    for (u32 s = tid; s < 4 * n_solid; s += T) tab.stamp_st(s, GA_NONE64);
     if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
-    __syncthreads();
+    // E. second walk over the flagged records only
     for (u64 bt = warp; bt < n_batches; bt += W) {
-        const u64 idx = bt * 32u + lane;
-        const bool have = idx < nrec;
+        // the flagged records of the batch move to the low lanes (sk_for_each_window wants the lanes
+        // that hold a record to be a prefix)
+        const u64 mine = bt * 32u + lane;
+        const u32 fmask = __ballot_sync(FULL, mine < nrec && (flag_all || tab.flag_ld((u32)mine)));
+        if (fmask == 0u) continue;
+        const bool have = lane < (u32)__popc(fmask);
         ulonglong2 b = make_ulonglong2(0, 0);
         u64 mt = 0;
         if (have) {
-            const u64 i = locate(idx);
+            const u64 i = locate(bt * 32u + __fns(fmask, 0, lane + 1));
             b = bases[i];
             mt = meta[i];
         }
-        sk_for_each_window<true>(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
+        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32) {
             if (!follows) return;
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
             const u32 sol = tab.solid_of(key, h, lg, cmask, threshold);
-            if (sol) {
-                const u32 at = 4u * (sol - 1u) + ((u32)(top >> (kshift - 2u)) & 3u);
-                if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
-            }
+            if (sol) stamp(sol, top, ord);
         });
     }
     __syncthreads();
@@ -774,7 +821,8 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     return true;
 }
 
-// counters: [0] next bucket, [1] solid windows so far, [2] passes listed for the spill path
+// counters: [0] next bucket, [1] solid windows so far, [2] passes listed for the spill path,
+// [3] passes run | failed passes << 32 (statistics)
 // hist: per bucket, records << 32 | windows
 //
 // A bucket is done in `parts` passes (a power of two), pass `part` taking the windows whose hash
@@ -816,7 +864,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             ctl.n_seg = n_seg;
         }
         const u64 est_d = (nw * ctl.ratio_d >> 12) * 9u / 8u + 64u, est_s = (nw * ctl.ratio_s >> 12) * 9u / 8u + 16u;
-        const u32 solid_room = min(solid_limit, (SB_POOL_BYTES - 10u * cap_limit) / 40u);
+        const u32 solid_room = min(solid_limit, (SB_POOL_BYTES - Tab::kSlotBytes * cap_limit - 2048u) / 40u);
         if (threadIdx.x == 0) {
             // passes: expected distinct windows of a pass within 85 % of the largest table, solid ones within
             // 85 % of what the pool holds next to it (a pass that overflows anyway is split below)
@@ -839,17 +887,24 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             const u64 want = ((nw * rd >> 12) / parts + 64u) * 5u / 2u;
             u32 cap = 256;
             while (cap < cap_limit && (u64)cap < want) cap <<= 1;
+            // pool: table (keys [+ counters] + solid indices), record flags, then solid keys + 4 stamps each
+            const u64 nrec = ctl.seg_pre[n_seg];
+            const bool flag_all = nrec > SB_MAX_FLAGS;
+            const u32 flag_bytes = flag_all ? 0u : ((u32)nrec + 7u) & ~7u;
             Tab tab;
             tab.keys = pool;
             tab.cnt = pool + 8u * cap;
-            tab.skeys = pool + 10u * cap;
-            u32 max_solid = (SB_POOL_BYTES - 10u * cap) / 40u;
+            tab.sidx = pool + (Tab::kSlotBytes - 2u) * cap;
+            tab.flags = pool + Tab::kSlotBytes * cap;
+            tab.skeys = tab.flags + flag_bytes;
+            u32 max_solid = (SB_POOL_BYTES - Tab::kSlotBytes * cap - flag_bytes) / 40u;
             if (max_solid > solid_limit) max_solid = solid_limit;
             tab.stamps = tab.skeys + 8u * max_solid;
-            const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, max_solid, parts, part, ctl,
+            const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, max_solid, flag_all, parts, part, ctl,
                                            solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
+                atomicAdd((unsigned long long*)&counters[3], ok ? 1ull : (1ull << 32) + 1ull);   // passes, failed passes << 32
                 if (ok) {
                     // running means (weight 1/4) of what the passes actually held
                     const u32 d = (u32)min((u64)ctl.n_distinct * parts * 4096u / (nw + 1u), 4096ull);
@@ -888,6 +943,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
     tab.skeys = tab.keys + cap;
     tab.stamps = tab.skeys + cap;
     tab.cnt = reinterpret_cast<u32*>(tab.stamps + 4 * (size_t)cap);
+    tab.sidx = tab.cnt + cap;
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
         const u64 entry = spill_list[oi];
@@ -905,7 +961,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
             ctl.n_seg = n_seg;
         }
         __syncthreads();
-        const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, cap, parts, part, ctl,
+        const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, cap, true, parts, part, ctl,
                                        solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
@@ -1069,8 +1125,8 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
 }
 
 extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
-    // keys + solid keys (8 B each) + 4 stamps (32 B) + one 32-bit counter per slot
-    return (uint64_t)table_slots * (8 + 8 + 32 + 4);
+    // keys + solid keys (8 B each) + 4 stamps (32 B) + a 32-bit counter and a 32-bit solid index per slot
+    return (uint64_t)table_slots * (8 + 8 + 32 + 4 + 4);
 }
 
 extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,

@@ -626,7 +626,10 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
                                          n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
                                          gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
                                          gn.ptr(spill_list), spill_cap, gn.ptr(status), _stream()))
-        _, n_solid, n_spill, _ = (int(v) for v in counters.cpu().tolist())
+        _, n_solid, n_spill, n_pass = (int(v) for v in counters.cpu().tolist())
+        if _TRACE:
+            print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled" %
+                  (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill), flush=True)
         if n_spill > spill_cap:
             spill_cap = n_spill
             continue
