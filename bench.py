@@ -201,6 +201,8 @@ def run_gpu_arm(args):
     genome_size, n_reads, read_len, paired, k, F, desc = WORKLOADS[args.workload]
     if args.reads:
         n_reads = args.reads
+    if args.genome:
+        genome_size = args.genome
     L = gn.lib()
     mates = 2 if paired else 1
     stride = (read_len + 31) // 32
@@ -246,6 +248,9 @@ def run_gpu_arm(args):
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     launches = L.ga_launch_count() - launches0
+    mem_after_steps = {"torch_reserved": round(torch.cuda.memory_reserved() / 1e9, 1),
+                       "device_free": round(torch.cuda.mem_get_info()[0] / 1e9, 1),
+                       "alloc_retries": torch.cuda.memory_stats().get("num_alloc_retries", 0)}
     clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -351,6 +356,10 @@ def run_gpu_arm(args):
                            "l2": "working set (count table %d MB) exceeds the 126 MB L2; tables rebuilt every step"
                                  % (int(occ_total * 1.25 * 16) >> 20)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+                "memory_gb": {"torch_reserved": round(torch.cuda.memory_reserved() / 1e9, 1),
+                              "torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                              "device_free": round(torch.cuda.mem_get_info()[0] / 1e9, 1),
+                              "after_timed_steps": mem_after_steps},
                 "clocks": clocks,
                 "graph": {"nodes": result.n_nodes, "edges": result.n_edges} if result is not None else None}
         print(json.dumps(line))
@@ -366,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GA_BENCH_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads / pairs")
+    ap.add_argument("--genome", type=int, default=0, help="override the genome size (profiling: scale reads and "
+                                                         "genome together to keep the workload's coverage)")
     ap.add_argument("--sample-reads", type=int, default=100000, help="reads in the CPU-baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -661,36 +661,48 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
     return ((u64)hi << 32) | lo;
 }
 
-// One batch = up to 32 records, one per lane, held by lanes 0..n-1.  f(top, ord, follows, owner) is called once per
-// window with all lanes converged between calls: `top` holds the window's symbols from bit 63 down
-// (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
+// One batch = up to 32 records, one per lane, held by lanes 0..n-1.  The records are cut into pieces of
+// at most SB_PIECE consecutive windows; the pieces of the batch are dealt to the lanes 32 at a time (warp
+// prefix sum + ballot/REDUX find the owner record of each piece), and a lane rolls through the windows
+// of its piece.  Finding the owner costs about as much as handling one window, so it is shared by a few
+// windows; longer pieces would leave lanes idle (records hold 6-7 windows on average).
+// f(top, ord, follows, owner) is called once per window: `top` holds the window's symbols from bit 63
+// down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
 // whether a next symbol exists, `owner` the lane whose record it belongs to.
+constexpr u32 SB_PIECE = 1;
+
 template <class F>
 __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
-    const u32 nwin = have ? meta_windows(meta) : 0u;
-    u32 incl = nwin;
+    const u32 npiece = have ? (meta_windows(meta) + SB_PIECE - 1u) / SB_PIECE : 0u;
+    u32 incl = npiece;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const u32 t = __shfl_up_sync(FULL, incl, off);
         if (lane >= (u32)off) incl += t;
     }
-    const u32 start = incl - nwin;
+    const u32 start = incl - npiece;
     const u32 total = __shfl_sync(FULL, incl, 31);
     const u32 le_mask = 0xFFFFFFFFu >> (31u - lane);
     for (u32 xb = 0; xb < total; xb += 32u) {
         const u32 before = __popc(__ballot_sync(FULL, start < xb));
-        const u32 bit = (nwin && start >= xb && start < xb + 32u) ? 1u << (start - xb) : 0u;
+        const u32 bit = (npiece && start >= xb && start < xb + 32u) ? 1u << (start - xb) : 0u;
         const u32 marks = __reduce_or_sync(FULL, bit);
         const u32 x = xb + lane;
         const bool active = x < total;
         const u32 owner = active ? before + __popc(marks & le_mask) - 1u : 0u;
-        const u32 j = x - __shfl_sync(FULL, start, owner);
+        const u32 j0 = (x - __shfl_sync(FULL, start, owner)) * SB_PIECE;
         const u64 ohi = shfl64(rhi, owner), olo = shfl64(rlo, owner);
         const u64 om = shfl64(meta, owner);
         if (active) {
-            const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-            f(top, meta_ordinal(om) + j, j + 1u < meta_windows(om) || meta_has_next(om), owner);
+            const u32 nwin = meta_windows(om);
+            const u32 j1 = min(j0 + SB_PIECE, nwin);
+            const u64 ord0 = meta_ordinal(om);
+            const bool has_next = meta_has_next(om);
+            for (u32 j = j0; j < j1; ++j) {
+                const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
+                f(top, ord0 + j, j + 1u < nwin || has_next, owner);
+            }
         }
         __syncwarp();
     }

@@ -67,15 +67,18 @@ def exchange_by_owner(owner: torch.Tensor, payloads, group=None):
     return received
 
 
-def exchange_ranges(src: torch.Tensor, send_rows, group=None, ws_name=None):
+def exchange_ranges(src: torch.Tensor, send_rows, group=None, ws_name=None, recv_rows=None):
     """All-to-all of contiguous row ranges: the first send_rows[0] rows of `src` go to rank 0, the next
     send_rows[1] to rank 1, ...  Returns (received rows, rows received from each rank).  ws_name: take the
-    receive buffer from ga_device's persistent workspace instead of the allocator."""
+    receive buffer from ga_device's persistent workspace instead of the allocator.  recv_rows: the rows
+    every rank will send here when the caller already knows them (skips the count exchange and its
+    host synchronisation)."""
     world = dist.get_world_size(group)
-    send = torch.tensor(list(send_rows), dtype=torch.int64, device=src.device)
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
-    recv_rows = [int(x) for x in recv.tolist()]
+    if recv_rows is None:
+        send = torch.tensor(list(send_rows), dtype=torch.int64, device=src.device)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        recv_rows = [int(x) for x in recv.tolist()]
     shape = (sum(recv_rows),) + tuple(src.shape[1:])
     if ws_name is not None:
         import ga_device as gd
@@ -88,12 +91,13 @@ def exchange_ranges(src: torch.Tensor, send_rows, group=None, ws_name=None):
     return dst, recv_rows
 
 
-def gather_rows(local: torch.Tensor, dst: int = 0, group=None):
-    """Rows of every rank concatenated on rank `dst` (rank order); other ranks get an empty tensor."""
+def gather_rows(local: torch.Tensor, dst: int = 0, group=None, recv_rows=None, want_rows: bool = False):
+    """Rows of every rank concatenated on rank `dst` (rank order); other ranks get an empty tensor.
+    recv_rows / want_rows: reuse the per-rank row counts of a previous gather of equally long tensors."""
     world = dist.get_world_size(group)
     send_rows = [local.shape[0] if g == dst else 0 for g in range(world)]
-    out, _ = exchange_ranges(local, send_rows, group)
-    return out
+    out, rows = exchange_ranges(local, send_rows, group, recv_rows=recv_rows)
+    return (out, rows) if want_rows else out
 
 
 _SIGN = -(1 << 63)
@@ -149,11 +153,12 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     gd._mark("multi: cut")
     with gd._timed("exchange"):
         got_bases, recv_rows = exchange_ranges(bases.view(-1, 2)[:total], send_rows, ws_name="sk_recv_bases")
-        got_meta, _ = exchange_ranges(meta[:total], send_rows, ws_name="sk_recv_meta")
-        got_hist, _ = exchange_ranges(hist, [bounds[g + 1] - bounds[g] for g in range(world)])
+        got_meta, _ = exchange_ranges(meta[:total], send_rows, ws_name="sk_recv_meta", recv_rows=recv_rows)
+        mine = bounds[rank + 1] - bounds[rank]
+        got_hist, _ = exchange_ranges(hist, [bounds[g + 1] - bounds[g] for g in range(world)],
+                                      recv_rows=[mine] * world)
     del bases, meta
     gd._mark("multi: exchange")
-    mine = bounds[rank + 1] - bounds[rank]
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
     if mine:
         # 3. one segment per source rank: positions from the per-source record counts
@@ -176,8 +181,8 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     # 4. everything solid meets on rank 0
     gd._mark("multi: bucket pass")
     with gd._timed("gather"):
-        all_keys = gather_rows(solid_keys[:n_solid])
-        all_stamps = gather_rows(edge_stamp[:4 * n_solid].view(-1, 4))
+        all_keys, rows = gather_rows(solid_keys[:n_solid], want_rows=True)
+        all_stamps = gather_rows(edge_stamp[:4 * n_solid].view(-1, 4), recv_rows=rows)
     gd._mark("multi: gather")
     if rank != 0:
         return None

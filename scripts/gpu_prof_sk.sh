@@ -1,9 +1,11 @@
 #!/bin/bash
-# ncu evidence for the bucketed path on a reduced C4 (same per-bucket shape, 10M reads): launch list + full capture.
+# ncu evidence for the bucketed path on a reduced C4 (reads and genome scaled together: same coverage,
+# same per-bucket shape): launch list + full capture.
 set -u
 mkdir -p gpurun_out
 R=${1:-10000000}
-CMD="python bench.py --workload c4 --reads $R --steps 1 --warmup 1 --sample-reads 2000"
+G=$((R / 2))
+CMD="python bench.py --workload c4 --reads $R --genome $G --steps 1 --warmup 1 --sample-reads 2000"
 $CMD > gpurun_out/plain_sk.json 2> gpurun_out/plain_sk.err
 echo "plain exit $?"; cat gpurun_out/plain_sk.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
