@@ -51,6 +51,17 @@ B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
             "sk_bucket": 38.0}     # count probe + RMW 16, build probe + count read 12, stamp RMW 10
 
 
+def measured_traffic(workload, kernel, launch_occ):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per occurrence), scaled to the
+    occurrences one launch of this run covers; None when the kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    per_occ = json.load(open(path)).get(workload, {}).get(kernel)
+    return None if per_occ is None else per_occ * launch_occ
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -243,6 +254,7 @@ def run_gpu_arm(args):
     start.record()
     result = None
     for _ in range(args.steps):
+        result = None      # one graph alive at a time: the CSR buffers of the previous step are reused
         result = step_fn(timers)
     stop.record()
     barrier()
@@ -261,6 +273,9 @@ def run_gpu_arm(args):
 
     # dominant-kernel roofline from the per-launch CUDA events recorded inside the timed steps
     # per kernel: total ms per step, launches per step, occurrences per launch (rank 0's shard)
+    host_notes = timers.pop("_host", [])
+    if rank == 0 and host_notes:
+        print("host: " + " | ".join(host_notes), file=sys.stderr)
     marks = timers.pop("_marks", [])
     stage_ms = {}
     for (_, ev0), (name, ev1) in zip(marks, marks[1:]):
@@ -275,7 +290,10 @@ def run_gpu_arm(args):
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": measured_traffic(args.workload, dominant, launch_occ),
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per occurrence (profiles/traffic.json) "
+                                  "x occurrences of this launch",
+                "peak_source": peak_src,
                 "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": stage_ms, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_occurrence": B_KERNEL.get(dominant, B_TOTAL),
                 "whole_path": {"achieved": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9,
@@ -353,8 +371,9 @@ def run_gpu_arm(args):
                 "data": "synthetic",
                 "config": {"workload": desc, "k": k, "filter": F, "paired": paired, "reads": n_reads,
                            "occurrences": occ_total, "sharding": "reads by index, k-mers by hash" if world > 1 else "none",
-                           "l2": "working set (count table %d MB) exceeds the 126 MB L2; tables rebuilt every step"
-                                 % (int(occ_total * 1.25 * 16) >> 20)},
+                           "l2": "inputs larger than L2: %d MB of packed reads (and the record stream cut from them) per "
+                                 "step against a 126 MB L2; every table is rebuilt each step"
+                                 % (int(n_reads * mates * stride * 8) >> 20)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "memory_gb": {"torch_reserved": round(torch.cuda.memory_reserved() / 1e9, 1),
                               "torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),

@@ -13,6 +13,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import os as _os_early
+
 import numpy as np
 import torch
 
@@ -25,7 +27,7 @@ TWO_PHASE_MIN_READS = 1 << 22
 TWO_PHASE_MIN_STEP = 1 << 20
 # bucketed (super-k-mer) count + build, csrc/ga_superkmer.cu: unpaired DNA, 64-bit keys
 SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
-SUPERKMER_TARGET = 16384                # windows per bucket aimed for
+SUPERKMER_TARGET = int(_os_early.environ.get("GA_SK_TARGET", "16384"))   # windows per bucket aimed for
 SUPERKMER_TABLE_SLOTS = 8192            # shared-memory table slots per bucket (tests shrink it to force spills)
 SUPERKMER_MAX_SOLID = 16000             # solid windows per bucket (further bounded by the shared-memory pool)
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
@@ -867,6 +869,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
                                       C.byref(attr)))
     try:
         nn, ne = n_nodes.value, n_edges.value
+        _t0 = _time.perf_counter()
         rowptr = torch.empty(nn + 1, dtype=torch.int32, device=dev)
         col = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
         indeg = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
@@ -874,10 +877,16 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         last_sym = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
         keys_a = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
         keys_b = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev) if reads.paired else None
+        _t1 = _time.perf_counter()
         with _timed("csr_emit"):
             gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
                                    gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
+        _t2 = _time.perf_counter()
         torch.cuda.current_stream().synchronize()
+        _t3 = _time.perf_counter()
+        if TIMERS is not None:
+            TIMERS.setdefault("_host", []).append(("emit: alloc %.1f call %.1f sync %.1f ms" %
+                                                   ((_t1 - _t0) * 1e3, (_t2 - _t1) * 1e3, (_t3 - _t2) * 1e3)))
         _mark("csr emit")
     finally:
         L.ga_csr_plan_free(plan)

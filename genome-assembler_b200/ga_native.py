@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libga_b200.so")
+LIB_PATH = os.environ.get("GA_LIB") or os.path.join(HERE, "libga_b200.so")   # GA_LIB: A/B builds of the library
 
 GA_OK = 0
 GA_ERR_BAD_ARG, GA_ERR_CAPACITY, GA_ERR_CUDA, GA_ERR_NCCL, GA_ERR_OVERFLOW_U16, GA_ERR_ALPHABET = \
