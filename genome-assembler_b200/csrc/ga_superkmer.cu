@@ -359,10 +359,15 @@ constexpr int S2_THREADS = 256;
 constexpr int S2_PER = 8;
 constexpr u32 S2_CHUNK = S2_THREADS * S2_PER;
 
+// INDEX = false: records move to their final bucket.  INDEX = true: only a 32-bit index (position inside the
+// level-1 bucket) is written per record; the bucket kernel then gathers the records from the level-1 bucket,
+// which is L2-sized (1024 final buckets share it and are processed back to back).  Same result, a quarter of
+// the traffic; the dense form is what the multi-GPU exchange needs.
+template <bool INDEX>
 __global__ void __launch_bounds__(S2_THREADS)
 sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __restrict__ in_meta, u64 cap1,
                           const u64* __restrict__ cursors1, u32 n_l1, int l2_bits, u64* __restrict__ cursors2,
-                          ulonglong2* __restrict__ out_bases, u64* __restrict__ out_meta) {
+                          ulonglong2* __restrict__ out_bases, u64* __restrict__ out_meta, u32* __restrict__ out_index) {
     __shared__ u32 hist[1024];
     __shared__ u64 gbase[1024];
     const u32 n_l2 = 1u << l2_bits;
@@ -383,7 +388,7 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
             const u64 i = lo + (u64)u * S2_THREADS + threadIdx.x;
             if (i < cnt1) {
                 const u64 src = (u64)b1 * cap1 + i;
-                bs[u] = in_bases[src];
+                if (!INDEX) bs[u] = in_bases[src];
                 mt[u] = in_meta[src];
                 rank[u] = atomicAdd(&hist[meta_b2(mt[u])], 1u);
             }
@@ -399,8 +404,12 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
             const u64 i = lo + (u64)u * S2_THREADS + threadIdx.x;
             if (i < cnt1) {
                 const u64 dst = gbase[meta_b2(mt[u])] + rank[u];
-                out_bases[dst] = bs[u];
-                out_meta[dst] = mt[u];
+                if (INDEX) {
+                    out_index[dst] = (u32)i;
+                } else {
+                    out_bases[dst] = bs[u];
+                    out_meta[dst] = mt[u];
+                }
             }
         }
         __syncthreads();
@@ -656,6 +665,14 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u64 seg_pre[SB_MAX_SEG + 1];
 };
 
+// where a bucket's records are: index == nullptr: at the positions the offsets give (dense form);
+// otherwise offsets address `index`, and record = base + index[position] (base = first record of the
+// bucket's level-1 bucket)
+struct SkGather {
+    const u32* index;
+    u64 base;
+};
+
 __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
     const u32 lo = __shfl_sync(FULL, (u32)v, src), hi = __shfl_sync(FULL, (u32)(v >> 32), src);
     return ((u64)hi << 32) | lo;
@@ -711,7 +728,7 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
 // returns false when the bucket does not fit: the caller lists it for the spill path
 template <class Tab>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
-                                               int w, u32 threshold, const Tab& tab, u32 cap,
+                                               SkGather gather, int w, u32 threshold, const Tab& tab, u32 cap,
                                                u32 max_solid, bool flag_all, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
                                                u64* __restrict__ edge_stamp_out, u64 out_capacity,
                                                u64* n_solid_global) {
@@ -723,10 +740,16 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u64 nrec = ctl.seg_pre[n_seg];
     const u64 n_batches = (nrec + 31u) / 32u;
     // position of the bucket's idx-th record (segments are few: linear scan)
-    auto locate = [&](u64 idx) -> u64 {
+    // `where(idx)`: position of the bucket's idx-th entry (segments are few: linear scan); in the index form
+    // that entry is a 32-bit index and the record sits at gather.base + index
+    auto where = [&](u64 idx) -> u64 {
         u32 sg = 0;
         while (sg + 1u < n_seg && idx >= ctl.seg_pre[sg + 1]) ++sg;
         return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
+    };
+    auto locate = [&](u64 idx) -> u64 {
+        const u64 at = where(idx);
+        return gather.index ? gather.base + __ldg(gather.index + at) : at;
     };
     // B. clear
     const u32 n_flags = flag_all ? 0u : (u32)nrec;
@@ -750,30 +773,28 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     //    window solid gives it its solid index and stamp slots; records with an occurrence that could
     //    not be stamped yet are flagged for the second walk.
     u32 inserted = 0;
-    // the next batch's records are requested before the current batch is walked (their DRAM latency
-    // then overlaps the walk)
-    auto fetch = [&](u64 bt, ulonglong2& b, u64& mt) -> bool {
+    // In the index form the record is two dependent loads away (index entry, then the gather): the next
+    // batch's index entry is requested one batch ahead (one register; prefetching whole records measured
+    // slower, A/B on one B200).
+    auto entry = [&](u64 bt) -> u32 {
         const u64 idx = bt * 32u + lane;
+        return (gather.index && bt < n_batches && idx < nrec) ? __ldg(gather.index + where(idx)) : 0u;
+    };
+    ulonglong2 b = make_ulonglong2(0, 0);
+    u64 mt = 0;
+    u32 ent = entry(warp);
+    for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
+        const u64 idx = bt * 32u + lane;
+        const bool have = idx < nrec;
+        const u32 ent_next = entry(bt + W);
         b = make_ulonglong2(0, 0);
         mt = 0;
-        if (bt >= n_batches || idx >= nrec) return false;
-        const u64 i = locate(idx);
-        b = bases[i];
-        mt = meta[i];
-        return true;
-    };
-    ulonglong2 b, b_next;
-    u64 mt, mt_next;
-#ifndef GA_SK_PREFETCH      // requesting the next batch early measured 4.5 % slower on C4 (A/B on one B200)
-    bool have = false, have_next = false;
-    for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
-        have = fetch(bt, b, mt);
-        (void)have_next; (void)b_next; (void)mt_next;
-#else
-    bool have = fetch(warp, b, mt), have_next = false;
-    for (u64 bt = warp; bt < n_batches && !*vovf; bt += W, b = b_next, mt = mt_next, have = have_next) {
-        have_next = fetch(bt + W, b_next, mt_next);
-#endif
+        if (have) {
+            const u64 i = gather.index ? gather.base + ent : where(idx);
+            b = bases[i];
+            mt = meta[i];
+        }
+        ent = ent_next;
         sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
@@ -862,7 +883,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                  u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
                  u32 solid_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
-                 u64* __restrict__ spill_list, u64 spill_capacity, u32* status) {
+                 u64* __restrict__ spill_list, u64 spill_capacity, u32* status, const u32* __restrict__ index,
+                 u64 l1_capacity, int l2_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BucketCtl ctl;
     // keep the pool's shared address in a register: left to itself the compiler re-derives it from the
@@ -932,7 +954,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             u32 max_solid = (SB_POOL_BYTES - Tab::kSlotBytes * cap - flag_bytes) / 40u;
             if (max_solid > solid_limit) max_solid = solid_limit;
             tab.stamps = tab.skeys + 8u * max_solid;
-            const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, max_solid, flag_all, parts, part, ctl,
+            const SkGather gather{index, (b >> l2_bits) * l1_capacity};
+            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, max_solid, flag_all, parts, part, ctl,
                                            solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
@@ -967,7 +990,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
                        const u64* __restrict__ spill_list, u64 n_spill, int w,
                        u32 threshold, u32 cap, unsigned char* __restrict__ scratch, u64 scratch_per_cta,
                        u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
-                       u64* counters, u32* status) {
+                       u64* counters, u32* status, const u32* __restrict__ index, u64 l1_capacity, int l2_bits) {
     __shared__ BucketCtl ctl;
     TabGlobal tab;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
@@ -993,7 +1016,8 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
             ctl.n_seg = n_seg;
         }
         __syncthreads();
-        const bool ok = sk_bucket_body(bases, meta, w, threshold, tab, cap, cap, true, parts, part, ctl,
+        const SkGather gather{index, (b >> l2_bits) * l1_capacity};
+        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, cap, true, parts, part, ctl,
                                        solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
@@ -1101,18 +1125,26 @@ extern "C" int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint6
 
 extern "C" int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
                                      const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
-                                     void* out_bases_dev, uint64_t* out_meta_dev, ga_stream stream) {
-    if (!rec_bases_dev || !rec_meta_dev || !l1_cursors_dev || !cursors_dev || !out_bases_dev || !out_meta_dev ||
-        l1_capacity == 0 || l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10) {
+                                     void* out_bases_dev, uint64_t* out_meta_dev, uint32_t* out_index_dev,
+                                     ga_stream stream) {
+    const bool dense = out_bases_dev && out_meta_dev && !out_index_dev;
+    const bool index = out_index_dev && !out_bases_dev && !out_meta_dev;
+    if (!rec_bases_dev || !rec_meta_dev || !l1_cursors_dev || !cursors_dev || (!dense && !index) ||
+        l1_capacity == 0 || l1_capacity > 0xFFFFFFFFull || l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10) {
         ga_set_error("ga_sk_scatter_buckets: bad arguments");
         return GA_ERR_BAD_ARG;
     }
     const u32 n_l1 = 1u << l1_bits;
     const u64 total = (u64)n_l1 * ((l1_capacity + S2_CHUNK - 1) / S2_CHUNK);
     const unsigned grid = (unsigned)(total < 148ull * 8 ? total : 148ull * 8);
-    sk_scatter_buckets_kernel<<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
-        (const ulonglong2*)rec_bases_dev, (const u64*)rec_meta_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1,
-        l2_bits, (u64*)cursors_dev, (ulonglong2*)out_bases_dev, (u64*)out_meta_dev);
+    if (index)
+        sk_scatter_buckets_kernel<true><<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
+            (const ulonglong2*)rec_bases_dev, (const u64*)rec_meta_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1,
+            l2_bits, (u64*)cursors_dev, nullptr, nullptr, out_index_dev);
+    else
+        sk_scatter_buckets_kernel<false><<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
+            (const ulonglong2*)rec_bases_dev, (const u64*)rec_meta_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1,
+            l2_bits, (u64*)cursors_dev, (ulonglong2*)out_bases_dev, (u64*)out_meta_dev, nullptr);
     GA_LAUNCH_CHECK("sk_scatter_buckets");
     return GA_OK;
 }
@@ -1123,7 +1155,7 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
                                  uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
                                  uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
                                  uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
-                                 ga_stream stream) {
+                                 const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream) {
     const int w = k - 1;
     if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev || !edge_stamp_out_dev ||
         !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
@@ -1148,7 +1180,7 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,                   \
         (const u64*)hist_dev, n_buckets, w,                                                                        \
         (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity, \
-        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev)
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits)
     if (packed) GA_SK_BUCKET(TabPacked);
     else GA_SK_BUCKET(TabShared);
 #undef GA_SK_BUCKET
@@ -1166,6 +1198,7 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
                                        uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
                                        uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                                        uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
+                                       const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits,
                                        ga_stream stream) {
     const int w = k - 1;
     if (!bases_dev || !meta_dev || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
@@ -1181,7 +1214,7 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
         (const u64*)spill_list_dev, n_spill, w,
         (u32)(threshold > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : threshold), table_slots, (unsigned char*)scratch_dev,
         ga_sk_spill_scratch_bytes(table_slots), (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, status_dev);
+        (u64*)counters_dev, status_dev, index_dev, l1_capacity, l2_bits);
     GA_LAUNCH_CHECK("sk_bucket_spill");
     return GA_OK;
 }

@@ -29,6 +29,7 @@ TWO_PHASE_MIN_STEP = 1 << 20
 SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
 SUPERKMER_TARGET = int(_os_early.environ.get("GA_SK_TARGET", "16384"))   # windows per bucket aimed for
 SUPERKMER_TABLE_SLOTS = 8192            # shared-memory table slots per bucket (tests shrink it to force spills)
+SUPERKMER_INDEX_FORM = _os_early.environ.get("GA_SK_DENSE", "0") != "1"   # single GPU: sort 32-bit indices, not records
 SUPERKMER_MAX_SOLID = 16000             # solid windows per bucket (further bounded by the shared-memory pool)
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
@@ -560,9 +561,12 @@ def sk_geometry(n_occ: int):
     return bits - l2_bits, l2_bits
 
 
-def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None):
-    """This rank's reads -> records sorted by bucket: (bases int64[2*total], meta int64[total],
-    offsets int64[n_buckets+1], hist int64[n_buckets] = records << 32 | windows, total).
+def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None, dense: bool = True):
+    """This rank's reads -> records sorted by bucket.  dense: (bases int64[2*total], meta int64[total],
+    offsets int64[n_buckets+1], hist int64[n_buckets] = records << 32 | windows, total) -- the records
+    themselves in bucket order, what the multi-GPU exchange sends.  Not dense: (level-1 bases, level-1 meta,
+    offsets, hist, total, index int32[total], l1_capacity) -- the records stay in their level-1 buckets and
+    only a 32-bit index per record is sorted (a quarter of the traffic).
     ga_sk_scatter_reads + ga_sk_offsets + ga_sk_scatter_buckets."""
     L = gn.lib()
     dev = _dev()
@@ -597,17 +601,24 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
             break
         cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
     _mark("sk scatter reads")
+    if not dense:
+        index = workspace("sk_index", max(total, 1), torch.int32)
+        with _timed("sk_scatter2", n_occ):
+            gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits,
+                                             l2_bits, gn.ptr(cursors2), None, None, gn.ptr(index), _stream()))
+        _mark("sk scatter buckets")
+        return rec_bases, rec_meta, offsets, hist, total, index, cap1
     bases = workspace("sk_bases", max(total, 1) * 2, torch.int64)
     meta = workspace("sk_meta", max(total, 1), torch.int64)
     with _timed("sk_scatter2", n_occ):
         gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits, l2_bits,
-                                         gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), _stream()))
+                                         gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), None, _stream()))
     _mark("sk scatter buckets")
     return bases, meta, offsets, hist, total
 
 
 def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, k: int, threshold: int,
-                   n_occ: int, status):
+                   n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0):
     """Bucket-sorted records -> (solid keys (cap, 1) int64, n_solid, candidate edge stamps int64[4*cap]).
     offsets: n_segments rows of n_buckets+1 record positions (one row on a single GPU, one per source
     rank after the multi-GPU exchange); hist[b] & 0xFFFFFFFF = windows of bucket b over all segments.
@@ -627,7 +638,8 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
             gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
                                          n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
                                          gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
-                                         gn.ptr(spill_list), spill_cap, gn.ptr(status), _stream()))
+                                         gn.ptr(spill_list), spill_cap, gn.ptr(status), gn.ptr(index), l1_capacity,
+                                         l2_bits, _stream()))
         _, n_solid, n_spill, n_pass = (int(v) for v in counters.cpu().tolist())
         if _TRACE:
             print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled" %
@@ -648,7 +660,8 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
                 gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, n_buckets,
                                                    gn.ptr(spill_list), n_spill, k, int(threshold), slots,
                                                    gn.ptr(scratch), n_ctas, gn.ptr(solid_keys), gn.ptr(edge_stamp),
-                                                   out_cap, gn.ptr(counters), gn.ptr(status), _stream()))
+                                                   out_cap, gn.ptr(counters), gn.ptr(status), gn.ptr(index),
+                                                   l1_capacity, l2_bits, _stream()))
             n_solid = int(counters[1].item())
             del scratch
         if _check_status(status) & gn.ST_TABLE_FULL:
@@ -670,8 +683,11 @@ def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
     host-buffer entry streams chunks in while earlier chunks are already being scattered."""
     n_occ = reads.windows_total(k)
     l1_bits, l2_bits = sk_geometry(n_occ)
-    bases, meta, offsets, hist, _ = sk_scatter_local(reads, k, l1_bits, l2_bits, feed)
-    return sk_bucket_pass(bases, meta, offsets, 1, hist, 1 << (l1_bits + l2_bits), k, threshold, n_occ, reads.status)
+    out = sk_scatter_local(reads, k, l1_bits, l2_bits, feed, dense=not SUPERKMER_INDEX_FORM)
+    bases, meta, offsets, hist = out[:4]
+    index, cap1 = (out[5], out[6]) if SUPERKMER_INDEX_FORM else (None, 0)
+    return sk_bucket_pass(bases, meta, offsets, 1, hist, 1 << (l1_bits + l2_bits), k, threshold, n_occ, reads.status,
+                          index, cap1, l2_bits)
 
 
 def resolve_and_emit(graph, solid_keys, n_solid: int, edge_stamp, k: int, alphabet, status, to_host: bool):

@@ -74,10 +74,12 @@ SIGNATURES = {
     "ga_sk_minimizer_len": (_i32, [_i32]),
     "ga_sk_scatter_reads": (_i32, [_PR, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "ga_sk_offsets": (_i32, [_vp, _u64, _vp, _vp, _vp]),
-    "ga_sk_scatter_buckets": (_i32, [_vp, _vp, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "ga_sk_count_build": (_i32, [_vp, _vp, _vp, _u32, _vp, _u64, _i32, _i64, _u32, _u32, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
+    "ga_sk_scatter_buckets": (_i32, [_vp, _vp, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ga_sk_count_build": (_i32, [_vp, _vp, _vp, _u32, _vp, _u64, _i32, _i64, _u32, _u32, _vp, _vp, _u64, _vp, _vp, _u64, _vp,
+                                 _vp, _u64, _i32, _vp]),
     "ga_sk_spill_scratch_bytes": (_u64, [_u32]),
-    "ga_sk_count_build_spill": (_i32, [_vp, _vp, _vp, _u32, _u64, _vp, _u64, _i32, _i64, _u32, _vp, _u32, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "ga_sk_count_build_spill": (_i32, [_vp, _vp, _vp, _u32, _u64, _vp, _u64, _i32, _i64, _u32, _vp, _u32, _vp, _vp, _u64, _vp, _vp,
+                                       _vp, _u64, _i32, _vp]),
     "ga_sk_resolve": (_i32, [_vp, _u64, _i32, _vp, _u64, _vp, _vp, _vp]),
     "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
     "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),

@@ -190,14 +190,22 @@ int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, 
 /* offsets_dev[n_buckets+1] = exclusive prefix sum of the record counts; cursors_dev[n_buckets] = a copy */
 int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
                   uint64_t* cursors_dev, ga_stream stream);
-/* level-1 buckets -> final buckets, densely packed at offsets_dev (cursors_dev is consumed) */
+/* level-1 buckets -> final buckets at offsets_dev (cursors_dev is consumed), in one of two forms:
+ *  dense (out_bases_dev + out_meta_dev, out_index_dev NULL): the records themselves, densely packed --
+ *    what the multi-GPU exchange sends;
+ *  index (out_index_dev, the other two NULL): per record only its 32-bit position inside its level-1
+ *    bucket; ga_sk_count_build then gathers the records from the level-1 buckets (a quarter of the
+ *    traffic on one GPU, where a level-1 bucket stays L2 resident while its final buckets are done). */
 int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
                           const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
-                          void* out_bases_dev, uint64_t* out_meta_dev, ga_stream stream);
+                          void* out_bases_dev, uint64_t* out_meta_dev, uint32_t* out_index_dev,
+                          ga_stream stream);
 /* offsets_dev holds n_segments rows of n_buckets+1 positions: the records of bucket b are the union of
  * [offsets[s][b], offsets[s][b+1]) over the segments s (one segment on a single GPU; after the
  * multi-GPU exchange, one per source rank, each sorted by bucket).  hist_dev[b] & 0xFFFFFFFF = windows
- * of bucket b over all segments.
+ * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev /
+ * meta_dev are then the level-1 bucket arrays of ga_sk_scatter_reads, offsets address index_dev, and the
+ * record of entry e of bucket b sits at (b >> l2_bits) * l1_capacity + index_dev[e].
  * One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
  * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
@@ -212,7 +220,8 @@ int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uin
                       uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
                       uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                       uint64_t out_capacity, uint64_t* counters_dev, uint64_t* spill_list_dev,
-                      uint64_t spill_capacity, uint32_t* status_dev, ga_stream stream);
+                      uint64_t spill_capacity, uint32_t* status_dev, const uint32_t* index_dev,
+                      uint64_t l1_capacity, int l2_bits, ga_stream stream);
 /* The listed buckets again with tables in global scratch (n_ctas slices of
  * ga_sk_spill_scratch_bytes(table_slots) bytes; table_slots >= twice the windows of the largest). */
 uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots);
@@ -221,7 +230,7 @@ int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, con
                             uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
                             uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
                             uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
-                            ga_stream stream);
+                            const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream);
 /* Candidate stamps -> the reference's graph: clears edge_stamp_dev[4*i + c] when the successor of
  * window i through c is not solid (solid_dev: id table over solid_keys_dev, id = index) and folds
  * 2e / 2e+1 into node_stamp_dev[n_solid] (0xFF filled by the caller).  The arrays then feed
