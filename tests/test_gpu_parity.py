@@ -255,6 +255,50 @@ def test_bucketed_build_fuzz_and_ragged(shape, monkeypatch):
         want.close()
 
 
+def test_bucketed_dense_form_matches_golden(monkeypatch):
+    """The dense level-2 form (what the multi-GPU exchange uses) on one GPU."""
+    import ga_device as gd
+    monkeypatch.setattr(gd, "SUPERKMER_MIN_OCC", 0)
+    monkeypatch.setattr(gd, "SUPERKMER_INDEX_FORM", False)
+    monkeypatch.setattr(gd, "SUPERKMER_TARGET", 2000)
+    for name in ("nd-unpaired", "nd-unpaired-k32", "two-circles"):
+        check_against_gold(name, check_counts=False)
+
+
+def test_bucket_segments_match_whole(monkeypatch):
+    """Buckets gathered from several sources (one segment per source rank after the multi-GPU exchange):
+    two read shards scattered separately and presented as two segments give the same solid set and the
+    same candidate stamps as one pass over all reads."""
+    import torch
+    import ga_device as gd
+    gold = GOLDEN["cases"]["nd-unpaired"]
+    reads = reads_for(gold["recipe"])
+    k, F = gold["k"], gold["F"]
+    monkeypatch.setattr(gd, "SUPERKMER_TARGET", 3000)
+    whole = gd.DeviceReads(reads, False)
+    n_occ = whole.windows_total(k)
+    l1_bits, l2_bits = gd.sk_geometry(n_occ)
+    n_buckets = 1 << (l1_bits + l2_bits)
+    cut = len(reads) // 3
+    parts = []
+    for lo, hi in ((0, cut), (cut, len(reads))):
+        shard = gd.DeviceReads(reads[lo:hi], False, first_read=lo, estride=whole.estride)
+        bases, meta, offsets, hist, total = gd.sk_scatter_local(shard, k, l1_bits, l2_bits, dense=True)
+        parts.append((bases[:2 * total].clone(), meta[:total].clone(), offsets.clone(), hist.clone(), total))
+    bases = torch.cat([p[0] for p in parts])
+    meta = torch.cat([p[1] for p in parts])
+    seg = torch.stack([parts[0][2], parts[1][2] + parts[0][4]]).contiguous()
+    hist = (parts[0][3] + parts[1][3]).contiguous()
+    keys2, n2, st2 = gd.sk_bucket_pass(bases, meta, seg, 2, hist, n_buckets, k, F, n_occ, whole.status)
+    keys2, st2 = keys2[:n2, 0].clone(), st2[:4 * n2].clone().view(-1, 4)
+    keys1, n1, st1 = gd.superkmer_stamps(whole, k, F)
+    keys1, st1 = keys1[:n1, 0], st1[:4 * n1].view(-1, 4)
+    assert n1 == n2 == gold["n_solid"]
+    o1, o2 = torch.argsort(keys1), torch.argsort(keys2)
+    assert torch.equal(keys1[o1], keys2[o2])
+    assert torch.equal(st1[o1], st2[o2])
+
+
 def test_deterministic_across_runs():
     gold = GOLDEN["cases"]["nd-paired-jitter2"]
     reads = reads_for(gold["recipe"])
