@@ -660,6 +660,7 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u32 ratio_d;       // running estimates, in 1/4096: distinct windows / windows, solid windows / windows
     u32 ratio_s;
     u32 n_seg;
+    u32 next_batch;    // dynamic batch hand-out of the current walk
     u32 stack[40];
     u64 seg_lo[SB_MAX_SEG];        // the bucket's records: segment s holds [seg_lo[s], +seg_pre[s+1]-seg_pre[s])
     u64 seg_pre[SB_MAX_SEG + 1];
@@ -759,9 +760,17 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         ctl.n_solid = 0;
         ctl.overflow = 0;
         ctl.n_distinct = 0;
+        ctl.next_batch = W;            // batches 0..W-1 are the warps' first ones
     }
     __syncthreads();
     volatile u32* vovf = &ctl.overflow;
+    // batches are handed out dynamically (one shared-memory atomic per batch): with 3-4 batches per warp a
+    // static split leaves a quarter of the warps waiting at the barrier for one batch's time
+    auto next_batch = [&]() -> u64 {
+        u32 v = 0;
+        if (lane == 0) v = atomicAdd(&ctl.next_batch, 1u);
+        return __shfl_sync(FULL, v, 0);
+    };
     const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
     // smallest ordinal of "solid window `sol` followed by symbol c"
     auto stamp = [&](u32 sol, u64 top, u64 ord) {
@@ -783,10 +792,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     ulonglong2 b = make_ulonglong2(0, 0);
     u64 mt = 0;
     u32 ent = entry(warp);
-    for (u64 bt = warp; bt < n_batches && !*vovf; bt += W) {
+    for (u64 bt = warp, bt_next = 0; bt < n_batches && !*vovf; bt = bt_next) {
         const u64 idx = bt * 32u + lane;
         const bool have = idx < nrec;
-        const u32 ent_next = entry(bt + W);
+        bt_next = next_batch();
+        const u32 ent_next = entry(bt_next);
         b = make_ulonglong2(0, 0);
         mt = 0;
         if (have) {
@@ -833,9 +843,13 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     if (ctl.overflow) return false;
     const u32 n_solid = ctl.n_solid;
     if (n_solid == 0) return true;
-    if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
+    if (tid == 0) {
+        ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
+        ctl.next_batch = W;
+    }
+    __syncthreads();
     // E. second walk over the flagged records only
-    for (u64 bt = warp; bt < n_batches; bt += W) {
+    for (u64 bt = warp; bt < n_batches; bt = next_batch()) {
         // the flagged records of the batch move to the low lanes (sk_for_each_window wants the lanes
         // that hold a record to be a prefix)
         const u64 mine = bt * 32u + lane;
