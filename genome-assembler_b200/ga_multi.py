@@ -19,8 +19,9 @@ The helpers that only move tensors (`exchange_by_owner`, `all_gather_var`, `exch
 Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_buckets`, csrc/ga_superkmer.cu):
   1. each rank cuts its read shard into super-k-mer records sorted by bucket (the bucket of a window
      depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
-  2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
-     records of that range (one `all_to_all_single` per record array, plus the per-bucket histograms);
+  2. hash-partition all-to-all: the bucket ids are cut into two halves, rank g owns a contiguous range of
+     each half and receives every rank's records of those ranges (`all_to_all_single` per record array and
+     phase, plus the per-bucket histograms); the second half travels while the first is being counted;
   3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
      segment per source rank;
   4. solid keys + candidate edge stamps are gathered on rank 0, which resolves them into the CSR.
@@ -134,6 +135,7 @@ def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = Fal
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
+PHASES = 2              # the exchange is cut in this many phases so that it overlaps the bucket kernel
 
 
 def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
@@ -146,43 +148,78 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     n_buckets = 1 << (l1_bits + l2_bits)
     # 1. local records sorted by bucket
     bases, meta, offsets, hist, total = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed)
-    # 2. rank g owns buckets [bounds[g], bounds[g+1])
-    bounds = [g * n_buckets // world for g in range(world + 1)]
-    cut = offsets[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
-    send_rows = [int(cut[g + 1] - cut[g]) for g in range(world)]
+    # 2. ownership: the bucket ids are cut into PHASES halves, each half is split over the ranks, so that
+    #    the exchange of the second half runs on the NCCL stream while the first half is being counted
+    phases = PHASES if n_buckets >= PHASES * world else 1
+    per_phase = n_buckets // phases
+    bounds = [[h * per_phase + g * per_phase // world for g in range(world + 1)] for h in range(phases)]
+    flat = [b for row in bounds for b in row]
+    cut = offsets[torch.tensor(flat, dtype=torch.int64, device=dev)].tolist()
+    cut = [cut[h * (world + 1):(h + 1) * (world + 1)] for h in range(phases)]
+    send_rows = [[int(cut[h][g + 1] - cut[h][g]) for g in range(world)] for h in range(phases)]
+    mine = [bounds[h][rank + 1] - bounds[h][rank] for h in range(phases)]
     gd._mark("multi: cut")
-    with gd._timed("exchange"):
-        got_bases, recv_rows = exchange_ranges(bases.view(-1, 2)[:total], send_rows, ws_name="sk_recv_bases")
-        got_meta, _ = exchange_ranges(meta[:total], send_rows, ws_name="sk_recv_meta", recv_rows=recv_rows)
-        mine = bounds[rank + 1] - bounds[rank]
-        got_hist, _ = exchange_ranges(hist, [bounds[g + 1] - bounds[g] for g in range(world)],
-                                      recv_rows=[mine] * world)
-    del bases, meta
-    gd._mark("multi: exchange")
+    # the row counts of every phase in one small all-to-all (one host synchronisation)
+    send_cnt = torch.tensor([[send_rows[h][g] for h in range(phases)] for g in range(world)], dtype=torch.int64,
+                            device=dev)
+    recv_cnt = torch.empty_like(send_cnt)
+    dist.all_to_all_single(recv_cnt, send_cnt)
+    recv_cnt = recv_cnt.tolist()
+    recv_rows = [[int(recv_cnt[s][h]) for s in range(world)] for h in range(phases)]
+    bases2 = bases.view(-1, 2)
+    pending = []
+    with gd._timed("exchange_issue"):
+        for h in range(phases):
+            lo, hi = int(cut[h][0]), int(cut[h][world])
+            got_bases = gd.workspace("sk_recv_bases%d" % h, (sum(recv_rows[h]), 2), torch.int64)
+            got_meta = gd.workspace("sk_recv_meta%d" % h, (sum(recv_rows[h]),), torch.int64)
+            got_hist = torch.empty(world * mine[h], dtype=torch.int64, device=dev)
+            works = [dist.all_to_all_single(got_bases, bases2[lo:hi], output_split_sizes=recv_rows[h],
+                                            input_split_sizes=send_rows[h], async_op=True),
+                     dist.all_to_all_single(got_meta, meta[lo:hi], output_split_sizes=recv_rows[h],
+                                            input_split_sizes=send_rows[h], async_op=True),
+                     dist.all_to_all_single(got_hist, hist[bounds[h][0]:bounds[h][world]],
+                                            output_split_sizes=[mine[h]] * world,
+                                            input_split_sizes=[bounds[h][g + 1] - bounds[h][g] for g in range(world)],
+                                            async_op=True)]
+            pending.append((works, got_bases, got_meta, got_hist))
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
-    if mine:
+    key_parts, stamp_parts = [], []
+    for h in range(phases):
+        works, got_bases, got_meta, got_hist = pending[h]
+        for wk in works:
+            wk.wait()                  # orders the current stream after the transfer; the host does not block
+        gd._mark("multi: exchange %d" % h)
+        if not mine[h]:
+            continue
         # 3. one segment per source rank: positions from the per-source record counts
-        per_source = got_hist.view(world, mine)
-        seg_offsets = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
+        per_source = got_hist.view(world, mine[h])
+        seg_offsets = torch.zeros((world, mine[h] + 1), dtype=torch.int64, device=dev)
         seg_offsets[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
         starts = [0]
-        for rows in recv_rows[:-1]:
+        for rows in recv_rows[h][:-1]:
             starts.append(starts[-1] + rows)
         seg_offsets += torch.tensor(starts, dtype=torch.int64, device=dev).view(world, 1)
         summed = per_source.sum(dim=0).contiguous()
         n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
         solid_keys, n_solid, edge_stamp = gd.sk_bucket_pass(
-            got_bases.contiguous().view(-1), got_meta.contiguous(), seg_offsets.contiguous(), world, summed, mine,
-            k, threshold, max(n_occ_mine, 1), reads.status)
+            got_bases.view(-1), got_meta, seg_offsets.contiguous(), world, summed, mine[h], k, threshold,
+            max(n_occ_mine, 1), reads.status)
+        # the pass reuses its output workspace: keep this phase's (small) result
+        key_parts.append(solid_keys[:n_solid].clone())
+        stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4).clone())
+    del bases, meta, bases2
+    if key_parts:
+        solid_keys, edge_stamp = torch.cat(key_parts), torch.cat(stamp_parts)
     else:
         solid_keys = torch.zeros((0, 1), dtype=torch.int64, device=dev)
-        edge_stamp = torch.zeros(0, dtype=torch.int64, device=dev)
-        n_solid = 0
+        edge_stamp = torch.zeros((0, 4), dtype=torch.int64, device=dev)
+    n_solid = solid_keys.shape[0]
     # 4. everything solid meets on rank 0
     gd._mark("multi: bucket pass")
     with gd._timed("gather"):
-        all_keys, rows = gather_rows(solid_keys[:n_solid], want_rows=True)
-        all_stamps = gather_rows(edge_stamp[:4 * n_solid].view(-1, 4), recv_rows=rows)
+        all_keys, rows = gather_rows(solid_keys, want_rows=True)
+        all_stamps = gather_rows(edge_stamp, recv_rows=rows)
     gd._mark("multi: gather")
     if rank != 0:
         return None
