@@ -19,9 +19,9 @@ The helpers that only move tensors (`exchange_by_owner`, `all_gather_var`, `exch
 Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_buckets`, csrc/ga_superkmer.cu):
   1. each rank cuts its read shard into super-k-mer records sorted by bucket (the bucket of a window
      depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
-  2. hash-partition all-to-all: the bucket ids are cut into two halves, rank g owns a contiguous range of
-     each half and receives every rank's records of those ranges (`all_to_all_single` per record array and
-     phase, plus the per-bucket histograms); the second half travels while the first is being counted;
+  2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
+     records of that range (`all_to_all_single` per record array, plus the per-bucket histograms, issued
+     asynchronously; PHASES = 2 would send a second half while the first is counted -- no gain measured);
   3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
      segment per source rank;
   4. solid keys + candidate edge stamps are gathered on rank 0, which resolves them into the CSR.
@@ -135,7 +135,9 @@ def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = Fal
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
-PHASES = 2              # the exchange is cut in this many phases so that it overlaps the bucket kernel
+PHASES = 1              # 2 cuts the exchange in two halves so that the second overlaps the counting of the first;
+                        # measured on 2 and 8 B200s it gains nothing (77.2 vs 75.4 ms at N=8: the second bucket
+                        # pass and its host round trip cost what the overlap saves), so one phase is the default
 
 
 def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
