@@ -81,6 +81,20 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_TOTAL_MEM = {}
+
+
+def _free_bytes() -> int:
+    """Device memory this process can still take: total minus what torch has reserved, plus what sits
+    unused in torch's cache.  cudaMemGetInfo costs milliseconds per call (3.7 ms measured on B200 with
+    a large heap) -- more than the kernels of the small workloads it was sizing tables for."""
+    dev = torch.cuda.current_device()
+    if dev not in _TOTAL_MEM:
+        _TOTAL_MEM[dev] = torch.cuda.get_device_properties(dev).total_memory
+    stats_reserved = torch.cuda.memory_reserved(dev)
+    return max(_TOTAL_MEM[dev] - stats_reserved, 0) + (stats_reserved - torch.cuda.memory_allocated(dev))
+
+
 # Persistent device workspace for the large intermediates of the bucketed path (records, bucket-sorted
 # records, solid keys + stamps, id table).  They are tens of GB at BASELINE config C4; allocating them
 # anew every call makes the caching allocator release and re-acquire segments next to the 180 GB limit,
@@ -381,7 +395,7 @@ class KmerCounts:
     def _count(self):
         L = gn.lib()
         dev = _dev()
-        free, _ = torch.cuda.mem_get_info()
+        free = _free_bytes()
         limit = max(1024, int(free * 0.6) // self.slot_bytes)
         cap = min(max(1024, int(self.n_occ * 1.25) + 64), limit)
         while True:
@@ -414,7 +428,7 @@ class KmerCounts:
         dev = _dev()
         bits = 4 if threshold + 1 <= 15 else 8
         _mark("enter candidates")
-        free, _ = torch.cuda.mem_get_info()
+        free = _free_bytes()
         _mark("mem_get_info")
         n_cells = max(1 << 16, min(self.n_occ, int(free * 0.25) * 8 // bits))
         words = torch.zeros((n_cells * bits + 31) // 32, dtype=torch.int32, device=dev)
@@ -653,7 +667,7 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
             while slots < 2 * windows:
                 slots <<= 1
             per_cta = int(L.ga_sk_spill_scratch_bytes(slots))
-            free, _ = torch.cuda.mem_get_info()
+            free = _free_bytes()
             n_ctas = max(1, min(n_spill, 148, int(free * 0.4) // per_cta))
             scratch = torch.empty(n_ctas * per_cta, dtype=torch.uint8, device=dev)
             with _timed("sk_bucket_spill"):
@@ -847,7 +861,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
         _mark("csr plan dna")
         if _check_status(status) & gn.ST_TABLE_FULL:
             raise gn.GaError("id table overflow")
-    free, _ = torch.cuda.mem_get_info()
+    free = _free_bytes()
     cap_limit = min(0xFFFFFFF0, max(4096, int(free * 0.4) // 32))
     cap = min(cap_limit, max(1024, 3 * n_solid))
     while not dna4:
@@ -874,15 +888,21 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     if dna4:
         pass
     elif not reads.paired:
-        gn.check(L.ga_csr_plan_unpaired(gn.ptr(node_stamp), n_solid, gn.ptr(solid_keys), kw, alphabet.sym_bits,
-                                        gn.ptr(edges), cap, _stream(), C.byref(plan), C.byref(n_nodes),
-                                        C.byref(n_edges)))
+        _mark("build")
+        with _timed("csr_plan"):
+            gn.check(L.ga_csr_plan_unpaired(gn.ptr(node_stamp), n_solid, gn.ptr(solid_keys), kw, alphabet.sym_bits,
+                                            gn.ptr(edges), cap, _stream(), C.byref(plan), C.byref(n_nodes),
+                                            C.byref(n_edges)))
         attr.value = n_edges.value
+        _mark("csr plan")
     else:
-        gn.check(L.ga_csr_plan_paired(gn.ptr(solid), solid_cap, gn.ptr(solid_keys), n_solid, kw, k,
-                                      alphabet.sym_bits, gn.ptr(queries), cap, gn.ptr(qedges), cap, gn.ptr(dh),
-                                      _stream(), C.byref(plan), C.byref(n_nodes), C.byref(n_edges),
-                                      C.byref(attr)))
+        _mark("build")
+        with _timed("csr_plan"):
+            gn.check(L.ga_csr_plan_paired(gn.ptr(solid), solid_cap, gn.ptr(solid_keys), n_solid, kw, k,
+                                          alphabet.sym_bits, gn.ptr(queries), cap, gn.ptr(qedges), cap, gn.ptr(dh),
+                                          _stream(), C.byref(plan), C.byref(n_nodes), C.byref(n_edges),
+                                          C.byref(attr)))
+        _mark("csr plan")
     try:
         nn, ne = n_nodes.value, n_edges.value
         _t0 = _time.perf_counter()
