@@ -68,9 +68,6 @@ SIGNATURES = {
     "ga_prefilter_update": (_i32, [_PR, _i32, _PF, _i64, _vp]),
     "ga_prefilter_hot": (_i32, [_PF, _i64, _vp, _vp]),
     "ga_count_candidates": (_i32, [_PR, _i32, _PF, _i64, _vp, _u64, _vp, _vp]),
-    "ga_partition_kmers": (_i32, [_PR, _i32, _u32, _vp, _u64, _vp, _vp, _vp]),
-    "ga_prefilter_update_keys": (_i32, [_vp, _u64, _PF, _i64, _vp]),
-    "ga_count_candidates_keys": (_i32, [_vp, _u64, _PF, _i64, _vp, _u64, _vp, _vp]),
     "ga_sk_minimizer_len": (_i32, [_i32]),
     "ga_sk_scatter_reads": (_i32, [_PR, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "ga_sk_offsets": (_i32, [_vp, _u64, _vp, _vp, _vp]),

@@ -160,20 +160,6 @@ int ga_prefilter_hot(const ga_prefilter* pf, int64_t threshold, uint64_t* n_hot_
 int ga_count_candidates(const ga_reads* reads, int k, const ga_prefilter* pf, int64_t threshold,
                         void* table_dev, uint64_t capacity, uint32_t* status_dev, ga_stream stream);
 
-/* The same two passes over a hash-partitioned copy of the occurrence stream (64-bit keys), for read
- * sets whose sketch and candidate table exceed the L2: ga_partition_kmers writes every window key
- * into bucket floor(hash * n_parts / 2^64) (bucket b occupies items_dev[b*part_capacity ..],
- * cursors_dev[b] = keys written, zeroed by the caller; GA_STATUS_TABLE_FULL if a bucket
- * overflowed); the *_keys passes then take one bucket (or any key array) at a time. */
-int ga_partition_kmers(const ga_reads* reads, int k, uint32_t n_parts, uint64_t* items_dev,
-                       uint64_t part_capacity, uint64_t* cursors_dev, uint32_t* status_dev,
-                       ga_stream stream);
-int ga_prefilter_update_keys(const uint64_t* keys_dev, uint64_t n, const ga_prefilter* pf,
-                             int64_t threshold, ga_stream stream);
-int ga_count_candidates_keys(const uint64_t* keys_dev, uint64_t n, const ga_prefilter* pf,
-                             int64_t threshold, void* table_dev, uint64_t capacity,
-                             uint32_t* status_dev, ga_stream stream);
-
 /* ---- bucketed count + build (unpaired DNA reads, 64-bit keys): replaces BOTH hot loops,
  *      _count_kmers (debruijn_graph.py:144-152) and _build_graph (:113-142), without one random
  *      global-memory access per occurrence (csrc/ga_superkmer.cu) ------------------ */
