@@ -1079,6 +1079,42 @@ def _stream_in(ascii_pinned: torch.Tensor, reads: DeviceReads, read_len: int):
         t.record_stream(main)
 
 
+def _stream_in_packed(words_pinned: torch.Tensor, reads: DeviceReads):
+    """Like _stream_in for reads that were already packed 2 bits per base on the host (the layout of
+    ga_reads): chunks are copied straight into place on a side stream; each chunk's read range is yielded
+    once the current stream has been ordered after its copy."""
+    dev = _dev()
+    n, stride = reads.n_reads, reads.stride_words
+    per_chunk = max(1, _STREAM_CHUNK_BYTES // (stride * 8))
+    side = _copy_stream.setdefault(dev.index, torch.cuda.Stream(device=dev))
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    for r0 in range(0, n, per_chunk):
+        r1 = min(n, r0 + per_chunk)
+        with torch.cuda.stream(side):
+            reads.words[r0 * stride:r1 * stride].copy_(words_pinned[r0 * stride:r1 * stride], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        main.wait_event(ready)
+        yield r0, r1
+
+
+def host_step_packed(words_pinned: torch.Tensor, n_reads: int, read_len: int, k: int, threshold: int):
+    """host_step for unpaired DNA reads the caller already holds packed (2 bits per base, 64-bit words,
+    ga_reads layout) in pinned host memory -- the ingest format BASELINE.json's north star describes: a
+    quarter of the bytes cross PCIe."""
+    alphabet = Alphabet(np.zeros(0))
+    stride = max(1, -(-int(read_len) // 32))
+    words = torch.empty(max(1, n_reads * stride), dtype=torch.int64, device=_dev())
+    reads = DeviceReads.from_packed(words, n_reads, read_len, False, estride=read_len, alphabet=alphabet)
+    counts = KmerCounts(k, reads)
+    if counts.n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(reads, k, threshold):
+        return build_graph(counts, reads, threshold, to_host=True, feed=_stream_in_packed(words_pinned, reads))
+    for _ in _stream_in_packed(words_pinned, reads):
+        pass
+    return build_graph(counts, reads, threshold, to_host=True)
+
+
 def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: bool, k: int, threshold: int):
     """The same from host memory: ASCII reads (pinned) -> H2D -> pack -> count -> filter -> build ->
     CSR arrays on the host.  This is the call bench.py times as `e2e`.  Unpaired DNA streams in by

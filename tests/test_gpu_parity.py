@@ -299,6 +299,37 @@ def test_bucket_segments_match_whole(monkeypatch):
     assert torch.equal(st1[o1], st2[o2])
 
 
+def test_host_buffer_entries_match_device_path(monkeypatch):
+    """host_step (ASCII in pinned memory, streamed in by chunks) and host_step_packed (2-bit words in
+    pinned memory) give the CSR of the device-resident path, chunk boundaries included."""
+    import torch
+    import ga_native as gn
+    import ga_device as gd
+    monkeypatch.setattr(gd, "SUPERKMER_MIN_OCC", 0)
+    monkeypatch.setattr(gd, "_STREAM_CHUNK_BYTES", 1 << 16)          # many chunks
+    L = gn.lib()
+    dev = torch.device("cuda", 0)
+    G, n, rl, k, F = 40000, 9000, 100, 31, 2
+    stride = (rl + 31) // 32
+    genome = torch.empty(G, dtype=torch.uint8, device=dev)
+    gn.check(L.ga_gen_genome(gn.ptr(genome), G, 3, None))
+    words = torch.empty(n * stride, dtype=torch.int64, device=dev)
+    gn.check(L.ga_gen_reads(gn.ptr(genome), G, 0, n, rl, 3, 100, gn.ptr(words), stride, 0, 0, None))
+    reads = gd.DeviceReads.from_packed(words, n, rl, False, estride=rl)
+    want = gd.build_graph(gd.KmerCounts(k, reads), reads, F, to_host=True)
+    ascii_dev = torch.empty(n * rl, dtype=torch.uint8, device=dev)
+    gn.check(L.ga_unpack_reads(gn.ptr(words), n, rl, stride, 2, gn.ptr(reads.alphabet.inv_dev), gn.ptr(ascii_dev), None))
+    pinned = torch.empty(n * rl, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(ascii_dev)
+    packed = torch.empty(n * stride, dtype=torch.int64, pin_memory=True)
+    packed.copy_(words)
+    torch.cuda.synchronize()
+    for got in (gd.host_step(pinned, n, rl, False, k, F), gd.host_step_packed(packed, n, rl, k, F)):
+        assert got.n_nodes == want.n_nodes > 0 and got.n_edges == want.n_edges
+        for field in ("rowptr", "col", "indeg", "branching", "last_char", "keys_a"):
+            assert np.array_equal(getattr(got, field), getattr(want, field)), field
+
+
 def test_deterministic_across_runs():
     gold = GOLDEN["cases"]["nd-paired-jitter2"]
     reads = reads_for(gold["recipe"])
