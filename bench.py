@@ -330,7 +330,7 @@ def run_gpu_arm(args):
         e2e_s = float(t.item())
         e2e = {"value": occ_total / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(n_reads * read_len),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
-    if world == 1:
+    if world == 1 and not os.environ.get("GA_BENCH_SKIP_E2E"):      # (A/B runs of kernel variants skip the host legs)
         ascii_dev = torch.empty(n_local * mates * read_len, dtype=torch.uint8, device=dev)
         gn.check(L.ga_unpack_reads(gn.ptr(words), n_local * mates, read_len, stride, 2,
                                    gn.ptr(reads.alphabet.inv_dev), gn.ptr(ascii_dev), None))
