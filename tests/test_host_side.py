@@ -135,3 +135,39 @@ def test_break_helpers():
         assert [list(t) for t in got] == want
     for a, b, want in GOLDEN["overlap"]:
         assert dg.PairedDeBruijnGraph._find_longest_overlap_brute(a, b) == want
+
+
+def test_bucketed_entries_reject_bad_arguments():
+    """Argument validation of the ga_sk_* entries happens before any CUDA call: checkable without a GPU."""
+    import ga_native as gn
+    L = _lib()
+    assert L.ga_sk_minimizer_len(31) == 15 and L.ga_sk_minimizer_len(32) == 16 and L.ga_sk_minimizer_len(5) == 4
+    assert L.ga_sk_minimizer_len(21) == 11 and L.ga_sk_minimizer_len(1) == 0
+    reads = gn.GaReads()
+    reads.n_reads, reads.uniform_len, reads.stride_words, reads.estride = 4, 100, 4, 100
+    reads.storage_bits = reads.sym_bits = 2
+    dummy = C.create_string_buffer(64)
+    ptr = C.cast(dummy, C.c_void_p)
+    # bucket bits out of range, paired reads, k beyond 64-bit keys
+    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 11, 10, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert b"bucket bits" in L.ga_last_error()
+    reads.paired = 1
+    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    reads.paired = 0
+    assert L.ga_sk_scatter_reads(C.byref(reads), 40, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    # ordinals beyond 47 bits
+    reads.first_read = 1 << 46
+    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert b"47 bits" in L.ga_last_error()
+    # level-2 pass: exactly one of the dense / index outputs
+    assert L.ga_sk_scatter_buckets(ptr, ptr, 16, ptr, 2, 2, ptr, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_buckets(ptr, ptr, 16, ptr, 2, 2, ptr, None, None, None, None) == gn.GA_ERR_BAD_ARG
+    # bucket pass: table size must be a power of two within the shared-memory pool, threshold within the counter
+    args = (ptr, ptr, ptr, 1, ptr, 4, 31, 3)
+    tail = (ptr, ptr, 16, ptr, ptr, 16, ptr, None, 0, 0, None)
+    assert L.ga_sk_count_build(*args, 3000, 16, *tail) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_count_build(*args, 1 << 20, 16, *tail) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_count_build(ptr, ptr, ptr, 1, ptr, 4, 31, 70000, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_count_build(ptr, ptr, ptr, 99, ptr, 4, 31, 3, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_resolve(None, 5, 31, ptr, 16, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 56
