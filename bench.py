@@ -274,7 +274,7 @@ def run_gpu_arm(args):
     # dominant-kernel roofline from the per-launch CUDA events recorded inside the timed steps
     # per kernel: total ms per step, launches per step, occurrences per launch (rank 0's shard)
     host_notes = timers.pop("_host", [])
-    if rank == 0 and host_notes:
+    if rank == 0 and host_notes and os.environ.get("GA_TRACE"):
         print("host: " + " | ".join(host_notes), file=sys.stderr)
     marks = timers.pop("_marks", [])
     stage_ms = {}

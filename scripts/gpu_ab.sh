@@ -9,6 +9,6 @@ for spec in "$@"; do
     timeout 600 python bench.py --workload c4 --steps 3 --warmup 2 --sample-reads 2000 > gpurun_out/bench_ab_$name.json 2>gpurun_out/bench_ab_$name.err )
   python -c "
 import json; d=json.load(open('gpurun_out/bench_ab_$name.json')); k=d['roofline']['kernel_ms_per_step']; print('$name', round(d['ms_per_step'],1), {a:round(b,1) for a,b in k.items() if b>1}, round(d['e2e']['ms_per_step'],1))"
-  grep "^host" gpurun_out/bench_ab_$name.err | tail -1
+
 done
 done
