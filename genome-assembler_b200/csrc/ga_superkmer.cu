@@ -127,7 +127,8 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const u64 r = tile * S1_WARPS + warp;
         const bool valid = r < rv.n_reads;
-        const u32 len = valid ? ga_read_len(rv, r) : 0u;
+        // paired input: both mates are plain reads here (counting only); windows run over mate 1's length
+        const u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
         const u32 nwt = len >= (u32)w ? len - (u32)w + 1u : 0u;     // windows of this read
         const u32 nch = (nwt + 127u) / 128u;
         const u64* rp = valid ? ga_read_ptr(rv, r) : rv.words;
@@ -730,7 +731,7 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
 template <class Tab>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                SkGather gather, int w, u32 threshold, const Tab& tab, u32 cap,
-                                               u32 max_solid, bool flag_all, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
+                                               u32 max_solid, bool flag_all, bool count_only, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
                                                u64* __restrict__ edge_stamp_out, u64 out_capacity,
                                                u64* n_solid_global) {
     const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
@@ -832,7 +833,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             } else if (state == CS_SOLID_BEFORE) {
                 sol = tab.sidx_ld(slot);          // 0: its index is still being published
             }
-            if (!follows) return;
+            if (!follows || count_only) return;
             if (sol) stamp(sol, top, ord);
             else if (!flag_all) tab.flag_set((u32)(bt * 32u) + owner);
         });
@@ -848,8 +849,8 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         ctl.next_batch = W;
     }
     __syncthreads();
-    // E. second walk over the flagged records only
-    for (u64 bt = warp; bt < n_batches; bt = next_batch()) {
+    // E. second walk over the flagged records only (none when only the solid set is asked for)
+    for (u64 bt = count_only ? n_batches : (u64)warp; bt < n_batches; bt = next_batch()) {
         // the flagged records of the batch move to the low lanes (sk_for_each_window wants the lanes
         // that hold a record to be a prefix)
         const u64 mine = bt * 32u + lane;
@@ -877,7 +878,8 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u64 base = ctl.out_base;
     if (base + n_solid <= out_capacity) {
         for (u32 s = tid; s < n_solid; s += T) solid_keys_out[base + s] = tab.skey_ld(s);
-        for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = tab.stamp_ld(s);
+        if (edge_stamp_out)
+            for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = tab.stamp_ld(s);
     }
     return true;
 }
@@ -969,7 +971,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             if (max_solid > solid_limit) max_solid = solid_limit;
             tab.stamps = tab.skeys + 8u * max_solid;
             const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, max_solid, flag_all, parts, part, ctl,
+            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, max_solid, flag_all,
+                                           edge_stamp_out == nullptr, parts, part, ctl,
                                            solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
@@ -1031,7 +1034,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         }
         __syncthreads();
         const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, cap, true, parts, part, ctl,
+        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, cap, true, edge_stamp_out == nullptr, parts, part, ctl,
                                        solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
@@ -1085,8 +1088,8 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
         return GA_ERR_BAD_ARG;
     }
     const int w = k - 1;
-    if (reads->paired || reads->storage_bits != 2 || reads->sym_bits != 2 || w < 1 || w > 31) {
-        ga_set_error("ga_sk_scatter_reads: needs unpaired 2-bit reads and 2 <= k <= 32");
+    if (reads->storage_bits != 2 || reads->sym_bits != 2 || w < 1 || w > 31) {
+        ga_set_error("ga_sk_scatter_reads: needs 2-bit reads and 2 <= k <= 32");
         return GA_ERR_BAD_ARG;
     }
     if (reads->estride == 0 || (reads->first_read + reads->n_reads) > ((1ull << 47) / reads->estride)) {
@@ -1171,7 +1174,7 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
                                  uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
                                  const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev || !edge_stamp_out_dev ||
+    if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev ||
         !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
         threshold > 60000 || !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS ||
         max_solid == 0 || n_segments == 0 || n_segments > SB_MAX_SEG) {
@@ -1216,7 +1219,7 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
                                        ga_stream stream) {
     const int w = k - 1;
     if (!bases_dev || !meta_dev || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
-        !edge_stamp_out_dev || !counters_dev || !status_dev || w < 1 || w > 31 || threshold < 0 ||
+        !counters_dev || !status_dev || w < 1 || w > 31 || threshold < 0 ||
         !is_pow2(table_slots) || table_slots < 256 || n_ctas == 0 || n_segments == 0 || n_segments > SB_MAX_SEG ||
         n_buckets == 0) {
         ga_set_error("ga_sk_count_build_spill: bad arguments");

@@ -548,9 +548,10 @@ def sketch_struct(cells: torch.Tensor, widths) -> gn.GaSketch:
 
 
 # ----------------------------------------------------------------------------------- buckets
-def superkmer_supported(reads: "DeviceReads", k: int, threshold: int) -> bool:
-    """The bucketed path covers unpaired 2-bit reads whose windows fit 62 bits."""
-    if reads.paired or reads.alphabet.storage_bits != 2 or not 2 <= k <= 32:
+def superkmer_supported(reads: "DeviceReads", k: int, threshold: int, counting_only: bool = False) -> bool:
+    """The bucketed path covers 2-bit reads whose windows fit 62 bits: count + build for unpaired reads,
+    counting alone (the solid set) for read pairs too."""
+    if (reads.paired and not counting_only) or reads.alphabet.storage_bits != 2 or not 2 <= k <= 32:
         return False
     if not 0 <= threshold <= 60000:
         return False
@@ -632,7 +633,7 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
 
 
 def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, k: int, threshold: int,
-                   n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0):
+                   n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0, want_stamps: bool = True):
     """Bucket-sorted records -> (solid keys (cap, 1) int64, n_solid, candidate edge stamps int64[4*cap]).
     offsets: n_segments rows of n_buckets+1 record positions (one row on a single GPU, one per source
     rank after the multi-GPU exchange); hist[b] & 0xFFFFFFFF = windows of bucket b over all segments.
@@ -646,7 +647,7 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
         solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
-        edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64)
+        edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64) if want_stamps else None
         status.zero_()
         with _timed("sk_bucket", n_occ):
             gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
@@ -685,6 +686,19 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
         out_cap = n_solid
     _mark("sk bucket pass")
     return solid_keys, n_solid, edge_stamp
+
+
+def superkmer_solid(reads: "DeviceReads", k: int, threshold: int):
+    """(solid keys (n, 1) int64, n) through the buckets, counting only -- paired reads too (both mates
+    count as plain reads, debruijn_graph.py:349-367)."""
+    n_occ = reads.windows_total(k)
+    l1_bits, l2_bits = sk_geometry(n_occ)
+    out = sk_scatter_local(reads, k, l1_bits, l2_bits, None, dense=not SUPERKMER_INDEX_FORM)
+    bases, meta, offsets, hist = out[:4]
+    index, cap1 = (out[5], out[6]) if SUPERKMER_INDEX_FORM else (None, 0)
+    keys, n_solid, _ = sk_bucket_pass(bases, meta, offsets, 1, hist, 1 << (l1_bits + l2_bits), k, threshold, n_occ,
+                                      reads.status, index, cap1, l2_bits, want_stamps=False)
+    return keys, n_solid
 
 
 def superkmer_stamps(reads: "DeviceReads", k: int, threshold: int, feed=None):
@@ -821,8 +835,13 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     bucketed = (keep_fn is None and sketch is None and counts._table is None and not counts._cand and
                 counts.n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(reads, k, threshold))
     edge_stamp = None
+    counted = (not bucketed and keep_fn is None and sketch is None and counts._table is None and not counts._cand and
+               reads.paired and counts.n_occ >= SUPERKMER_MIN_OCC and
+               superkmer_supported(reads, k, threshold, counting_only=True))
     if bucketed:
         solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold, feed)
+    elif counted:
+        solid_keys, n_solid = superkmer_solid(reads, k, threshold)       # read pairs: the solid set from the buckets
     elif keep_fn is not None:
         solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
     else:

@@ -165,7 +165,9 @@ int ga_count_candidates(const ga_reads* reads, int k, const ga_prefilter* pf, in
  *      global-memory access per occurrence (csrc/ga_superkmer.cu) ------------------ */
 /* m-mer length used to pick a window's bucket for --kmer_length k */
 int ga_sk_minimizer_len(int k);
-/* Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases in
+/* Paired input (reads->paired) is taken as 2*pairs plain reads whose windows run over mate 1's length
+ * (debruijn_graph.py:349-374): enough for counting, i.e. for ga_sk_count_build without edge stamps.
+ * Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases in
  * rec_bases_dev + one meta word in rec_meta_dev) and scatter them to 2^l1_bits level-1 buckets of
  * l1_capacity records each (bucket b at index b*l1_capacity; l1_cursors_dev[b] = records written,
  * zeroed by the caller).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) accumulates, per final
@@ -196,7 +198,7 @@ int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_de
  * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
  * stamps (edge_stamp_out_dev[4*i + c] = smallest occurrence ordinal of "window i followed by symbol
- * c", all-ones if never).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
+ * c", all-ones if never; edge_stamp_out_dev == NULL: counting only, just the solid windows).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
  * windows found (may exceed out_capacity: nothing is written beyond it, the caller retries with
  * that many), [2] passes that did not fit and were listed in spill_list_dev.  A bucket whose distinct
  * or solid windows exceed the pool is done in 2, 4, ... 32 passes over disjoint hash ranges of its

@@ -255,6 +255,21 @@ def test_bucketed_build_fuzz_and_ragged(shape, monkeypatch):
         want.close()
 
 
+@pytest.mark.parametrize("name", ["nd-paired", "nd-paired-jitter2", "toy-paired", "kat-f1", "homopoly-A-paired"])
+def test_bucketed_counting_for_pairs_matches_golden(name, monkeypatch):
+    """Read pairs take the buckets for counting (the solid set) and the paired build afterwards."""
+    import ga_device as gd
+    monkeypatch.setattr(gd, "SUPERKMER_MIN_OCC", 0)
+    monkeypatch.setattr(gd, "SUPERKMER_TARGET", 3000)
+    calls = []
+    real = gd.superkmer_solid
+    monkeypatch.setattr(gd, "superkmer_solid", lambda *a, **kw: calls.append(1) or real(*a, **kw))
+    check_against_gold(name, check_counts=False)
+    gold = GOLDEN["cases"][name]
+    dna = all(set(a) | set(b) <= set("ACGT") for a, b in reads_for(gold["recipe"]))
+    assert bool(calls) == (dna and gold["k"] <= 32)
+
+
 def test_bucketed_dense_form_matches_golden(monkeypatch):
     """The dense level-2 form (what the multi-GPU exchange uses) on one GPU."""
     import ga_device as gd

@@ -148,12 +148,9 @@ def test_bucketed_entries_reject_bad_arguments():
     reads.storage_bits = reads.sym_bits = 2
     dummy = C.create_string_buffer(64)
     ptr = C.cast(dummy, C.c_void_p)
-    # bucket bits out of range, paired reads, k beyond 64-bit keys
+    # bucket bits out of range, k beyond 64-bit keys
     assert L.ga_sk_scatter_reads(C.byref(reads), 31, 11, 10, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     assert b"bucket bits" in L.ga_last_error()
-    reads.paired = 1
-    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
-    reads.paired = 0
     assert L.ga_sk_scatter_reads(C.byref(reads), 40, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     # ordinals beyond 47 bits
     reads.first_read = 1 << 46
