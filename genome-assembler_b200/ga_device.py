@@ -27,6 +27,8 @@ TWO_PHASE_MIN_READS = 1 << 22
 TWO_PHASE_MIN_STEP = 1 << 20
 # bucketed (super-k-mer) count + build, csrc/ga_superkmer.cu: unpaired DNA, 64-bit keys
 SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path (tests set 0 to force buckets)
+SUPERKMER_MIN_OCC_PAIRS = 1 << 28       # read pairs: bucketed counting only pays once the tables outgrow the L2
+                                        # (C3, 1.0e8 occurrences: 4.5 ms through the buckets, 3.9 ms through the tables)
 SUPERKMER_TARGET = int(_os_early.environ.get("GA_SK_TARGET", "8192"))    # windows per bucket aimed for (C2 sweep: 8192 beats 16384 by 38 % on the bucket kernel; C4 sits at the 2^20-bucket cap either way)
 SUPERKMER_TABLE_SLOTS = 8192            # shared-memory table slots per bucket (tests shrink it to force spills)
 SUPERKMER_INDEX_FORM = _os_early.environ.get("GA_SK_DENSE", "0") != "1"   # single GPU: sort 32-bit indices, not records
@@ -836,7 +838,7 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
                 counts.n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(reads, k, threshold))
     edge_stamp = None
     counted = (not bucketed and keep_fn is None and sketch is None and counts._table is None and not counts._cand and
-               reads.paired and counts.n_occ >= SUPERKMER_MIN_OCC and
+               reads.paired and counts.n_occ >= max(SUPERKMER_MIN_OCC, SUPERKMER_MIN_OCC_PAIRS) and
                superkmer_supported(reads, k, threshold, counting_only=True))
     if bucketed:
         solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold, feed)

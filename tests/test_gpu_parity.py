@@ -260,6 +260,7 @@ def test_bucketed_counting_for_pairs_matches_golden(name, monkeypatch):
     """Read pairs take the buckets for counting (the solid set) and the paired build afterwards."""
     import ga_device as gd
     monkeypatch.setattr(gd, "SUPERKMER_MIN_OCC", 0)
+    monkeypatch.setattr(gd, "SUPERKMER_MIN_OCC_PAIRS", 0)
     monkeypatch.setattr(gd, "SUPERKMER_TARGET", 3000)
     calls = []
     real = gd.superkmer_solid
