@@ -40,6 +40,17 @@ __host__ __device__ __forceinline__ u32 sk_hash32(u32 x) {
     return x ^ (x >> 16);
 }
 
+// hash of one m-mer (only its rank among the <= 16 m-mers of a window matters: one multiplication with an
+// xor-fold is enough to break the bias towards poly-A; the bucket bits come from sk_hash32 of the minimum)
+__device__ __forceinline__ u32 sk_mmer_hash(u32 x) {
+#ifdef GA_SK_FULL_MMER_HASH
+    return sk_hash32(x);
+#else
+    x *= 0x9E3779B1u;
+    return x ^ (x >> 15);
+#endif
+}
+
 // reverse the order of the 32 two-bit symbols of a word (reads store symbol i at bits 2i..2i+1,
 // records and keys keep the first symbol most significant)
 __device__ __forceinline__ u64 sk_rev2(u64 x) {
@@ -159,8 +170,8 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
                     const u64 y = lane < 4u ? get64(q0 + 128u) : 0ull;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        v[t] = q0 + t + (u32)m <= len ? sk_hash32((u32)(x >> (2 * t)) & mmask) : 0xFFFFFFFFu;
-                        ov[t] = (lane < 4u && q0 + 128u + t + (u32)m <= len) ? sk_hash32((u32)(y >> (2 * t)) & mmask)
+                        v[t] = q0 + t + (u32)m <= len ? sk_mmer_hash((u32)(x >> (2 * t)) & mmask) : 0xFFFFFFFFu;
+                        ov[t] = (lane < 4u && q0 + 128u + t + (u32)m <= len) ? sk_mmer_hash((u32)(y >> (2 * t)) & mmask)
                                                                              : 0xFFFFFFFFu;
                     }
                 }
