@@ -32,23 +32,11 @@ namespace {
 
 constexpr u32 FULL = 0xFFFFFFFFu;
 
-__host__ __device__ __forceinline__ u32 sk_hash32(u32 x) {
-    x ^= x >> 16;
-    x *= 0x85ebca6bu;
-    x ^= x >> 13;
-    x *= 0xc2b2ae35u;
-    return x ^ (x >> 16);
-}
-
 // hash of one m-mer (only its rank among the <= 16 m-mers of a window matters: one multiplication with an
-// xor-fold is enough to break the bias towards poly-A; the bucket bits come from sk_hash32 of the minimum)
+// xor-fold is enough to break the bias towards poly-A; the bucket bits come from sk_bucket_of the minimum)
 __device__ __forceinline__ u32 sk_mmer_hash(u32 x) {
-#ifdef GA_SK_FULL_MMER_HASH
-    return sk_hash32(x);
-#else
     x *= 0x9E3779B1u;
     return x ^ (x >> 15);
-#endif
 }
 
 // reverse the order of the 32 two-bit symbols of a word (reads store symbol i at bits 2i..2i+1,
@@ -63,6 +51,24 @@ __device__ __forceinline__ u32 meta_windows(u64 meta) { return (u32)(meta & 31u)
 __device__ __forceinline__ bool meta_has_next(u64 meta) { return (meta >> 5) & 1u; }
 __device__ __forceinline__ u32 meta_b2(u64 meta) { return (u32)(meta >> 6) & 1023u; }
 __device__ __forceinline__ u64 meta_ordinal(u64 meta) { return meta >> 16; }
+
+// A level-1 bucket holds 32-byte slots {bases hi, bases lo, meta, 0}: ONE full-sector store per record.
+// Two arrays (16 bytes of bases here, the meta word there) cost two partial-sector requests per record, and
+// those requests -- not instructions, not DRAM bytes -- were what bounded every variant of the scatter
+// kernel (scripts/scatter_probe.py: 26.8 ms -> 12.9 ms on a quarter of C4 with nothing else changed).
+__device__ __forceinline__ void sk_store_slot(u64* __restrict__ rec, u64 slot, u64 hi, u64 lo, u64 meta) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(rec + 4u * slot), "l"(hi), "l"(lo), "l"(meta), "l"(0ull)
+                 : "memory");
+}
+__device__ __forceinline__ void sk_load_slot(const u64* __restrict__ rec, u64 slot, ulonglong2& bases, u64& meta) {
+    u64 pad;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(bases.x), "=l"(bases.y), "=l"(meta), "=l"(pad)
+                 : "l"(rec + 4u * slot));
+}
+// The level-1 cursors sit 128 bytes apart: packed into 8 KB they all live in a handful of L2 slices, whose
+// atomic units then bound the kernel (one returned atomic per record: 18.3 ms packed, 5.5 ms spread, same probe).
+constexpr u32 SK_CURSOR_STRIDE = 16;
 
 // ------------------------------------------------------------------------------------------------
 // 1. reads -> records in level-1 buckets
@@ -82,15 +88,24 @@ struct S1Shared {
     u32 wcount[S1_WARPS];
 };
 
-__device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n, u32 n_l1, ulonglong2* __restrict__ out_bases,
-                                         u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors,
-                                         bool& overflow) {
+// the minimum of n hashes crowds near zero: mix it once more before taking the bucket bits from the top
+// (bits == 0: one bucket)
+__device__ __forceinline__ u32 sk_bucket_of(u32 min_hash, int bits) {
+    const u32 x = (min_hash ^ (min_hash >> 13)) * 0x85EBCA77u;
+    return __funnelshift_rc(x, 0u, 32u - (u32)bits);
+}
+
+// stage -> level-1 buckets: one global cursor bump per non-empty bucket, then the records of a bucket land
+// next to each other.  SM: S1Shared or S1LShared; THREADS: the CTA's size.
+template <class SM, int THREADS>
+__device__ __forceinline__ void s1_flush(SM& sm, u32 n, u32 n_l1, u64* __restrict__ out_rec, u64 cap1,
+                                         u64* __restrict__ cursors, bool& overflow) {
     __syncthreads();
-    for (u32 p = threadIdx.x; p < n_l1; p += S1_THREADS) {
+    for (u32 p = threadIdx.x; p < n_l1; p += THREADS) {
         const u32 c = sm.hist[p];
         u64 base = 0;
         if (c) {
-            base = atomicAdd((unsigned long long*)&cursors[p], (unsigned long long)c);
+            base = atomicAdd((unsigned long long*)&cursors[p * SK_CURSOR_STRIDE], (unsigned long long)c);
             if (base + c > cap1) {
                 overflow = true;
                 base = GA_NONE64;      // dropped: the host retries with larger buckets
@@ -100,14 +115,13 @@ __device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n, u32 n_l1, ulonglon
         sm.hist[p] = 0;
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < n; i += S1_THREADS) {
+    for (u32 i = threadIdx.x; i < n; i += THREADS) {
         const u32 br = sm.br[i];
         const u32 b1 = br >> 16;
         const u64 base = sm.gbase[b1];
         if (base == GA_NONE64) continue;
-        const u64 dst = (u64)b1 * cap1 + base + (br & 0xFFFFu);
-        out_bases[dst] = sm.bases[i];
-        out_meta[dst] = sm.meta[i];
+        const ulonglong2 bs = sm.bases[i];
+        sk_store_slot(out_rec, (u64)b1 * cap1 + base + (br & 0xFFFFu), bs.x, bs.y, sm.meta[i]);
     }
     __syncthreads();
 }
@@ -118,9 +132,8 @@ __device__ __forceinline__ void s1_flush(S1Shared& sm, u32 n, u32 n_l1, ulonglon
 // NMM: m-mers per window when known at compile time (16 for k >= 27, the common case), 0 = runtime.
 template <int NMM>
 __global__ void __launch_bounds__(S1_THREADS)
-sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ulonglong2* __restrict__ out_bases,
-                        u64* __restrict__ out_meta, u64 cap1, u64* __restrict__ cursors, u64* __restrict__ ghist,
-                        u32* status) {
+sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
+                        u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sm = *reinterpret_cast<S1Shared*>(smem_raw);
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -202,8 +215,7 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
                             res = min(res, fetch(a, b, f + 1u));
                         }
                     }
-                    // the minimum of n hashes crowds near zero: hash it again before taking bucket bits
-                    bkt[t] = bits ? sk_hash32(res ^ 0x5bd1e995u) >> (32 - bits) : 0u;
+                    bkt[t] = sk_bucket_of(res, bits);
                 }
                 // record starts: bucket change, or a multiple of 32 windows (records hold at most 32)
                 const u32 nvalid = min(nwt - c * 128u, 128u);
@@ -254,7 +266,7 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
             const u32 total = __shfl_sync(FULL, incl, S1_WARPS - 1);
             const u32 my_base = __shfl_sync(FULL, incl - mine, warp);
             if (staged + total > S1_STAGE) {
-                s1_flush(sm, staged, n_l1, out_bases, out_meta, cap1, cursors, overflow);
+                s1_flush<S1Shared, S1_THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
                 staged = 0;
             }
             for (u32 l = lane; l < mycount; l += 32u) {
@@ -274,7 +286,283 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, ul
             staged += total;
         }
     }
-    s1_flush(sm, staged, n_l1, out_bases, out_meta, cap1, cursors, overflow);
+    s1_flush<S1Shared, S1_THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
+    if (overflow) atomicOr(status, GA_ST_TABLE_FULL);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1b. the same cut, one LANE per read (windows of 16 m-mers: 26 <= k-1 <= 31, every real configuration).
+// The warp-per-read kernel above pays ~610 warp instructions per 150-base read, most of them shuffles and
+// ballots of the cooperative sliding minimum and of the record search, at 24 of 32 lanes.  Here a thread walks
+// its own read 32 windows at a time with everything in registers:
+//   * the chunk's 47 m-mer hashes are taken from three 64-bit words with funnel shifts; the sliding minimum
+//     over 16 m-mers is a suffix minimum of one aligned block of 16 combined with a running prefix minimum of
+//     the next block (3 min per window, no shuffles, no branches);
+//   * a window starts a record when its bucket differs from its predecessor's (or at a multiple of 32 windows):
+//     the start mask stays in a register, the bucket of the i-th record goes to a per-thread column in shared
+//     memory (predicated store);
+//   * the records are then built by their own thread (divergent, but short) into the CTA's stage, at most SUB
+//     per thread and sub-round so that a sub-round always fits the stage; one barrier per sub-round.
+// Buckets, record cuts and record contents are bit-identical to the kernel above (tests compare the two).
+template <int THREADS, int STAGE, int SUB>
+struct S1LShared {
+    ulonglong2 bases[STAGE];
+    u64 meta[STAGE];
+    u32 br[STAGE];                 // level-1 bucket << 16 | rank inside this flush
+    u64 gbase[S1_MAXB];
+    u32 hist[S1_MAXB];
+    u32 bk[32][THREADS];           // bucket of a thread's i-th record of the current chunk
+    u32 round[3];                  // records of a sub-round | records still to come << 16; three slots in rotation
+};
+
+template <int THREADS, int STAGE, int SUB>
+__global__ void __launch_bounds__(THREADS, 2)
+sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
+                             u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
+    static_assert(THREADS * SUB <= STAGE, "a sub-round must fit the stage");
+    using Shared = S1LShared<THREADS, STAGE, SUB>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u32 n_l1 = 1u << l1_bits;
+    const int bits = l1_bits + l2_bits;
+    const u32 l2_mask = (1u << l2_bits) - 1u;
+    const u32 mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    bool overflow = false;
+    u32 staged = 0;                                       // records in the stage; identical in every thread
+    u32 slot = 0;                                         // sub-round counter slot; identical in every thread
+    for (u32 p = tid; p < n_l1; p += THREADS) sm.hist[p] = 0;
+    if (tid < 3u) sm.round[tid] = 0;
+    __syncthreads();
+
+    const u64 n_tiles = (rv.n_reads + THREADS - 1) / THREADS;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 r = tile * THREADS + tid;
+        const bool valid = r < rv.n_reads;
+        // paired input: both mates are plain reads here (counting only); windows run over mate 1's length
+        const u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
+        const u32 nwt = len >= (u32)w ? len - (u32)w + 1u : 0u;     // windows of this read
+        const u32 nch = (nwt + 31u) / 32u;
+        const u64* rp = valid ? ga_read_ptr(rv, r) : rv.words;
+        const u32 n_words = nwt ? (len + 31u) / 32u : 0u;
+        const u64 e_read = (rv.first_read + r) * (u64)rv.estride;
+        // words c, c+1, c+2 of the read while chunk c (windows 32c .. 32c+31) is walked
+        u64 w0 = 0, w1 = n_words > 0u ? __ldg(rp) : 0ull, w2 = n_words > 1u ? __ldg(rp + 1) : 0ull;
+        for (u32 c = 0;; ++c) {
+            const bool more = c < nch;
+            if (!__syncthreads_or(more)) break;
+            w0 = w1;
+            w1 = w2;
+            w2 = c + 2u < n_words ? __ldg(rp + c + 2u) : 0ull;
+            u32 mask = 0, cur = 0, nv = 0;                // record starts, records, windows of this chunk
+            if (more) {
+                nv = min(nwt - c * 32u, 32u);
+                const u32 vmask = nv >= 32u ? FULL : (1u << nv) - 1u;
+                const u32 R[4] = {(u32)w0, (u32)(w0 >> 32), (u32)w1, (u32)(w1 >> 32)};
+                // hash of the m-mer at symbol 32c + j, j = 0..46 (past the read's end: anything, such windows are masked)
+                auto mm = [&](int j) -> u32 {
+                    return sk_mmer_hash(__funnelshift_r(R[j >> 4], R[(j >> 4) + 1], 2u * ((u32)j & 15u)) & mmask);
+                };
+                // a window past the read's end may "start a record" too: its column entry lands behind the real
+                // ones and its mask bit is dropped below
+                u32 prev = 0;
+                u32* col = &sm.bk[0][tid];
+                auto window = [&](int j, u32 min_hash) {
+                    const u32 bkt = sk_bucket_of(min_hash, bits);
+                    if (j == 0 || bkt != prev) {
+                        *col = bkt;
+                        col += THREADS;
+                        mask |= 1u << j;
+                    }
+                    prev = bkt;
+                };
+                u32 S[16], T[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) S[o] = mm(o);
+#pragma unroll
+                for (int o = 14; o >= 0; --o) S[o] = min(S[o], S[o + 1]);       // S[o] = min of m-mers o..15
+                u32 P = 0xFFFFFFFFu;                                             // min of the next block's m-mers so far
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    window(o, o ? min(S[o], P) : S[0]);                          // m-mers o..15 and 16..15+o
+                    T[o] = mm(16 + o);
+                    P = min(P, T[o]);
+                }
+#pragma unroll
+                for (int o = 14; o >= 0; --o) T[o] = min(T[o], T[o + 1]);
+                P = 0xFFFFFFFFu;
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    window(16 + o, o ? min(T[o], P) : T[0]);
+                    if (o < 15) P = min(P, mm(32 + o));
+                }
+                mask &= vmask;
+                cur = (u32)__popc(mask);
+            }
+            // records: at most SUB per thread and sub-round
+            u32 rest = mask, done = 0;
+            for (;;) {
+                const u32 cnt = min(cur - done, (u32)SUB);
+                const u32 mine = cnt | ((cur - done - cnt) << 16);          // this sub-round | later ones
+                u32 incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= (u32)o) incl += t;
+                }
+                const u32 wsum = __shfl_sync(FULL, incl, 31);
+                u32 wbase = 0;
+                if (lane == 31u && wsum) wbase = atomicAdd(&sm.round[slot], wsum);
+                wbase = __shfl_sync(FULL, wbase, 31) & 0xFFFFu;
+                __syncthreads();
+                const u32 all = sm.round[slot];
+                // the slot of the previous sub-round is free (every thread read it before this barrier) and is not
+                // touched again before the barrier after next
+                if (tid == 0) sm.round[slot == 0u ? 2u : slot - 1u] = 0;
+                slot = slot == 2u ? 0u : slot + 1u;
+                const u32 total = all & 0xFFFFu;
+                if (staged + total > (u32)STAGE) {
+                    s1_flush<Shared, THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
+                    staged = 0;
+                }
+                u32 idx = staged + wbase + ((incl - mine) & 0xFFFFu);
+                for (u32 it = 0; it < cnt; ++it, ++idx) {
+                    const u32 j = (u32)__ffs(rest) - 1u;
+                    rest &= rest - 1u;
+                    const u32 nwin = (rest ? (u32)__ffs(rest) - 1u : nv) - j;
+                    const u32 b = sm.bk[done + it][tid];
+                    const u32 p = c * 32u + j, sh = 2u * j;
+                    const u64 hi = sk_rev2(sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0);
+                    const u64 lo = sk_rev2(sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1);
+                    const u32 has_next = p + nwin - 1u + (u32)w < len ? 1u : 0u;
+                    const u32 b1 = b >> l2_bits, b2 = b & l2_mask;
+                    const u32 rank = atomicAdd(&sm.hist[b1], 1u);
+                    atomicAdd((unsigned long long*)&ghist[b], (1ull << 32) | (unsigned long long)nwin);
+                    sm.bases[idx] = make_ulonglong2(hi, lo);
+                    sm.meta[idx] = ((e_read + p) << 16) | ((u64)b2 << 6) | ((u64)has_next << 5) | (u64)(nwin - 1u);
+                    sm.br[idx] = (b1 << 16) | rank;
+                }
+                done += cnt;
+                staged += total;
+                if ((all >> 16) == 0u) break;
+            }
+        }
+    }
+    s1_flush<Shared, THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
+    if (overflow) atomicOr(status, GA_ST_TABLE_FULL);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1c. lane per read, no stage: the staged kernels spend half their time in the flush (ncu, profiles/r01:
+// three barriers, one returned global atomic per level-1 bucket and flush whether the bucket got one record or
+// none -- a 2048-record stage over 1024 buckets holds 1-2 records per bucket -- and a copy whose scattered
+// 16 + 8 byte stores are no better coalesced than direct ones).  Here a record takes its place in its level-1
+// bucket with ONE returned global atomic and is written straight from registers; a thread keeps BATCH atomics
+// in flight before it builds the records.  No shared-memory stage, no barrier: every thread is on its own, and
+// the CTA's shared memory is just the per-thread bucket columns, so occupancy is set by registers.
+template <int THREADS, int BATCH>
+__global__ void __launch_bounds__(THREADS)
+sk_scatter_reads_direct_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
+                               u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
+    __shared__ u32 bk[32][THREADS];                      // bucket of this thread's i-th record of the current chunk
+    const u32 tid = threadIdx.x;
+    const int bits = l1_bits + l2_bits;
+    const u32 l2_mask = (1u << l2_bits) - 1u;
+    const u32 mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    bool overflow = false;
+    for (u64 r = (u64)blockIdx.x * THREADS + tid; r < rv.n_reads; r += (u64)gridDim.x * THREADS) {
+        // paired input: both mates are plain reads here (counting only); windows run over mate 1's length
+        const u32 len = ga_read_len(rv, rv.paired ? (r & ~1ull) : r);
+        const u32 nwt = len >= (u32)w ? len - (u32)w + 1u : 0u;     // windows of this read
+        const u32 nch = (nwt + 31u) / 32u;
+        const u64* rp = ga_read_ptr(rv, r);
+        const u32 n_words = nwt ? (len + 31u) / 32u : 0u;
+        const u64 e_read = (rv.first_read + r) * (u64)rv.estride;
+        // words c, c+1, c+2 of the read while chunk c (windows 32c .. 32c+31) is walked
+        u64 w0 = 0, w1 = n_words > 0u ? __ldg(rp) : 0ull, w2 = n_words > 1u ? __ldg(rp + 1) : 0ull;
+        for (u32 c = 0; c < nch; ++c) {
+            w0 = w1;
+            w1 = w2;
+            w2 = c + 2u < n_words ? __ldg(rp + c + 2u) : 0ull;
+            const u32 nv = min(nwt - c * 32u, 32u);
+            u32 mask = 0;
+            {
+                const u32 R[4] = {(u32)w0, (u32)(w0 >> 32), (u32)w1, (u32)(w1 >> 32)};
+                auto mm = [&](int j) -> u32 {
+                    return sk_mmer_hash(__funnelshift_r(R[j >> 4], R[(j >> 4) + 1], 2u * ((u32)j & 15u)) & mmask);
+                };
+                u32 prev = 0;
+                u32* col = &bk[0][tid];
+                auto window = [&](int j, u32 min_hash) {
+                    const u32 bkt = sk_bucket_of(min_hash, bits);
+                    if (j == 0 || bkt != prev) {
+                        *col = bkt;
+                        col += THREADS;
+                        mask |= 1u << j;
+                    }
+                    prev = bkt;
+                };
+                u32 S[16], T[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) S[o] = mm(o);
+#pragma unroll
+                for (int o = 14; o >= 0; --o) S[o] = min(S[o], S[o + 1]);
+                u32 P = 0xFFFFFFFFu;
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    window(o, o ? min(S[o], P) : S[0]);
+                    T[o] = mm(16 + o);
+                    P = min(P, T[o]);
+                }
+#pragma unroll
+                for (int o = 14; o >= 0; --o) T[o] = min(T[o], T[o + 1]);
+                P = 0xFFFFFFFFu;
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    window(16 + o, o ? min(T[o], P) : T[0]);
+                    if (o < 15) P = min(P, mm(32 + o));
+                }
+                mask &= nv >= 32u ? FULL : (1u << nv) - 1u;
+            }
+            const u32 cur = (u32)__popc(mask);
+            u32 rest = mask;
+            for (u32 done = 0; done < cur; done += BATCH) {
+                u64 pos[BATCH];
+                u32 what[BATCH];                          // start window | windows << 8 | bucket << 12 (bucket: 20 bits)
+#pragma unroll
+                for (int q = 0; q < BATCH; ++q) {
+                    pos[q] = 0;
+                    what[q] = 0;
+                    if (done + q < cur) {
+                        const u32 j = (u32)__ffs(rest) - 1u;
+                        rest &= rest - 1u;
+                        const u32 nwin = (rest ? (u32)__ffs(rest) - 1u : nv) - j;
+                        const u32 b = bk[done + q][tid];
+                        what[q] = j | ((nwin - 1u) << 5) | (b << 12);
+                        pos[q] = atomicAdd((unsigned long long*)&cursors[(b >> l2_bits) * SK_CURSOR_STRIDE], 1ull);
+                        atomicAdd((unsigned long long*)&ghist[b], (1ull << 32) | (unsigned long long)nwin);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < BATCH; ++q) {
+                    if (done + q < cur) {
+                        const u32 j = what[q] & 31u, nwin = ((what[q] >> 5) & 31u) + 1u, b = what[q] >> 12;
+                        const u32 p = c * 32u + j, sh = 2u * j;
+                        const u64 hi = sk_rev2(sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0);
+                        const u64 lo = sk_rev2(sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1);
+                        const u32 has_next = p + nwin - 1u + (u32)w < len ? 1u : 0u;
+                        if (pos[q] < cap1) {
+                            sk_store_slot(out_rec, (u64)(b >> l2_bits) * cap1 + pos[q], hi, lo,
+                                          ((e_read + p) << 16) | ((u64)(b & l2_mask) << 6) | ((u64)has_next << 5) |
+                                              (u64)(nwin - 1u));
+                        } else {
+                            overflow = true;              // dropped: the host retries with larger buckets
+                        }
+                    }
+                }
+            }
+        }
+    }
     if (overflow) atomicOr(status, GA_ST_TABLE_FULL);
 }
 
@@ -377,7 +665,7 @@ constexpr u32 S2_CHUNK = S2_THREADS * S2_PER;
 // the traffic; the dense form is what the multi-GPU exchange needs.
 template <bool INDEX>
 __global__ void __launch_bounds__(S2_THREADS)
-sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __restrict__ in_meta, u64 cap1,
+sk_scatter_buckets_kernel(const u64* __restrict__ in_rec, u64 cap1,
                           const u64* __restrict__ cursors1, u32 n_l1, int l2_bits, u64* __restrict__ cursors2,
                           ulonglong2* __restrict__ out_bases, u64* __restrict__ out_meta, u32* __restrict__ out_index) {
     __shared__ u32 hist[1024];
@@ -388,7 +676,7 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
     for (u64 chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
         const u32 b1 = (u32)(chunk / chunks_per);
         const u64 lo = (chunk % chunks_per) * S2_CHUNK;
-        const u64 cnt1 = min(cursors1[b1], cap1);
+        const u64 cnt1 = min(cursors1[b1 * SK_CURSOR_STRIDE], cap1);
         if (lo >= cnt1) continue;                           // CTA-uniform
         for (u32 p = threadIdx.x; p < n_l2; p += S2_THREADS) hist[p] = 0;
         __syncthreads();
@@ -400,8 +688,8 @@ sk_scatter_buckets_kernel(const ulonglong2* __restrict__ in_bases, const u64* __
             const u64 i = lo + (u64)u * S2_THREADS + threadIdx.x;
             if (i < cnt1) {
                 const u64 src = (u64)b1 * cap1 + i;
-                if (!INDEX) bs[u] = in_bases[src];
-                mt[u] = in_meta[src];
+                if (INDEX) mt[u] = __ldg(in_rec + 4u * src + 2u);       // the meta word of the slot
+                else sk_load_slot(in_rec, src, bs[u], mt[u]);
                 rank[u] = atomicAdd(&hist[meta_b2(mt[u])], 1u);
             }
         }
@@ -678,9 +966,10 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u64 seg_pre[SB_MAX_SEG + 1];
 };
 
-// where a bucket's records are: index == nullptr: at the positions the offsets give (dense form);
-// otherwise offsets address `index`, and record = base + index[position] (base = first record of the
-// bucket's level-1 bucket)
+// where a bucket's records are: index == nullptr: at the positions the offsets give, bases and meta in two
+// dense arrays (dense form); otherwise offsets address `index`, `bases` points at the level-1 buckets'
+// 32-byte slots and the record is slot base + index[position] (base = first slot of the bucket's level-1
+// bucket; `meta` is not used)
 struct SkGather {
     const u32* index;
     u64 base;
@@ -812,9 +1101,13 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         b = make_ulonglong2(0, 0);
         mt = 0;
         if (have) {
-            const u64 i = gather.index ? gather.base + ent : where(idx);
-            b = bases[i];
-            mt = meta[i];
+            if (gather.index) {
+                sk_load_slot((const u64*)bases, gather.base + ent, b, mt);     // a 32-byte slot of the level-1 bucket
+            } else {
+                const u64 i = where(idx);
+                b = bases[i];
+                mt = meta[i];
+            }
         }
         ent = ent_next;
         sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
@@ -872,8 +1165,12 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         u64 mt = 0;
         if (have) {
             const u64 i = locate(bt * 32u + __fns(fmask, 0, lane + 1));
-            b = bases[i];
-            mt = meta[i];
+            if (gather.index) {
+                sk_load_slot((const u64*)bases, i, b, mt);
+            } else {
+                b = bases[i];
+                mt = meta[i];
+            }
         }
         sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32) {
             if (!follows) return;
@@ -1090,12 +1387,14 @@ extern "C" int ga_sk_minimizer_len(int k) {
     return m;
 }
 
-extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* rec_bases_dev,
-                                   uint64_t* rec_meta_dev, uint64_t l1_capacity, uint64_t* l1_cursors_dev,
-                                   uint64_t* hist_dev, uint32_t* status_dev, ga_stream stream) {
-    if (!reads || !rec_bases_dev || !rec_meta_dev || !l1_cursors_dev || !hist_dev || !status_dev || l1_capacity == 0 ||
-        l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10) {
-        ga_set_error("ga_sk_scatter_reads: bad arguments (bucket bits must be 0..10 each)");
+extern "C" int ga_sk_cursor_stride(void) { return (int)SK_CURSOR_STRIDE; }
+
+extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* records_dev,
+                                   uint64_t l1_capacity, uint64_t* l1_cursors_dev, uint64_t* hist_dev,
+                                   uint32_t* status_dev, ga_stream stream) {
+    if (!reads || !records_dev || !l1_cursors_dev || !hist_dev || !status_dev || l1_capacity == 0 ||
+        l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10 || ((uintptr_t)records_dev & 31u)) {
+        ga_set_error("ga_sk_scatter_reads: bad arguments (bucket bits must be 0..10 each, records 32-byte aligned)");
         return GA_ERR_BAD_ARG;
     }
     const int w = k - 1;
@@ -1109,24 +1408,60 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     }
     if (reads->n_reads == 0) return GA_OK;
     ReadsView rv = ga_view(reads);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(S1Shared)));
-        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(S1Shared)));
-        attr_set = true;
-    }
-    const u64 n_tiles = (rv.n_reads + S1_WARPS - 1) / S1_WARPS;
-    const unsigned grid = (unsigned)(n_tiles < 148ull * 2 ? n_tiles : 148ull * 2);
     const int m = ga_sk_minimizer_len(k);
-#define GA_SK_SCATTER(NMM)                                                                                          \
-    sk_scatter_reads_kernel<NMM><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(                      \
-        rv, w, m, l1_bits, l2_bits, (ulonglong2*)rec_bases_dev, (u64*)rec_meta_dev, l1_capacity, (u64*)l1_cursors_dev, \
-        (u64*)hist_dev, status_dev)
-    if (w - m + 1 == 16) GA_SK_SCATTER(16);
-    else GA_SK_SCATTER(0);
-#undef GA_SK_SCATTER
+    // which kernel: windows of 16 m-mers take the lane-per-read kernel; GA_SK_SCATTER=warp|lane|lane128 picks one by
+    // hand (A/B runs and the test that compares their records)
+    const int variant = [] {
+        const char* e = getenv("GA_SK_SCATTER");
+        return !e ? 1 : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : (!strcmp(e, "direct") ? 3 : (!strcmp(e, "direct256") ? 4 : 1))));
+    }();
+#define GA_SK_ARGS                                                                                                   \
+    rv, w, m, l1_bits, l2_bits, (u64*)records_dev, l1_capacity, (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev
+#define GA_SK_LANE(T, STAGE, SUB, PER_SM)                                                                            \
+    do {                                                                                                             \
+        static bool attr_set = false;                                                                                \
+        const int bytes = (int)sizeof(S1LShared<T, STAGE, SUB>);                                                     \
+        if (!attr_set) {                                                                                             \
+            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_lane_kernel<T, STAGE, SUB>,                                \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));                       \
+            attr_set = true;                                                                                         \
+        }                                                                                                            \
+        const u64 n_tiles = (rv.n_reads + T - 1) / T;                                                                \
+        const unsigned grid = (unsigned)(n_tiles < 148ull * PER_SM ? n_tiles : 148ull * PER_SM);                     \
+        sk_scatter_reads_lane_kernel<T, STAGE, SUB><<<grid, T, bytes, (cudaStream_t)stream>>>(GA_SK_ARGS);           \
+    } while (0)
+    if (w - m + 1 == 16 && variant == 1) {
+        GA_SK_LANE(256, 2048, 8, 2);
+    } else if (w - m + 1 == 16 && variant == 2) {
+        GA_SK_LANE(128, 1536, 12, 3);
+    } else if (w - m + 1 == 16 && (variant == 3 || variant == 4)) {
+        // persistent grid: as many CTAs as fit (registers and the bucket columns in shared memory decide)
+        static int per_sm[2] = {0, 0};
+        if (!per_sm[0]) {
+            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sk_scatter_reads_direct_kernel<128, 4>, 128, 0));
+            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sk_scatter_reads_direct_kernel<256, 4>, 256, 0));
+        }
+        const unsigned threads = variant == 3 ? 128 : 256;
+        const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = 148ull * (u64)per_sm[variant == 3 ? 0 : 1];
+        const unsigned grid = (unsigned)(n_ctas < most ? n_ctas : most);
+        if (variant == 3) sk_scatter_reads_direct_kernel<128, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
+        else sk_scatter_reads_direct_kernel<256, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
+    } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(S1Shared)));
+            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(S1Shared)));
+            attr_set = true;
+        }
+        const u64 n_tiles = (rv.n_reads + S1_WARPS - 1) / S1_WARPS;
+        const unsigned grid = (unsigned)(n_tiles < 148ull * 2 ? n_tiles : 148ull * 2);
+        if (w - m + 1 == 16) sk_scatter_reads_kernel<16><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
+        else sk_scatter_reads_kernel<0><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
+    }
+#undef GA_SK_LANE
+#undef GA_SK_ARGS
     GA_LAUNCH_CHECK("sk_scatter_reads");
     return GA_OK;
 }
@@ -1151,13 +1486,12 @@ extern "C" int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint6
     return GA_OK;
 }
 
-extern "C" int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
-                                     const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
-                                     void* out_bases_dev, uint64_t* out_meta_dev, uint32_t* out_index_dev,
-                                     ga_stream stream) {
+extern "C" int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capacity, const uint64_t* l1_cursors_dev,
+                                     int l1_bits, int l2_bits, uint64_t* cursors_dev, void* out_bases_dev,
+                                     uint64_t* out_meta_dev, uint32_t* out_index_dev, ga_stream stream) {
     const bool dense = out_bases_dev && out_meta_dev && !out_index_dev;
     const bool index = out_index_dev && !out_bases_dev && !out_meta_dev;
-    if (!rec_bases_dev || !rec_meta_dev || !l1_cursors_dev || !cursors_dev || (!dense && !index) ||
+    if (!records_dev || !l1_cursors_dev || !cursors_dev || (!dense && !index) || ((uintptr_t)records_dev & 31u) ||
         l1_capacity == 0 || l1_capacity > 0xFFFFFFFFull || l1_bits < 0 || l1_bits > 10 || l2_bits < 0 || l2_bits > 10) {
         ga_set_error("ga_sk_scatter_buckets: bad arguments");
         return GA_ERR_BAD_ARG;
@@ -1167,12 +1501,12 @@ extern "C" int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* 
     const unsigned grid = (unsigned)(total < 148ull * 8 ? total : 148ull * 8);
     if (index)
         sk_scatter_buckets_kernel<true><<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
-            (const ulonglong2*)rec_bases_dev, (const u64*)rec_meta_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1,
-            l2_bits, (u64*)cursors_dev, nullptr, nullptr, out_index_dev);
+            (const u64*)records_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1, l2_bits, (u64*)cursors_dev, nullptr,
+            nullptr, out_index_dev);
     else
         sk_scatter_buckets_kernel<false><<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
-            (const ulonglong2*)rec_bases_dev, (const u64*)rec_meta_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1,
-            l2_bits, (u64*)cursors_dev, (ulonglong2*)out_bases_dev, (u64*)out_meta_dev, nullptr);
+            (const u64*)records_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1, l2_bits, (u64*)cursors_dev,
+            (ulonglong2*)out_bases_dev, (u64*)out_meta_dev, nullptr);
     GA_LAUNCH_CHECK("sk_scatter_buckets");
     return GA_OK;
 }
@@ -1185,8 +1519,8 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
                                  uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
                                  const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || !meta_dev || !offsets_dev || !hist_dev || !solid_keys_out_dev ||
-        !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
+    if (!bases_dev || (!meta_dev && !index_dev) || (index_dev && ((uintptr_t)bases_dev & 31u)) || !offsets_dev ||
+        !hist_dev || !solid_keys_out_dev || !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
         threshold > 60000 || !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS ||
         max_solid == 0 || n_segments == 0 || n_segments > SB_MAX_SEG) {
         ga_set_error("ga_sk_count_build: bad arguments (0 <= threshold <= 60000, table_slots a power of two in "
@@ -1229,7 +1563,7 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
                                        const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits,
                                        ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || !meta_dev || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
+    if (!bases_dev || (!meta_dev && !index_dev) || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
         !counters_dev || !status_dev || w < 1 || w > 31 || threshold < 0 ||
         !is_pow2(table_slots) || table_slots < 256 || n_ctas == 0 || n_segments == 0 || n_segments > SB_MAX_SEG ||
         n_buckets == 0) {

@@ -581,9 +581,9 @@ def sk_geometry(n_occ: int):
 def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None, dense: bool = True):
     """This rank's reads -> records sorted by bucket.  dense: (bases int64[2*total], meta int64[total],
     offsets int64[n_buckets+1], hist int64[n_buckets] = records << 32 | windows, total) -- the records
-    themselves in bucket order, what the multi-GPU exchange sends.  Not dense: (level-1 bases, level-1 meta,
-    offsets, hist, total, index int32[total], l1_capacity) -- the records stay in their level-1 buckets and
-    only a 32-bit index per record is sorted (a quarter of the traffic).
+    themselves in bucket order, what the multi-GPU exchange sends.  Not dense: (level-1 slots int64[4 * n_l1 *
+    l1_capacity], None, offsets, hist, total, index int32[total], l1_capacity) -- the records stay in the 32-byte
+    slots of their level-1 buckets and only a 32-bit index per record is sorted.
     ga_sk_scatter_reads + ga_sk_offsets + ga_sk_scatter_buckets."""
     L = gn.lib()
     dev = _dev()
@@ -594,17 +594,17 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
     status = reads.status
     est = int(n_occ * 2.0 / (per_window + 1)) + _record_groups(reads, w)
     cap1 = int(est / n_l1 * 1.08) + 4096
+    cstride = L.ga_sk_cursor_stride()
     while True:
-        rec_bases = workspace("sk_l1_bases", n_l1 * cap1 * 2, torch.int64)
-        rec_meta = workspace("sk_l1_meta", n_l1 * cap1, torch.int64)
-        cursors1 = torch.zeros(n_l1, dtype=torch.int64, device=dev)
+        rec = workspace("sk_l1_records", n_l1 * cap1 * 4, torch.int64)        # 32-byte slots: bases hi, lo, meta, 0
+        cursors1 = torch.zeros(n_l1 * cstride, dtype=torch.int64, device=dev)
         hist = torch.zeros(n_buckets, dtype=torch.int64, device=dev)
         status.zero_()
         with _timed("sk_scatter1", n_occ):
             for r0, r1 in (feed if feed is not None else ((0, reads.n_reads),)):
                 gn.check(L.ga_sk_scatter_reads(C.byref(reads.struct_range(r0, r1)), k, l1_bits, l2_bits,
-                                               gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1),
-                                               gn.ptr(hist), gn.ptr(status), _stream()))
+                                               gn.ptr(rec), cap1, gn.ptr(cursors1), gn.ptr(hist), gn.ptr(status),
+                                               _stream()))
             feed = None                     # a retry finds every read resident
         offsets = torch.empty(n_buckets + 1, dtype=torch.int64, device=dev)
         cursors2 = torch.empty(n_buckets, dtype=torch.int64, device=dev)
@@ -621,15 +621,15 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
     if not dense:
         index = workspace("sk_index", max(total, 1), torch.int32)
         with _timed("sk_scatter2", n_occ):
-            gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits,
-                                             l2_bits, gn.ptr(cursors2), None, None, gn.ptr(index), _stream()))
+            gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec), cap1, gn.ptr(cursors1), l1_bits, l2_bits, gn.ptr(cursors2),
+                                             None, None, gn.ptr(index), _stream()))
         _mark("sk scatter buckets")
-        return rec_bases, rec_meta, offsets, hist, total, index, cap1
+        return rec, None, offsets, hist, total, index, cap1
     bases = workspace("sk_bases", max(total, 1) * 2, torch.int64)
     meta = workspace("sk_meta", max(total, 1), torch.int64)
     with _timed("sk_scatter2", n_occ):
-        gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec_bases), gn.ptr(rec_meta), cap1, gn.ptr(cursors1), l1_bits, l2_bits,
-                                         gn.ptr(cursors2), gn.ptr(bases), gn.ptr(meta), None, _stream()))
+        gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec), cap1, gn.ptr(cursors1), l1_bits, l2_bits, gn.ptr(cursors2),
+                                         gn.ptr(bases), gn.ptr(meta), None, _stream()))
     _mark("sk scatter buckets")
     return bases, meta, offsets, hist, total
 

@@ -69,9 +69,10 @@ SIGNATURES = {
     "ga_prefilter_hot": (_i32, [_PF, _i64, _vp, _vp]),
     "ga_count_candidates": (_i32, [_PR, _i32, _PF, _i64, _vp, _u64, _vp, _vp]),
     "ga_sk_minimizer_len": (_i32, [_i32]),
-    "ga_sk_scatter_reads": (_i32, [_PR, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "ga_sk_cursor_stride": (_i32, []),
+    "ga_sk_scatter_reads": (_i32, [_PR, _i32, _i32, _i32, _vp, _u64, _vp, _vp, _vp, _vp]),
     "ga_sk_offsets": (_i32, [_vp, _u64, _vp, _vp, _vp]),
-    "ga_sk_scatter_buckets": (_i32, [_vp, _vp, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ga_sk_scatter_buckets": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ga_sk_count_build": (_i32, [_vp, _vp, _vp, _u32, _vp, _u64, _i32, _i64, _u32, _u32, _vp, _vp, _u64, _vp, _vp, _u64, _vp,
                                  _vp, _u64, _i32, _vp]),
     "ga_sk_spill_scratch_bytes": (_u64, [_u32]),

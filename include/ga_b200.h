@@ -167,14 +167,19 @@ int ga_count_candidates(const ga_reads* reads, int k, const ga_prefilter* pf, in
 int ga_sk_minimizer_len(int k);
 /* Paired input (reads->paired) is taken as 2*pairs plain reads whose windows run over mate 1's length
  * (debruijn_graph.py:349-374): enough for counting, i.e. for ga_sk_count_build without edge stamps.
- * Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases in
- * rec_bases_dev + one meta word in rec_meta_dev) and scatter them to 2^l1_bits level-1 buckets of
- * l1_capacity records each (bucket b at index b*l1_capacity; l1_cursors_dev[b] = records written,
- * zeroed by the caller).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) accumulates, per final
- * bucket, records << 32 | windows.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed, retry with a larger capacity. */
-int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* rec_bases_dev,
-                        uint64_t* rec_meta_dev, uint64_t l1_capacity, uint64_t* l1_cursors_dev,
-                        uint64_t* hist_dev, uint32_t* status_dev, ga_stream stream);
+ * Cut every read into records (runs of consecutive windows that share a bucket: 16 bytes of bases + one
+ * meta word) and scatter them to 2^l1_bits level-1 buckets of l1_capacity 32-byte slots each in records_dev
+ * (slot = {bases hi, bases lo, meta, 0}, one full-sector store per record; bucket b starts at slot
+ * b*l1_capacity; records_dev 32-byte aligned).  l1_cursors_dev[b * ga_sk_cursor_stride()] = records written
+ * to bucket b (2^l1_bits * stride words, zeroed by the caller; the cursors sit 128 bytes apart so that their
+ * atomics spread over the L2 slices).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) accumulates, per
+ * final bucket, records << 32 | windows.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed (its cursor kept
+ * counting), retry with a larger capacity.  GA_SK_SCATTER=warp|lane|lane128|direct in the environment picks
+ * the kernel by hand (same records from each; tests and A/B runs). */
+int ga_sk_cursor_stride(void);
+int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* records_dev,
+                        uint64_t l1_capacity, uint64_t* l1_cursors_dev, uint64_t* hist_dev,
+                        uint32_t* status_dev, ga_stream stream);
 /* offsets_dev[n_buckets+1] = exclusive prefix sum of the record counts; cursors_dev[n_buckets] = a copy */
 int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offsets_dev,
                   uint64_t* cursors_dev, ga_stream stream);
@@ -184,16 +189,15 @@ int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint64_t* offset
  *  index (out_index_dev, the other two NULL): per record only its 32-bit position inside its level-1
  *    bucket; ga_sk_count_build then gathers the records from the level-1 buckets (a quarter of the
  *    traffic on one GPU, where a level-1 bucket stays L2 resident while its final buckets are done). */
-int ga_sk_scatter_buckets(const void* rec_bases_dev, const uint64_t* rec_meta_dev, uint64_t l1_capacity,
-                          const uint64_t* l1_cursors_dev, int l1_bits, int l2_bits, uint64_t* cursors_dev,
-                          void* out_bases_dev, uint64_t* out_meta_dev, uint32_t* out_index_dev,
-                          ga_stream stream);
+int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capacity, const uint64_t* l1_cursors_dev,
+                          int l1_bits, int l2_bits, uint64_t* cursors_dev, void* out_bases_dev,
+                          uint64_t* out_meta_dev, uint32_t* out_index_dev, ga_stream stream);
 /* offsets_dev holds n_segments rows of n_buckets+1 positions: the records of bucket b are the union of
  * [offsets[s][b], offsets[s][b+1]) over the segments s (one segment on a single GPU; after the
  * multi-GPU exchange, one per source rank, each sorted by bucket).  hist_dev[b] & 0xFFFFFFFF = windows
- * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev /
- * meta_dev are then the level-1 bucket arrays of ga_sk_scatter_reads, offsets address index_dev, and the
- * record of entry e of bucket b sits at (b >> l2_bits) * l1_capacity + index_dev[e].
+ * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev is
+ * then records_dev of ga_sk_scatter_reads (32-byte slots; meta_dev is not used and may be NULL), offsets
+ * address index_dev, and the record of entry e of bucket b is slot (b >> l2_bits) * l1_capacity + index_dev[e].
  * One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
  * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge

@@ -315,6 +315,46 @@ def test_bucket_segments_match_whole(monkeypatch):
     assert torch.equal(st1[o1], st2[o2])
 
 
+@pytest.mark.parametrize("k", [27, 31, 32])
+def test_scatter_kernels_cut_identical_records(k, monkeypatch):
+    """The lane-per-read scatter kernel (both shapes) and the warp-per-read one cut the same reads into the
+    same records in the same buckets (ga_sk_scatter_reads, GA_SK_SCATTER picks the kernel): uniform reads and
+    ragged ones -- shorter than a window, exactly 32 / 33 / 64 / 65 windows, several chunks."""
+    import random
+    import torch
+    import ga_device as gd
+    monkeypatch.setattr(gd, "SUPERKMER_TARGET", 300)
+    rng = random.Random(k)
+    w = k - 1
+    genome = "".join(rng.choice("ACGT") for _ in range(30000))
+    lengths = [w - 1, w, w + 1, w + 30, w + 31, w + 32, w + 63, w + 64, w + 95, w + 96, 5, 1, 400, 1000]
+    ragged = []
+    for i in range(4000):
+        n = lengths[i % len(lengths)] if i % 3 else rng.randrange(1, 330)
+        at = rng.randrange(len(genome) - n)
+        ragged.append(genome[at:at + n] if i % 50 else "A" * n)          # some reads of one repeated symbol
+    uniform = [genome[at:at + 150] for at in (rng.randrange(len(genome) - 150) for _ in range(5000))]
+    for reads in (uniform, ragged):
+        dr = gd.DeviceReads(reads, False)
+        l1_bits, l2_bits = gd.sk_geometry(dr.windows_total(k))
+        assert l1_bits > 0 and l2_bits > 0
+        got = {}
+        for variant in ("warp", "lane", "lane128", "direct", "direct256"):
+            monkeypatch.setenv("GA_SK_SCATTER", variant)
+            bases, meta, offsets, hist, total = gd.sk_scatter_local(dr, k, l1_bits, l2_bits, dense=True)
+            meta = meta[:total].clone()
+            bases = bases[:2 * total].clone().view(-1, 2)
+            counts = offsets[1:] - offsets[:-1]
+            bucket = torch.repeat_interleave(torch.arange(counts.numel(), device=meta.device), counts)
+            order = torch.argsort(meta)
+            got[variant] = (meta[order], bases[order], bucket[order], hist.clone(), total)
+        assert got["warp"][4] > len(reads) // 2
+        for variant in ("lane", "lane128", "direct", "direct256"):
+            assert got[variant][4] == got["warp"][4], variant
+            for a, b in zip(got[variant][:4], got["warp"][:4]):
+                assert torch.equal(a, b), variant
+
+
 def test_host_buffer_entries_match_device_path(monkeypatch):
     """host_step (ASCII in pinned memory, streamed in by chunks) and host_step_packed (2-bit words in
     pinned memory) give the CSR of the device-resident path, chunk boundaries included."""

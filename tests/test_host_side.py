@@ -146,19 +146,20 @@ def test_bucketed_entries_reject_bad_arguments():
     reads = gn.GaReads()
     reads.n_reads, reads.uniform_len, reads.stride_words, reads.estride = 4, 100, 4, 100
     reads.storage_bits = reads.sym_bits = 2
-    dummy = C.create_string_buffer(64)
-    ptr = C.cast(dummy, C.c_void_p)
+    dummy = C.create_string_buffer(128)
+    ptr = C.c_void_p((C.addressof(dummy) + 31) & ~31)          # the record slots are 32-byte aligned
+    assert L.ga_sk_cursor_stride() == 16
     # bucket bits out of range, k beyond 64-bit keys
-    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 11, 10, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 11, 10, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     assert b"bucket bits" in L.ga_last_error()
-    assert L.ga_sk_scatter_reads(C.byref(reads), 40, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_reads(C.byref(reads), 40, 2, 2, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     # ordinals beyond 47 bits
     reads.first_read = 1 << 46
-    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 2, 2, ptr, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_reads(C.byref(reads), 31, 2, 2, ptr, 16, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     assert b"47 bits" in L.ga_last_error()
     # level-2 pass: exactly one of the dense / index outputs
-    assert L.ga_sk_scatter_buckets(ptr, ptr, 16, ptr, 2, 2, ptr, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
-    assert L.ga_sk_scatter_buckets(ptr, ptr, 16, ptr, 2, 2, ptr, None, None, None, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_buckets(ptr, 16, ptr, 2, 2, ptr, ptr, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_scatter_buckets(ptr, 16, ptr, 2, 2, ptr, None, None, None, None) == gn.GA_ERR_BAD_ARG
     # bucket pass: table size must be a power of two within the shared-memory pool, threshold within the counter
     args = (ptr, ptr, ptr, 1, ptr, 4, 31, 3)
     tail = (ptr, ptr, 16, ptr, ptr, 16, ptr, None, 0, 0, None)
