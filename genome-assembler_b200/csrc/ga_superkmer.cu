@@ -96,7 +96,7 @@ __device__ __forceinline__ u32 sk_bucket_of(u32 min_hash, int bits) {
 }
 
 // stage -> level-1 buckets: one global cursor bump per non-empty bucket, then the records of a bucket land
-// next to each other.  SM: S1Shared or S1LShared; THREADS: the CTA's size.
+// next to each other.
 template <class SM, int THREADS>
 __device__ __forceinline__ void s1_flush(SM& sm, u32 n, u32 n_l1, u64* __restrict__ out_rec, u64 cap1,
                                          u64* __restrict__ cursors, bool& overflow) {
@@ -294,175 +294,22 @@ sk_scatter_reads_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u6
 // 1b. the same cut, one LANE per read (windows of 16 m-mers: 26 <= k-1 <= 31, every real configuration).
 // The warp-per-read kernel above pays ~610 warp instructions per 150-base read, most of them shuffles and
 // ballots of the cooperative sliding minimum and of the record search, at 24 of 32 lanes.  Here a thread walks
-// its own read 32 windows at a time with everything in registers:
+// its own read 32 windows at a time with everything in registers (~200 warp instructions per read):
 //   * the chunk's 47 m-mer hashes are taken from three 64-bit words with funnel shifts; the sliding minimum
 //     over 16 m-mers is a suffix minimum of one aligned block of 16 combined with a running prefix minimum of
 //     the next block (3 min per window, no shuffles, no branches);
 //   * a window starts a record when its bucket differs from its predecessor's (or at a multiple of 32 windows):
 //     the start mask stays in a register, the bucket of the i-th record goes to a per-thread column in shared
 //     memory (predicated store);
-//   * the records are then built by their own thread (divergent, but short) into the CTA's stage, at most SUB
-//     per thread and sub-round so that a sub-round always fits the stage; one barrier per sub-round.
-// Buckets, record cuts and record contents are bit-identical to the kernel above (tests compare the two).
-template <int THREADS, int STAGE, int SUB>
-struct S1LShared {
-    ulonglong2 bases[STAGE];
-    u64 meta[STAGE];
-    u32 br[STAGE];                 // level-1 bucket << 16 | rank inside this flush
-    u64 gbase[S1_MAXB];
-    u32 hist[S1_MAXB];
-    u32 bk[32][THREADS];           // bucket of a thread's i-th record of the current chunk
-    u32 round[3];                  // records of a sub-round | records still to come << 16; three slots in rotation
-};
-
-template <int THREADS, int STAGE, int SUB>
-__global__ void __launch_bounds__(THREADS, 2)
-sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
-                             u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
-    static_assert(THREADS * SUB <= STAGE, "a sub-round must fit the stage");
-    using Shared = S1LShared<THREADS, STAGE, SUB>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31u;
-    const u32 n_l1 = 1u << l1_bits;
-    const int bits = l1_bits + l2_bits;
-    const u32 l2_mask = (1u << l2_bits) - 1u;
-    const u32 mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
-    bool overflow = false;
-    u32 staged = 0;                                       // records in the stage; identical in every thread
-    u32 slot = 0;                                         // sub-round counter slot; identical in every thread
-    for (u32 p = tid; p < n_l1; p += THREADS) sm.hist[p] = 0;
-    if (tid < 3u) sm.round[tid] = 0;
-    __syncthreads();
-
-    const u64 n_tiles = (rv.n_reads + THREADS - 1) / THREADS;
-    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const u64 r = tile * THREADS + tid;
-        const bool valid = r < rv.n_reads;
-        // paired input: both mates are plain reads here (counting only); windows run over mate 1's length
-        const u32 len = valid ? ga_read_len(rv, rv.paired ? (r & ~1ull) : r) : 0u;
-        const u32 nwt = len >= (u32)w ? len - (u32)w + 1u : 0u;     // windows of this read
-        const u32 nch = (nwt + 31u) / 32u;
-        const u64* rp = valid ? ga_read_ptr(rv, r) : rv.words;
-        const u32 n_words = nwt ? (len + 31u) / 32u : 0u;
-        const u64 e_read = (rv.first_read + r) * (u64)rv.estride;
-        // words c, c+1, c+2 of the read while chunk c (windows 32c .. 32c+31) is walked
-        u64 w0 = 0, w1 = n_words > 0u ? __ldg(rp) : 0ull, w2 = n_words > 1u ? __ldg(rp + 1) : 0ull;
-        for (u32 c = 0;; ++c) {
-            const bool more = c < nch;
-            if (!__syncthreads_or(more)) break;
-            w0 = w1;
-            w1 = w2;
-            w2 = c + 2u < n_words ? __ldg(rp + c + 2u) : 0ull;
-            u32 mask = 0, cur = 0, nv = 0;                // record starts, records, windows of this chunk
-            if (more) {
-                nv = min(nwt - c * 32u, 32u);
-                const u32 vmask = nv >= 32u ? FULL : (1u << nv) - 1u;
-                const u32 R[4] = {(u32)w0, (u32)(w0 >> 32), (u32)w1, (u32)(w1 >> 32)};
-                // hash of the m-mer at symbol 32c + j, j = 0..46 (past the read's end: anything, such windows are masked)
-                auto mm = [&](int j) -> u32 {
-                    return sk_mmer_hash(__funnelshift_r(R[j >> 4], R[(j >> 4) + 1], 2u * ((u32)j & 15u)) & mmask);
-                };
-                // a window past the read's end may "start a record" too: its column entry lands behind the real
-                // ones and its mask bit is dropped below
-                u32 prev = 0;
-                u32* col = &sm.bk[0][tid];
-                auto window = [&](int j, u32 min_hash) {
-                    const u32 bkt = sk_bucket_of(min_hash, bits);
-                    if (j == 0 || bkt != prev) {
-                        *col = bkt;
-                        col += THREADS;
-                        mask |= 1u << j;
-                    }
-                    prev = bkt;
-                };
-                u32 S[16], T[16];
-#pragma unroll
-                for (int o = 0; o < 16; ++o) S[o] = mm(o);
-#pragma unroll
-                for (int o = 14; o >= 0; --o) S[o] = min(S[o], S[o + 1]);       // S[o] = min of m-mers o..15
-                u32 P = 0xFFFFFFFFu;                                             // min of the next block's m-mers so far
-#pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    window(o, o ? min(S[o], P) : S[0]);                          // m-mers o..15 and 16..15+o
-                    T[o] = mm(16 + o);
-                    P = min(P, T[o]);
-                }
-#pragma unroll
-                for (int o = 14; o >= 0; --o) T[o] = min(T[o], T[o + 1]);
-                P = 0xFFFFFFFFu;
-#pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    window(16 + o, o ? min(T[o], P) : T[0]);
-                    if (o < 15) P = min(P, mm(32 + o));
-                }
-                mask &= vmask;
-                cur = (u32)__popc(mask);
-            }
-            // records: at most SUB per thread and sub-round
-            u32 rest = mask, done = 0;
-            for (;;) {
-                const u32 cnt = min(cur - done, (u32)SUB);
-                const u32 mine = cnt | ((cur - done - cnt) << 16);          // this sub-round | later ones
-                u32 incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const u32 t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= (u32)o) incl += t;
-                }
-                const u32 wsum = __shfl_sync(FULL, incl, 31);
-                u32 wbase = 0;
-                if (lane == 31u && wsum) wbase = atomicAdd(&sm.round[slot], wsum);
-                wbase = __shfl_sync(FULL, wbase, 31) & 0xFFFFu;
-                __syncthreads();
-                const u32 all = sm.round[slot];
-                // the slot of the previous sub-round is free (every thread read it before this barrier) and is not
-                // touched again before the barrier after next
-                if (tid == 0) sm.round[slot == 0u ? 2u : slot - 1u] = 0;
-                slot = slot == 2u ? 0u : slot + 1u;
-                const u32 total = all & 0xFFFFu;
-                if (staged + total > (u32)STAGE) {
-                    s1_flush<Shared, THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
-                    staged = 0;
-                }
-                u32 idx = staged + wbase + ((incl - mine) & 0xFFFFu);
-                for (u32 it = 0; it < cnt; ++it, ++idx) {
-                    const u32 j = (u32)__ffs(rest) - 1u;
-                    rest &= rest - 1u;
-                    const u32 nwin = (rest ? (u32)__ffs(rest) - 1u : nv) - j;
-                    const u32 b = sm.bk[done + it][tid];
-                    const u32 p = c * 32u + j, sh = 2u * j;
-                    const u64 hi = sk_rev2(sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0);
-                    const u64 lo = sk_rev2(sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1);
-                    const u32 has_next = p + nwin - 1u + (u32)w < len ? 1u : 0u;
-                    const u32 b1 = b >> l2_bits, b2 = b & l2_mask;
-                    const u32 rank = atomicAdd(&sm.hist[b1], 1u);
-                    atomicAdd((unsigned long long*)&ghist[b], (1ull << 32) | (unsigned long long)nwin);
-                    sm.bases[idx] = make_ulonglong2(hi, lo);
-                    sm.meta[idx] = ((e_read + p) << 16) | ((u64)b2 << 6) | ((u64)has_next << 5) | (u64)(nwin - 1u);
-                    sm.br[idx] = (b1 << 16) | rank;
-                }
-                done += cnt;
-                staged += total;
-                if ((all >> 16) == 0u) break;
-            }
-        }
-    }
-    s1_flush<Shared, THREADS>(sm, staged, n_l1, out_rec, cap1, cursors, overflow);
-    if (overflow) atomicOr(status, GA_ST_TABLE_FULL);
-}
-
-// ------------------------------------------------------------------------------------------------
-// 1c. lane per read, no stage: the staged kernels spend half their time in the flush (ncu, profiles/r01:
-// three barriers, one returned global atomic per level-1 bucket and flush whether the bucket got one record or
-// none -- a 2048-record stage over 1024 buckets holds 1-2 records per bucket -- and a copy whose scattered
-// 16 + 8 byte stores are no better coalesced than direct ones).  Here a record takes its place in its level-1
-// bucket with ONE returned global atomic and is written straight from registers; a thread keeps BATCH atomics
-// in flight before it builds the records.  No shared-memory stage, no barrier: every thread is on its own, and
-// the CTA's shared memory is just the per-thread bucket columns, so occupancy is set by registers.
+//   * each record then takes its slot in its level-1 bucket with ONE returned global atomic and is written
+//     straight from registers with one 256-bit store; a thread keeps BATCH atomics in flight before it builds
+//     the records.  No shared-memory stage, no barrier: a stage of a few thousand records over 1024 level-1
+//     buckets holds 1-2 records per bucket, so its flush coalesces nothing and costs three barriers plus one
+//     returned atomic per bucket (a staged variant of this kernel measured the same time; profiles/r01).
+// Buckets, record cuts and record contents are bit-identical to the kernel above (a GPU test compares the two).
 template <int THREADS, int BATCH>
 __global__ void __launch_bounds__(THREADS)
-sk_scatter_reads_direct_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
+sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
                                u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
     __shared__ u32 bk[32][THREADS];                      // bucket of this thread's i-th record of the current chunk
     const u32 tid = threadIdx.x;
@@ -1413,39 +1260,22 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     // hand (A/B runs and the test that compares their records)
     const int variant = [] {
         const char* e = getenv("GA_SK_SCATTER");
-        return !e ? 1 : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : (!strcmp(e, "direct") ? 3 : (!strcmp(e, "direct256") ? 4 : 1))));
+        return !e ? 1 : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : 1));
     }();
-#define GA_SK_ARGS                                                                                                   \
+#define GA_SK_ARGS \
     rv, w, m, l1_bits, l2_bits, (u64*)records_dev, l1_capacity, (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev
-#define GA_SK_LANE(T, STAGE, SUB, PER_SM)                                                                            \
-    do {                                                                                                             \
-        static bool attr_set = false;                                                                                \
-        const int bytes = (int)sizeof(S1LShared<T, STAGE, SUB>);                                                     \
-        if (!attr_set) {                                                                                             \
-            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_lane_kernel<T, STAGE, SUB>,                                \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));                       \
-            attr_set = true;                                                                                         \
-        }                                                                                                            \
-        const u64 n_tiles = (rv.n_reads + T - 1) / T;                                                                \
-        const unsigned grid = (unsigned)(n_tiles < 148ull * PER_SM ? n_tiles : 148ull * PER_SM);                     \
-        sk_scatter_reads_lane_kernel<T, STAGE, SUB><<<grid, T, bytes, (cudaStream_t)stream>>>(GA_SK_ARGS);           \
-    } while (0)
-    if (w - m + 1 == 16 && variant == 1) {
-        GA_SK_LANE(256, 2048, 8, 2);
-    } else if (w - m + 1 == 16 && variant == 2) {
-        GA_SK_LANE(128, 1536, 12, 3);
-    } else if (w - m + 1 == 16 && (variant == 3 || variant == 4)) {
+    if (w - m + 1 == 16 && variant != 0) {
         // persistent grid: as many CTAs as fit (registers and the bucket columns in shared memory decide)
         static int per_sm[2] = {0, 0};
         if (!per_sm[0]) {
-            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sk_scatter_reads_direct_kernel<128, 4>, 128, 0));
-            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sk_scatter_reads_direct_kernel<256, 4>, 256, 0));
+            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sk_scatter_reads_lane_kernel<256, 4>, 256, 0));
+            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sk_scatter_reads_lane_kernel<128, 4>, 128, 0));
         }
-        const unsigned threads = variant == 3 ? 128 : 256;
-        const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = 148ull * (u64)per_sm[variant == 3 ? 0 : 1];
+        const unsigned threads = variant == 1 ? 256 : 128;
+        const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = 148ull * (u64)per_sm[variant == 1 ? 0 : 1];
         const unsigned grid = (unsigned)(n_ctas < most ? n_ctas : most);
-        if (variant == 3) sk_scatter_reads_direct_kernel<128, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
-        else sk_scatter_reads_direct_kernel<256, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
+        if (variant == 1) sk_scatter_reads_lane_kernel<256, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
+        else sk_scatter_reads_lane_kernel<128, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
     } else {
         static bool attr_set = false;
         if (!attr_set) {
@@ -1460,7 +1290,6 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
         if (w - m + 1 == 16) sk_scatter_reads_kernel<16><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
         else sk_scatter_reads_kernel<0><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
     }
-#undef GA_SK_LANE
 #undef GA_SK_ARGS
     GA_LAUNCH_CHECK("sk_scatter_reads");
     return GA_OK;

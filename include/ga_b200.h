@@ -174,7 +174,7 @@ int ga_sk_minimizer_len(int k);
  * to bucket b (2^l1_bits * stride words, zeroed by the caller; the cursors sit 128 bytes apart so that their
  * atomics spread over the L2 slices).  hist_dev[2^(l1_bits+l2_bits)] (zeroed by the caller) accumulates, per
  * final bucket, records << 32 | windows.  GA_STATUS_TABLE_FULL: a level-1 bucket overflowed (its cursor kept
- * counting), retry with a larger capacity.  GA_SK_SCATTER=warp|lane|lane128|direct in the environment picks
+ * counting), retry with a larger capacity.  GA_SK_SCATTER=warp|lane|lane128 in the environment picks
  * the kernel by hand (same records from each; tests and A/B runs). */
 int ga_sk_cursor_stride(void);
 int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, int l2_bits, void* records_dev,

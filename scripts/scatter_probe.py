@@ -47,5 +47,7 @@ def run(variant, dbg):
     print("%-10s dbg=%-2d %7.2f ms  records=%d status=%d" % (variant, dbg, best, recs, int(status[0].item())), flush=True)
 
 
-for variant in ("warp", "lane", "lane128", "direct", "direct256"):
-    run(variant, 0)
+for spec in (sys.argv[1:] or ["warp", "lane", "lane128"]):
+    variant, _, dbg = spec.partition(":")
+    os.environ["GA_SK_DBG"] = dbg or "0"          # only a probe build of the library looks at it
+    run(variant, int(dbg or 0))
