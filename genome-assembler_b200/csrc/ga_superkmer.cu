@@ -1256,11 +1256,13 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     if (reads->n_reads == 0) return GA_OK;
     ReadsView rv = ga_view(reads);
     const int m = ga_sk_minimizer_len(k);
-    // which kernel: windows of 16 m-mers take the lane-per-read kernel; GA_SK_SCATTER=warp|lane|lane128 picks one by
-    // hand (A/B runs and the test that compares their records)
-    const int variant = [] {
+    // which kernel: windows of 16 m-mers take the lane-per-read kernel when there are enough level-1 buckets for
+    // its one-atomic-per-record cursors (with 8 buckets every record of the GPU bumps one of 8 words: C2's scatter
+    // went from 0.7 to 1.9 ms); GA_SK_SCATTER=warp|lane|lane128 picks one by hand (A/B runs and the test that
+    // compares their records)
+    const int variant = [&] {
         const char* e = getenv("GA_SK_SCATTER");
-        return !e ? 1 : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : 1));
+        return !e ? (l1_bits >= 5 ? 1 : 0) : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : 1));
     }();
 #define GA_SK_ARGS \
     rv, w, m, l1_bits, l2_bits, (u64*)records_dev, l1_capacity, (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev
