@@ -541,9 +541,19 @@ sk_scatter_buckets_kernel(const u64* __restrict__ in_rec, u64 cap1,
             }
         }
         __syncthreads();
-        for (u32 p = threadIdx.x; p < n_l2; p += S2_THREADS) {
-            const u32 c = hist[p];
-            gbase[p] = c ? atomicAdd(&cursors2[((u64)b1 << l2_bits) + p], (u64)c) : 0ull;
+        {   // one returned atomic per non-empty final bucket, all of a thread's (<= 4) in flight together
+            u64 got[1024 / S2_THREADS];
+#pragma unroll
+            for (u32 u = 0; u < 1024 / S2_THREADS; ++u) {
+                const u32 p = threadIdx.x + u * S2_THREADS;
+                const u32 c = p < n_l2 ? hist[p] : 0u;
+                got[u] = c ? atomicAdd((unsigned long long*)&cursors2[((u64)b1 << l2_bits) + p], (unsigned long long)c) : 0ull;
+            }
+#pragma unroll
+            for (u32 u = 0; u < 1024 / S2_THREADS; ++u) {
+                const u32 p = threadIdx.x + u * S2_THREADS;
+                if (p < n_l2) gbase[p] = got[u];
+            }
         }
         __syncthreads();
 #pragma unroll
