@@ -573,6 +573,89 @@ sk_scatter_buckets_kernel(const u64* __restrict__ in_rec, u64 cap1,
     }
 }
 
+// Index form with the chunk sorted by final bucket before it is written: a chunk of 8192 slots holds ~8 entries per
+// final bucket, which leave as one 32-byte run (lanes next to each other write addresses next to each other) instead
+// of eight 4-byte stores into sectors that other CTAs are writing too.
+constexpr int S3_THREADS = 512;
+constexpr int S3_PER = 16;
+constexpr u32 S3_CHUNK = S3_THREADS * S3_PER;
+struct S3Shared {
+    u64 gbase[1024];
+    u32 hist[1024];
+    u32 scan[1024];
+    u32 sorted_i[S3_CHUNK];
+    u16 sorted_b[S3_CHUNK];
+    u32 wsum[32];
+};
+__global__ void __launch_bounds__(S3_THREADS)
+sk_index_buckets_sorted_kernel(const u64* __restrict__ in_rec, u64 cap1, const u64* __restrict__ cursors1, u32 n_l1,
+                               int l2_bits, u64* __restrict__ cursors2, u32* __restrict__ out_index) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S3Shared& sm = *reinterpret_cast<S3Shared*>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 chunks_per = (cap1 + S3_CHUNK - 1) / S3_CHUNK;
+    const u64 total = (u64)n_l1 * chunks_per;
+    for (u64 chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        const u32 b1 = (u32)(chunk / chunks_per);
+        const u64 lo = (chunk % chunks_per) * S3_CHUNK;
+        const u64 cnt1 = min(cursors1[b1 * SK_CURSOR_STRIDE], cap1);
+        if (lo >= cnt1) continue;                           // CTA-uniform
+        sm.hist[tid] = 0;
+        sm.hist[tid + S3_THREADS] = 0;
+        __syncthreads();
+        u32 br[S3_PER];                                     // level-2 bucket | rank inside the chunk << 16
+#pragma unroll
+        for (int u = 0; u < S3_PER; ++u) {
+            const u64 i = lo + (u64)u * S3_THREADS + tid;
+            br[u] = 0;
+            if (i < cnt1) {
+                const u32 b2 = meta_b2(__ldg(in_rec + 4u * ((u64)b1 * cap1 + i) + 2u));
+                br[u] = b2 | (atomicAdd(&sm.hist[b2], 1u) << 16);
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan of the 1024 counts (two per thread) and the buckets' places in the index
+            const u32 a = sm.hist[2u * tid], b = sm.hist[2u * tid + 1u];
+            u32 incl = a + b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (u32)o) incl += t;
+            }
+            if (lane == 31u) sm.wsum[warp] = incl;
+            const u64 first = (u64)b1 << l2_bits;
+            const u64 ga = a ? atomicAdd((unsigned long long*)&cursors2[first + 2u * tid], (unsigned long long)a) : 0ull;
+            const u64 gb = b ? atomicAdd((unsigned long long*)&cursors2[first + 2u * tid + 1u], (unsigned long long)b) : 0ull;
+            __syncthreads();
+            u32 before = 0;
+            for (u32 q = 0; q < warp; ++q) before += sm.wsum[q];
+            const u32 base = before + incl - (a + b);
+            sm.scan[2u * tid] = base;
+            sm.scan[2u * tid + 1u] = base + a;
+            sm.gbase[2u * tid] = ga;
+            sm.gbase[2u * tid + 1u] = gb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < S3_PER; ++u) {
+            const u64 i = lo + (u64)u * S3_THREADS + tid;
+            if (i < cnt1) {
+                const u32 b2 = br[u] & 0xFFFFu;
+                const u32 pos = sm.scan[b2] + (br[u] >> 16);
+                sm.sorted_i[pos] = (u32)i;
+                sm.sorted_b[pos] = (u16)b2;
+            }
+        }
+        __syncthreads();
+        const u32 n = (u32)min(cnt1 - lo, (u64)S3_CHUNK);
+        for (u32 t = tid; t < n; t += S3_THREADS) {
+            const u32 b2 = sm.sorted_b[t];
+            out_index[sm.gbase[b2] + (t - sm.scan[b2])] = sm.sorted_i[t];
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps
 //
@@ -1363,7 +1446,24 @@ extern "C" int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capaci
     const u32 n_l1 = 1u << l1_bits;
     const u64 total = (u64)n_l1 * ((l1_capacity + S2_CHUNK - 1) / S2_CHUNK);
     const unsigned grid = (unsigned)(total < 148ull * 8 ? total : 148ull * 8);
-    if (index)
+    if (index && !getenv("GA_SK_INDEX_STAGED")) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GA_CUDA(cudaFuncSetAttribute(sk_index_buckets_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(S3Shared)));
+            attr_set = true;
+        }
+        const u64 total3 = (u64)n_l1 * ((l1_capacity + S3_CHUNK - 1) / S3_CHUNK);
+        static int per_sm3 = 0;
+        if (!per_sm3)
+            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, sk_index_buckets_sorted_kernel, S3_THREADS,
+                                                                  sizeof(S3Shared)));
+        const u64 most3 = 148ull * (u64)(per_sm3 > 0 ? per_sm3 : 1);
+        const unsigned grid3 = (unsigned)(total3 < most3 ? total3 : most3);
+        sk_index_buckets_sorted_kernel<<<grid3, S3_THREADS, sizeof(S3Shared), (cudaStream_t)stream>>>(
+            (const u64*)records_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1, l2_bits, (u64*)cursors_dev,
+            out_index_dev);
+    } else if (index)
         sk_scatter_buckets_kernel<true><<<grid, S2_THREADS, 0, (cudaStream_t)stream>>>(
             (const u64*)records_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1, l2_bits, (u64*)cursors_dev, nullptr,
             nullptr, out_index_dev);
