@@ -642,6 +642,9 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
     L = gn.lib()
     dev = bases.device
+    # the bucket kernel hands out a bucket's records through a 31-bit counter
+    if n_occ >= (1 << 31) and bool((((hist >> 32) >= (1 << 31)) | (hist < 0)).any().item()):
+        raise gn.GaError("bucketed count: a bucket holds 2^31 records or more (one repeated window?)")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16

@@ -198,6 +198,7 @@ int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capacity, const u
  * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev is
  * then records_dev of ga_sk_scatter_reads (32-byte slots; meta_dev is not used and may be NULL), offsets
  * address index_dev, and the record of entry e of bucket b is slot (b >> l2_bits) * l1_capacity + index_dev[e].
+ * A bucket must hold fewer than 2^31 records (the kernel hands them out through a 31-bit counter; the host checks).
  * One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
  * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
  * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
