@@ -8,8 +8,9 @@ One "step" = one full pass of the path over the workload's synthetic reads.
   e2e     the same through the host-buffer entry: ASCII reads in pinned host memory -> H2D ->
           pack -> count -> filter -> build -> CSR -> D2H of the CSR arrays, all timed
   roofline  algorithmic bytes of the dominant kernel / its CUDA-event duration vs measured HBM peak
-  cpu_baseline  the oracle's pure-Python port (the reference is pure Python) on a bounded sample
-`--impl reference` times that CPU port alone (the reference cannot travel to the GPU box).
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py) through its own CLI on a bounded sample
+`--impl reference` times that reference run alone, K timed steps after W warm-up steps (the pure-Python port of
+oracle/py_oracle.py stands in only when oracle/_ref/ is missing).
 Workloads are synthetic stand-ins of BASELINE.json's configs ("Measurement").
 """
 from __future__ import annotations
@@ -141,8 +142,12 @@ def workload_occ(n_reads, read_len, paired, k):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")          # the unmodified reference (oracle/make_ref.py)
+
+
 def cpu_port_rate(reads, k, F, paired):
-    """Occurrences/s of the oracle's pure-Python port (count + build), one core."""
+    """Occurrences/s of the oracle's pure-Python port (count + build), one core.  Only used when the
+    reference itself is not available (oracle/_ref/ missing)."""
     from oracle import py_oracle as po
     t0 = time.perf_counter()
     tally = (po.count_paired if paired else po.count_unpaired)(k, reads)
@@ -166,30 +171,114 @@ def host_sample_reads(genome_size, n_reads, sample, read_len, paired):
     return list(zip(strings[0::2], strings[1::2])) if paired else strings
 
 
+def write_reference_input(path, reads, paired):
+    """The stdin format of the reference's IOHandler.read_input (assemble.py:40-71)."""
+    with open(path, "w") as fh:
+        fh.write("%d\n" % len(reads))
+        if paired:
+            fh.write("".join("%s|%s|125\n" % pair for pair in reads))
+        else:
+            fh.write("\n".join(reads) + "\n")
+
+
+def reference_cli_step(path, k, F, sketch=False):
+    """One run of the UNMODIFIED reference through its own CLI and stock code path
+    (`python assemble.py --stdout -t -k K -f F [-c] < reads`, assemble.py:172-194); stage times from its own
+    `-t` prints (debug_graph.py:20-85).  Returns (count + [sketch] + build seconds, wall seconds)."""
+    cmd = [sys.executable, os.path.join(REF_DIR, "assemble.py"), "--stdout", "-t", "-k", str(k), "-f", str(F)]
+    if sketch:
+        cmd.append("-c")
+    t0 = time.perf_counter()
+    with open(path) as fh:
+        proc = subprocess.run(cmd, stdin=fh, capture_output=True, text=True, cwd=REF_DIR)
+    wall = time.perf_counter() - t0
+    if proc.returncode != 0:
+        raise RuntimeError("reference CLI failed: " + proc.stderr[-400:])
+    stamp = {}
+    for line in proc.stdout.split("\n"):
+        for key in ("STARTING TO COUNT KMERS", "FINISHED BUILDING GRAPH"):
+            if key in line:
+                stamp[key] = float(line.split("T =")[1].split()[0].rstrip("-"))
+    return stamp["FINISHED BUILDING GRAPH"] - stamp["STARTING TO COUNT KMERS"], wall
+
+
+def cpu_arm_sample(args, budget_s, runs):
+    """Reads of the CPU sample: the whole workload when `runs` passes of it fit the time budget at the
+    reference's measured ~0.9 M k-mers/s (large samples; small ones run up to 2 M/s), otherwise a coverage-scaled subsample that does."""
+    genome_size, n_reads, read_len, paired, k, F, _ = WORKLOADS[args.workload]
+    per_read = (2 if paired else 1) * (read_len - k + 2)
+    fit = int(budget_s / max(runs, 1) * 0.9e6 / per_read)
+    sample = max(1000, min(n_reads, fit, args.sample_reads if args.sample_reads else fit))
+    return sample, host_sample_reads(genome_size, n_reads, sample, read_len, paired)
+
+
+def cpu_arm_measure(args, reads, runs, warmup):
+    """(k-mers/s, mean seconds per run, occurrences, kind, wall seconds per run) of the CPU arm."""
+    _, _, read_len, paired, k, F, _ = WORKLOADS[args.workload]
+    occ = len(reads) * (2 if paired else 1) * (read_len - k + 2)
+    if os.path.exists(os.path.join(REF_DIR, "assemble.py")):
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "reads.txt")
+            write_reference_input(path, reads, paired)
+            times, walls = [], []
+            for step in range(warmup + runs):
+                dt, wall = reference_cli_step(path, k, F, sketch=getattr(args, "sketch", False))
+                if step >= warmup:
+                    times.append(dt)
+                    walls.append(wall)
+        mean = sum(times) / len(times)
+        return occ / mean, mean, occ, "reference", sum(walls) / len(walls)
+    times = []
+    for step in range(warmup + runs):
+        _, dt, occ = cpu_port_rate(reads, k, F, paired)
+        if step >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return occ / mean, mean, occ, "port", mean
+
+
+def cpu_sample_text(kind, sample, n_reads, paired, mean, wall):
+    what = ("the unmodified reference through its CLI (oracle/_ref/assemble.py --stdout -t%s, stock code path, "
+            "single-threaded pure Python); count + build seconds from its own -t prints, %.2f s of %.2f s wall per run"
+            % ("", mean, wall)) if kind == "reference" else \
+           "oracle/py_oracle.py (pure-Python port; oracle/_ref/ not present), %.2f s per run" % mean
+    scope = "the whole workload" if sample >= n_reads else \
+        "%d reads%s over a genome scaled to keep the workload's coverage" % (sample, " pairs" if paired else "")
+    return "%s; %s" % (scope, what)
+
+
+def workload_config(args, world):
+    """The `config` object both arms print (identical keys and values)."""
+    genome_size, n_reads, read_len, paired, k, F, desc = WORKLOADS[args.workload]
+    if args.reads:
+        n_reads = args.reads
+    mates = 2 if paired else 1
+    stride = (read_len + 31) // 32
+    return {"workload": desc, "k": k, "filter": F, "paired": paired, "reads": n_reads,
+            "occurrences": workload_occ(n_reads, read_len, paired, k), "sketch": bool(getattr(args, "sketch", False)),
+            "sharding": "reads by index, k-mers by hash" if world > 1 else "none",
+            "l2": "inputs larger than L2: %d MB of packed reads (and the record stream cut from them) per "
+                  "step against a 126 MB L2; every table is rebuilt each step"
+                  % (int(n_reads * mates * stride * 8) >> 20)}
+
+
 def run_reference_arm(args):
     genome_size, n_reads, read_len, paired, k, F, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(n_reads, args.sample_reads)
-    reads = host_sample_reads(genome_size, n_reads, sample, read_len, paired)
-    times, occ = [], 0
-    for step in range(args.warmup + args.steps):
-        rate, dt, occ = cpu_port_rate(reads, k, F, paired)
-        if step >= args.warmup:
-            times.append(dt)
-    mean = sum(times) / len(times)
-    value = occ / mean
+    runs = args.warmup + args.steps
+    sample, reads = cpu_arm_sample(args, 150.0, runs)
+    value, mean, occ, kind, wall = cpu_arm_measure(args, reads, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "k-mers/sec counted+filtered+graph-built", "value": value,
             "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "k": k, "filter": F, "paired": paired},
-            "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": 1, "kind": "port",
-                             "sample": "%d reads%s per step over a genome scaled to keep the workload's coverage; "
-                                       "oracle/py_oracle.py (pure-Python restatement; the reference is "
-                                       "single-threaded pure Python and cannot travel to the GPU box)"
-                                       % (sample, " pairs" if paired else "")},
+            "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+            "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": 1, "kind": kind,
+                             "host_cores": os.cpu_count(),
+                             "sample": cpu_sample_text(kind, sample, n_reads, paired, mean, wall)},
             "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -376,24 +465,17 @@ def run_gpu_arm(args):
 
     cpu_baseline = None
     if rank == 0:
-        sample = min(n_reads, args.sample_reads)
-        sreads = host_sample_reads(genome_size, n_reads, sample, read_len, paired)
-        rate, dt, occ = cpu_port_rate(sreads, k, F, paired)
-        cpu_baseline = {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": "port",
-                        "sample": "%d reads%s over a genome scaled to keep the workload's coverage, %.1f s; "
-                                  "oracle/py_oracle.py (pure-Python restatement of the pure-Python reference)" %
-                                  (sample, " pairs" if paired else "", dt),
+        sample, sreads = cpu_arm_sample(args, 20.0, 1)
+        rate, mean, occ, kind, wall = cpu_arm_measure(args, sreads, 1, 0)
+        cpu_baseline = {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": kind,
+                        "sample": cpu_sample_text(kind, sample, n_reads, paired, mean, wall),
                         "host_cores": os.cpu_count()}
     if rank == 0:
         line = {"metric": "k-mers/sec counted+filtered+graph-built", "value": value, "unit": "k-mers/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic",
-                "config": {"workload": desc, "k": k, "filter": F, "paired": paired, "reads": n_reads,
-                           "occurrences": occ_total, "sharding": "reads by index, k-mers by hash" if world > 1 else "none",
-                           "l2": "inputs larger than L2: %d MB of packed reads (and the record stream cut from them) per "
-                                 "step against a 126 MB L2; every table is rebuilt each step"
-                                 % (int(n_reads * mates * stride * 8) >> 20)},
+                "config": workload_config(args, world),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
                 "memory_gb": {"torch_reserved": round(torch.cuda.memory_reserved() / 1e9, 1),
                               "torch_peak_allocated": round(torch.cuda.max_memory_allocated() / 1e9, 1),
@@ -416,11 +498,10 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads / pairs")
     ap.add_argument("--genome", type=int, default=0, help="override the genome size (profiling: scale reads and "
                                                          "genome together to keep the workload's coverage)")
-    ap.add_argument("--sample-reads", type=int, default=100000, help="reads in the CPU-baseline sample")
+    ap.add_argument("--sample-reads", type=int, default=0, help="cap on the reads (pairs) of the CPU sample "
+                                                                "(default: what fits the time budget)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.sample_reads == 100000:
-            args.sample_reads = 30000
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

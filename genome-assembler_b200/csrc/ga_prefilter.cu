@@ -23,9 +23,15 @@ __global__ void __launch_bounds__(256) prefilter_update_kernel(ReadsView rv, int
             u32 sh;
             u32 v = ga_prefilter_value(pf, ga_key_hash(key), wi, sh);
             if (v < pf.limit) {   // cells stop counting once they mark a candidate
-                u32 old = atomicAdd(pf.words + wi, 1u << sh);
-                // a cell that wrapped (many racing adds) is pinned at its maximum: never under-estimate
-                if (((old >> sh) & cmask) == cmask) atomicOr(pf.words + wi, cmask << sh);
+                // Carry-free bump: the field is incremented by a CAS on its word only while it is below the
+                // limit (<= the field's maximum), so racing adders can neither wrap the cell nor carry into
+                // its neighbour -- a cell never under-estimates, whatever the contention.
+                u32 cur = __ldcg(pf.words + wi);
+                while (((cur >> sh) & cmask) < pf.limit) {
+                    const u32 seen = atomicCAS(pf.words + wi, cur, cur + (1u << sh));
+                    if (seen == cur) break;
+                    cur = seen;
+                }
             }
         });
     }

@@ -617,6 +617,7 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
         if not st & gn.ST_TABLE_FULL:
             break
         cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
+        del rec                              # the view keeps the old slab alive: drop it before workspace() grows
     _mark("sk scatter reads")
     if not dense:
         index = workspace("sk_index", max(total, 1), torch.int32)
@@ -642,9 +643,11 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
     L = gn.lib()
     dev = bases.device
-    # the bucket kernel hands out a bucket's records through a 31-bit counter
-    if n_occ >= (1 << 31) and bool((((hist >> 32) >= (1 << 31)) | (hist < 0)).any().item()):
-        raise gn.GaError("bucketed count: a bucket holds 2^31 records or more (one repeated window?)")
+    # the bucket kernel hands out a bucket's records through a 31-bit counter that every warp bumps once more
+    # after the last record, and hist packs records << 32 | windows with at most 32 windows per record: 2^27
+    # records keep both fields (and the hand-out counter) inside their bits
+    if n_occ >= (1 << 27) and bool((((hist >> 32) >= (1 << 27)) | (hist < 0)).any().item()):
+        raise gn.GaError("bucketed count: a bucket holds 2^27 records or more (one repeated window?)")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16
@@ -689,6 +692,7 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
         if n_solid <= out_cap:
             break
         out_cap = n_solid
+        del solid_keys, edge_stamp           # views of the old buffers: drop them before workspace() grows
     _mark("sk bucket pass")
     return solid_keys, n_solid, edge_stamp
 
