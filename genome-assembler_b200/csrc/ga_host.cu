@@ -121,3 +121,119 @@ extern "C" int ga_traverse_contigs(const int32_t* rowptr, const int32_t* col, co
     *n_contigs = offs.size() - 1;
     return GA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Raw ingest: the reference's IOHandler.read_input (assemble.py:40-71) over the bytes of stdin, without
+// a Python string per read.  Same rules: universal newlines ("\n", "\r\n", lone "\r");
+// every line is stripped of leading / trailing white space; the first line is the number of reads n;
+// the first read line decides paired ("|" present) vs unpaired; max(n, 1) read lines are consumed,
+// missing ones are empty reads (unpaired) or an error (paired: a pair line must have exactly three
+// "|" fields); the distance is the third field of the last pair line; trailing lines are ignored.
+// Only plain ASCII is handled here (GA_ERR_ALPHABET otherwise: the caller then parses as text).
+namespace {
+inline bool ga_is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+
+struct LineScan {
+    const uint8_t* p;
+    const uint8_t* end;
+    // next line, stripped: [lo, hi); false when the input is exhausted
+    bool next(const uint8_t*& lo, const uint8_t*& hi) {
+        if (p >= end) return false;
+        const uint8_t* q = p;
+        while (q < end && *q != '\n' && *q != '\r') ++q;
+        lo = p;
+        hi = q;
+        if (q < end) p = (*q == '\r' && q + 1 < end && q[1] == '\n') ? q + 2 : q + 1;
+        else p = end;
+        while (lo < hi && ga_is_space(*lo)) ++lo;
+        while (hi > lo && ga_is_space(hi[-1])) --hi;
+        return true;
+    }
+};
+
+bool ga_parse_int(const uint8_t* lo, const uint8_t* hi, int64_t* out) {
+    while (lo < hi && ga_is_space(*lo)) ++lo;
+    while (hi > lo && ga_is_space(hi[-1])) --hi;
+    bool neg = false;
+    if (lo < hi && (*lo == '+' || *lo == '-')) neg = *lo++ == '-';
+    if (lo >= hi || hi - lo > 18) return false;
+    int64_t v = 0;
+    for (; lo < hi; ++lo) {
+        if (*lo < '0' || *lo > '9') return false;
+        v = v * 10 + (*lo - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+}  // namespace
+
+extern "C" int ga_parse_reads(const uint8_t* text, uint64_t n_bytes, uint8_t* symbols_out, int32_t* lens_out,
+                              uint64_t lens_capacity, uint64_t* n_reads_out, int* paired_out, int64_t* distance_out,
+                              uint64_t* n_symbols_out) {
+    if (!text || !n_reads_out || !paired_out || !distance_out || !n_symbols_out) {
+        ga_set_error("ga_parse_reads: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    for (uint64_t i = 0; i < n_bytes; ++i)
+        if (text[i] >= 0x80) {
+            ga_set_error("ga_parse_reads: non-ASCII input");
+            return GA_ERR_ALPHABET;
+        }
+    LineScan scan{text, text + n_bytes};
+    const uint8_t *lo = text, *hi = text;
+    int64_t wanted = 0;
+    if (!scan.next(lo, hi)) lo = hi = text;
+    if (!ga_parse_int(lo, hi, &wanted)) {
+        ga_set_error("ga_parse_reads: the first line is not an integer");
+        return GA_ERR_BAD_ARG;
+    }
+    const uint64_t count = wanted < 1 ? 1ull : (uint64_t)wanted;
+    // the first read line decides the input kind
+    LineScan peek = scan;
+    const uint8_t *flo = text, *fhi = text;
+    if (!peek.next(flo, fhi)) flo = fhi = text;
+    const bool paired = memchr(flo, '|', (size_t)(fhi - flo)) != nullptr;
+    *paired_out = paired ? 1 : 0;
+    *n_reads_out = count;
+    *distance_out = 0;
+    if (!symbols_out || !lens_out) {          // sizing call
+        *n_symbols_out = n_bytes;
+        return GA_OK;
+    }
+    if (lens_capacity < count * (paired ? 2u : 1u)) {
+        ga_set_error("ga_parse_reads: length array too small");
+        return GA_ERR_CAPACITY;
+    }
+    uint8_t* out = symbols_out;
+    for (uint64_t r = 0; r < count; ++r) {
+        if (!scan.next(lo, hi)) lo = hi = text;
+        if (!paired) {
+            const size_t n = (size_t)(hi - lo);
+            if (n > 0x7FFFFFFFu) return GA_ERR_CAPACITY;
+            memcpy(out, lo, n);
+            out += n;
+            lens_out[r] = (int32_t)n;
+            continue;
+        }
+        const uint8_t* b1 = (const uint8_t*)memchr(lo, '|', (size_t)(hi - lo));
+        const uint8_t* b2 = b1 ? (const uint8_t*)memchr(b1 + 1, '|', (size_t)(hi - b1 - 1)) : nullptr;
+        if (!b1 || !b2 || memchr(b2 + 1, '|', (size_t)(hi - b2 - 1))) {
+            ga_set_error("ga_parse_reads: read-pair line %llu does not have three '|' fields",
+                         (unsigned long long)(r + 1));
+            return GA_ERR_BAD_ARG;
+        }
+        const size_t n1 = (size_t)(b1 - lo), n2 = (size_t)(b2 - b1 - 1);
+        if (n1 > 0x7FFFFFFFu || n2 > 0x7FFFFFFFu) return GA_ERR_CAPACITY;
+        memcpy(out, lo, n1);
+        memcpy(out + n1, b1 + 1, n2);
+        out += n1 + n2;
+        lens_out[2 * r] = (int32_t)n1;
+        lens_out[2 * r + 1] = (int32_t)n2;
+        if (r + 1 == count && !ga_parse_int(b2 + 1, hi, distance_out)) {
+            ga_set_error("ga_parse_reads: the distance field of the last pair is not an integer");
+            return GA_ERR_BAD_ARG;
+        }
+    }
+    *n_symbols_out = (uint64_t)(out - symbols_out);
+    return GA_OK;
+}

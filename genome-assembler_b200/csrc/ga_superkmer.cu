@@ -657,18 +657,45 @@ sk_index_buckets_sorted_kernel(const u64* __restrict__ in_rec, u64 cap1, const u
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps
+// 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps -- in ONE walk
 //
 // Work is flattened per warp: each lane loads one record, the warp prefix-sums the window counts and
 // then walks the windows of its 32 records 32 at a time, so every lane probes an independent window
-// (full lanes, no serial key roll, balanced warps).  Table, counters and stamps live in shared
-// memory and are addressed with explicit ld/atom.shared.
-constexpr int SB_THREADS = 512;
-constexpr int SB_CTAS_PER_SM = 2;
-constexpr u32 SB_MAX_SLOTS = 8192;
-constexpr u32 SB_POOL_BYTES = 106496;          // 104 KB of dynamic shared memory per CTA: table + solid keys + stamps
+// (full lanes, no serial key roll, balanced warps).  Table and stamps live in shared memory and are
+// addressed with explicit ld/atom.shared.
+//
+// Table slot = 16 bytes {K, A}, read with one 128-bit load:
+//   K  the window's key (all ones: empty), claimed with one 64-bit CAS;
+//   A  the window's state, advanced with 64-bit CAS only:
+//        0                                   nothing recorded yet
+//        FIRST | ordinal << 3 | c << 1 | f   seen once: the ordinal of that occurrence, the symbol c after it,
+//                                            f = whether a symbol follows (count is 1 by construction)
+//        CAND  | count << 24 | index         seen at least twice (or once when the threshold is 0): `index`
+//                                            names its key + 4 stamp slots in the candidate area; count
+//                                            saturates just above the threshold
+// The occurrence that takes a window from FIRST to CAND allocates the candidate, folds the remembered first
+// occurrence and its own into the (still private) stamps and publishes everything with the one CAS that also
+// moves the count to 2 -- so whoever sees CAND sees initialised stamps, and no occurrence ever has to be
+// revisited: the flagged second walk of the previous generation (23 % of the kernel, 35 % of all records on
+// C4, nearly all of them because of sequencing-error windows that never become solid) is gone, and so are
+// the per-record flags and the separate solid-index array.  Stamps are taken for every window seen twice
+// (a superset of the solid ones); at the end the candidates whose count is above the threshold are written
+// out.  cand[p][c] = min ordinal of "p followed by c" is kept with a compare + 64-bit CAS (taken only when
+// the stored ordinal is larger: a handful of times per stamp).
+#ifndef GA_SB_THREADS
+#define GA_SB_THREADS 512
+#endif
+#ifndef GA_SB_CTAS
+#define GA_SB_CTAS 2
+#endif
+constexpr int SB_THREADS = GA_SB_THREADS;
+constexpr int SB_CTAS_PER_SM = GA_SB_CTAS;
+// dynamic shared memory per CTA (table + candidates): what is left of the SM's 227 KB after the per-CTA static
+// control block and the 1 KB the system reserves per CTA
+constexpr u32 SB_POOL_BYTES = ((232448u / GA_SB_CTAS - 1024u - 1536u) / 1024u) * 1024u;
+constexpr u32 SB_MAX_SLOTS = 8192;             // upper bound of the table_slots argument (16-byte slots)
 constexpr u32 SB_PROBE_MAX = 192;
-constexpr u32 SB_MAX_FLAGS = 6144;             // records of a bucket that can carry a "walk again" flag
+constexpr u32 SB_CAND_BYTES = 42;              // key 8 + 4 stamps 32 + slot number 2
 #ifndef GA_SK_TAIL
 #define GA_SK_TAIL 16
 #endif
@@ -683,230 +710,115 @@ __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
     return h * 0xC2B2AE3Du;                     // use the TOP bits
 }
 
-// ---- table access: two shared-memory flavours (byte addresses in the shared window) and a global one.
-// kKind 0: shared, count packed into the key word ((key << 4) | count, count <= 15) -- one 64-bit CAS
-//          inserts a window with count 1, no separate counter traffic; needs 2w + 4 <= 64, threshold <= 13.
-// kKind 1: shared, separate 16-bit counters (two per word).
-// kKind 2: global scratch (spill path), 32-bit counters.
-__device__ __forceinline__ u64 sh_ld64v(u32 a) {
-    u64 v;
-    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ u64 sh_ld64(u32 a) {
-    u64 v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sh_st64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
-__device__ __forceinline__ u32 sh_ld32v(u32 a) {
-    u32 v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sh_st32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sh_st16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((u16)v) : "memory"); }
-__device__ __forceinline__ u64 sh_cas64(u32 a, u64 cmp, u64 val) {
-    u64 old;
-    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
-    return old;
-}
+constexpr u64 SA_FIRST = 1ull << 62, SA_CAND = 2ull << 62;
+constexpr u32 SA_CNT_SHIFT = 24;
+constexpr u32 SA_IDX_MASK = (1u << SA_CNT_SHIFT) - 1u;
+__device__ __forceinline__ u32 sa_type(u64 a) { return (u32)(a >> 62); }
+__device__ __forceinline__ u32 sa_count(u64 a) { return (u32)(a >> SA_CNT_SHIFT); }     // bits 55..24
+__device__ __forceinline__ u32 sa_index(u64 a) { return (u32)a & SA_IDX_MASK; }
 
-// Result of counting one occurrence of a window.
-enum : u32 {
-    CS_SOLID_BEFORE = 0,   // its count was above the threshold already
-    CS_BECAME_SOLID = 1,   // this occurrence took it above the threshold: the caller gives it a solid index
-    CS_NOT_YET = 2,        // still at or below the threshold after this occurrence
-    CS_TABLE_FULL = 3,
-    CS_INSERTED = 4        // OR-ed in when the occurrence created the entry (distinct-window statistics)
-};
-
-struct TabSharedBase {
-    u32 keys, cnt, sidx, flags, skeys, stamps;  // shared byte addresses
-    __device__ __forceinline__ void skey_st(u32 i, u64 v) const { sh_st64(skeys + 8u * i, v); }
-    __device__ __forceinline__ u64 skey_ld(u32 i) const { return sh_ld64(skeys + 8u * i); }
-    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { sh_st64(stamps + 8u * i, v); }
-    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return sh_ld64v(stamps + 8u * i); }
-    __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
-        asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
+// ---- table + candidate storage: shared memory (byte addresses in the shared window) or global scratch
+struct MemShared {
+    u32 slots, ckey, cstamp, cslot;             // shared byte addresses
+    __device__ __forceinline__ void ld_slot(u32 s, u64& k, u64& a) const {
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(a) : "r"(slots + 16u * s));
     }
-    // solid index + 1 of a slot (0: none yet); published after the slot's stamps are initialised
-    __device__ __forceinline__ u32 sidx_ld(u32 s) const {
+    __device__ __forceinline__ u64 ld_a(u32 s) const {
+        u64 v;
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(slots + 16u * s + 8u));
+        return v;
+    }
+    __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
+        u64 old;
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(slots + 16u * s), "l"(cmp), "l"(val) : "memory");
+        return old;
+    }
+    __device__ __forceinline__ u64 cas_a(u32 s, u64 cmp, u64 val) const {
+        u64 old;
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(slots + 16u * s + 8u), "l"(cmp), "l"(val) : "memory");
+        return old;
+    }
+    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T)
+            asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(slots + 16u * s), "l"(GA_NONE64), "l"(0ull) : "memory");
+    }
+    __device__ __forceinline__ void ckey_st(u32 i, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(ckey + 8u * i), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ u64 ckey_ld(u32 i) const {
+        u64 v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(ckey + 8u * i));
+        return v;
+    }
+    __device__ __forceinline__ void cslot_st(u32 i, u32 s) const {
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(cslot + 2u * i), "h"((u16)s) : "memory");
+    }
+    __device__ __forceinline__ u32 cslot_ld(u32 i) const {
         u16 v;
-        asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(v) : "r"(sidx + 2u * s));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(cslot + 2u * i));
         return v;
     }
-    __device__ __forceinline__ void sidx_st(u32 s, u32 idx1) const { sh_st16(sidx + 2u * s, idx1); }
-    // per-record "walk me again" flags (bytes)
-    __device__ __forceinline__ void flag_set(u32 i) const {
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(flags + i), "r"(1u) : "memory");
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(cstamp + 8u * i), "l"(v) : "memory");
     }
-    __device__ __forceinline__ u32 flag_ld(u32 i) const {
-        u32 v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(flags + i));
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const {
+        u64 v;
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(cstamp + 8u * i));
         return v;
     }
-    __device__ __forceinline__ void clear_aux(u32 cap, u32 n_flags, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap / 2; s += T) sh_st32(sidx + 4u * s, 0u);
-        for (u32 s = tid; s < (n_flags + 3u) / 4u; s += T) sh_st32(flags + 4u * s, 0u);
+    __device__ __forceinline__ u64 stamp_cas(u32 i, u64 cmp, u64 val) const {
+        u64 old;
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(cstamp + 8u * i), "l"(cmp), "l"(val) : "memory");
+        return old;
     }
 };
 
-struct TabPacked : TabSharedBase {
-    static constexpr u32 kSlotBytes = 10;       // key word + solid index
-    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);
+struct MemGlobal {
+    u64* slots;                                 // {K, A} pairs
+    u64* ckey;
+    u64* cstamp;
+    u32* cslot;
+    __device__ __forceinline__ void ld_slot(u32 s, u64& k, u64& a) const {
+        k = ((volatile u64*)slots)[2u * (size_t)s];
+        a = ((volatile u64*)slots)[2u * (size_t)s + 1u];
     }
-    // count one occurrence (saturating just above the threshold)
-    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            const u32 a = keys + 8u * s;
-            u64 cur = sh_ld64v(a);
-            if (cur == GA_NONE64) {
-                cur = sh_cas64(a, GA_NONE64, (key << 4) | 1ull);
-                if (cur == GA_NONE64) {
-                    slot = s;
-                    return (threshold == 0u ? CS_BECAME_SOLID : CS_NOT_YET) | CS_INSERTED;
-                }
-            }
-            if ((cur >> 4) == key) {
-                slot = s;
-                for (;;) {
-                    const u32 c0 = (u32)(cur & 15ull);
-                    if (c0 > threshold) return CS_SOLID_BEFORE;
-                    const u64 old = sh_cas64(a, cur, cur + 1ull);
-                    if (old == cur) return c0 == threshold ? CS_BECAME_SOLID : CS_NOT_YET;
-                    cur = old;
-                }
-            }
-            s = (s + 1u) & cmask;
-        }
-        return CS_TABLE_FULL;
+    __device__ __forceinline__ u64 ld_a(u32 s) const { return ((volatile u64*)slots)[2u * (size_t)s + 1u]; }
+    __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
+        return atomicCAS((unsigned long long*)(slots + 2u * (size_t)s), cmp, val);
     }
-    // second walk: solid index + 1 of a counted window, 0 if not solid
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            const u64 cur = sh_ld64(keys + 8u * s);
-            if ((cur >> 4) == key) return (u32)(cur & 15ull) > threshold ? sidx_ld(s) : 0u;
-            s = (s + 1u) & cmask;
-        }
-        return 0u;
+    __device__ __forceinline__ u64 cas_a(u32 s, u64 cmp, u64 val) const {
+        return atomicCAS((unsigned long long*)(slots + 2u * (size_t)s + 1u), cmp, val);
     }
-};
-
-struct TabShared : TabSharedBase {
-    static constexpr u32 kSlotBytes = 12;       // key + 16-bit counter + solid index
-    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap; s += T) sh_st64(keys + 8u * s, GA_NONE64);
-        for (u32 s = tid; s < cap / 2; s += T) sh_st32(cnt + 4u * s, 0u);
-    }
-    __device__ __forceinline__ u32 cnt_get(u32 s) const { return (sh_ld32v(cnt + 4u * (s >> 1)) >> ((s & 1u) * 16u)) & 0xFFFFu; }
-    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            const u32 a = keys + 8u * s;
-            u64 cur = sh_ld64v(a);
-            u32 ins = 0;
-            if (cur == GA_NONE64) {
-                cur = sh_cas64(a, GA_NONE64, key);
-                if (cur == GA_NONE64) {
-                    cur = key;
-                    ins = CS_INSERTED;
-                }
-            }
-            if (cur == key) {
-                slot = s;
-                if (cnt_get(s) > threshold) return CS_SOLID_BEFORE | ins;
-                u32 old;
-                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(cnt + 4u * (s >> 1)), "r"(1u << ((s & 1u) * 16u)) : "memory");
-                old = (old >> ((s & 1u) * 16u)) & 0xFFFFu;
-                return (old == threshold ? CS_BECAME_SOLID : (old > threshold ? CS_SOLID_BEFORE : CS_NOT_YET)) | ins;
-            }
-            s = (s + 1u) & cmask;
-        }
-        return CS_TABLE_FULL;
-    }
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            if (sh_ld64(keys + 8u * s) == key) return sidx_ld(s);
-            s = (s + 1u) & cmask;
-        }
-        return 0u;
-    }
-};
-
-struct TabGlobal {
-    u64* keys;
-    u32* cnt;                                   // one 32-bit counter per slot
-    u32* sidx;                                  // solid index + 1 per slot
-    u64* skeys;
-    u64* stamps;
     __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
         for (u32 s = tid; s < cap; s += T) {
-            keys[s] = GA_NONE64;
-            cnt[s] = 0u;
+            slots[2u * (size_t)s] = GA_NONE64;
+            slots[2u * (size_t)s + 1u] = 0ull;
         }
     }
-    __device__ __forceinline__ void clear_aux(u32 cap, u32, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap; s += T) sidx[s] = 0u;
-    }
-    __device__ __forceinline__ u32 count(u64 key, u32 h, u32 lg, u32 cmask, u32 threshold, u32& slot) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            u64 cur = ((volatile u64*)keys)[s];
-            u32 ins = 0;
-            if (cur == GA_NONE64) {
-                cur = atomicCAS((unsigned long long*)(keys + s), GA_NONE64, key);
-                if (cur == GA_NONE64) {
-                    cur = key;
-                    ins = CS_INSERTED;
-                }
-            }
-            if (cur == key) {
-                slot = s;
-                if (((volatile u32*)cnt)[s] > threshold) return CS_SOLID_BEFORE | ins;
-                const u32 old = atomicAdd(cnt + s, 1u);
-                return (old == threshold ? CS_BECAME_SOLID : (old > threshold ? CS_SOLID_BEFORE : CS_NOT_YET)) | ins;
-            }
-            s = (s + 1u) & cmask;
-        }
-        return CS_TABLE_FULL;
-    }
-    __device__ __forceinline__ u32 solid_of(u64 key, u32 h, u32 lg, u32 cmask, u32) const {
-        u32 s = h >> (32u - lg);
-        for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-            if (keys[s] == key) return ((volatile u32*)sidx)[s];
-            s = (s + 1u) & cmask;
-        }
-        return 0u;
-    }
-    __device__ __forceinline__ u32 sidx_ld(u32 s) const { return ((volatile u32*)sidx)[s]; }
-    __device__ __forceinline__ void sidx_st(u32 s, u32 idx1) const { ((volatile u32*)sidx)[s] = idx1; }
-    __device__ __forceinline__ void flag_set(u32) const {}
-    __device__ __forceinline__ u32 flag_ld(u32) const { return 1u; }
-    __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
-    __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
-    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { stamps[i] = v; }
-    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return ((volatile u64*)stamps)[i]; }
-    __device__ __forceinline__ void stamp_min(u32 i, u64 v) const {
-        atomicMin((unsigned long long*)(stamps + i), (unsigned long long)v);
+    __device__ __forceinline__ void ckey_st(u32 i, u64 v) const { ckey[i] = v; }
+    __device__ __forceinline__ u64 ckey_ld(u32 i) const { return ckey[i]; }
+    __device__ __forceinline__ void cslot_st(u32 i, u32 s) const { cslot[i] = s; }
+    __device__ __forceinline__ u32 cslot_ld(u32 i) const { return cslot[i]; }
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { cstamp[i] = v; }
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return ((volatile u64*)cstamp)[i]; }
+    __device__ __forceinline__ u64 stamp_cas(u32 i, u64 cmp, u64 val) const {
+        return atomicCAS((unsigned long long*)(cstamp + i), cmp, val);
     }
 };
 
 struct BucketCtl {     // shared-memory control block of one CTA
-    u32 n_solid;
+    u32 n_solid;       // windows whose count went above the threshold (this pass)
+    u32 n_cand;        // candidate slots handed out (this pass)
     u32 overflow;
     u32 bucket;
     u32 n_distinct;
+    u32 out_pos;       // solid windows written so far (this pass)
     u64 out_base;
     u32 sp;            // pending (parts << 16 | part) items of the current bucket
-    u32 ratio_d;       // running estimates, in 1/4096: distinct windows / windows, solid windows / windows
-    u32 ratio_s;
+    u32 ratio_d;       // running estimates, in 1/4096: distinct windows / windows, candidates / windows
+    u32 ratio_c;
     u32 n_seg;
-    u32 next_batch;    // dynamic batch hand-out of the current walk
+    u32 next_batch;    // dynamic record hand-out of the walk
     u32 stack[40];
     u64 seg_lo[SB_MAX_SEG];        // the bucket's records: segment s holds [seg_lo[s], +seg_pre[s+1]-seg_pre[s])
     u64 seg_pre[SB_MAX_SEG + 1];
@@ -926,20 +838,15 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
     return ((u64)hi << 32) | lo;
 }
 
-// One batch = up to 32 records, one per lane, held by lanes 0..n-1.  The records are cut into pieces of
-// at most SB_PIECE consecutive windows; the pieces of the batch are dealt to the lanes 32 at a time (warp
-// prefix sum + ballot/REDUX find the owner record of each piece), and a lane rolls through the windows
-// of its piece.  Finding the owner costs about as much as handling one window, so it is shared by a few
-// windows; longer pieces would leave lanes idle (records hold 6-7 windows on average).
-// f(top, ord, follows, owner) is called once per window: `top` holds the window's symbols from bit 63
+// One batch = up to 32 records, one per lane, held by lanes 0..n-1.  The windows of the batch are dealt to
+// the lanes 32 at a time (warp prefix sum + ballot/REDUX find the owner record of each window).
+// f(top, ord, follows) is called once per window: `top` holds the window's symbols from bit 63
 // down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
-// whether a next symbol exists, `owner` the lane whose record it belongs to.
-constexpr u32 SB_PIECE = 1;
-
+// whether a next symbol exists.
 template <class F>
 __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
-    const u32 npiece = have ? (meta_windows(meta) + SB_PIECE - 1u) / SB_PIECE : 0u;
+    const u32 npiece = have ? meta_windows(meta) : 0u;
     u32 incl = npiece;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -956,86 +863,64 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
         const u32 x = xb + lane;
         const bool active = x < total;
         const u32 owner = active ? before + __popc(marks & le_mask) - 1u : 0u;
-        const u32 j0 = (x - __shfl_sync(FULL, start, owner)) * SB_PIECE;
+        const u32 j = x - __shfl_sync(FULL, start, owner);
         const u64 ohi = shfl64(rhi, owner), olo = shfl64(rlo, owner);
         const u64 om = shfl64(meta, owner);
         if (active) {
             const u32 nwin = meta_windows(om);
-            const u32 j1 = min(j0 + SB_PIECE, nwin);
-            const u64 ord0 = meta_ordinal(om);
-            const bool has_next = meta_has_next(om);
-            for (u32 j = j0; j < j1; ++j) {
-                const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-                f(top, ord0 + j, j + 1u < nwin || has_next, owner);
-            }
+            const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
+            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om));
         }
         __syncwarp();
     }
 }
 
-// returns false when the bucket does not fit: the caller lists it for the spill path
-template <class Tab>
+// returns false when the pass does not fit (table or candidate area full): the caller splits it or lists it
+// for the spill path
+template <class Mem>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
-                                               SkGather gather, int w, u32 threshold, const Tab& tab, u32 cap,
-                                               u32 max_solid, bool flag_all, bool count_only, u32 parts, u32 part, BucketCtl& ctl, u64* __restrict__ solid_keys_out,
-                                               u64* __restrict__ edge_stamp_out, u64 out_capacity,
-                                               u64* n_solid_global) {
+                                               SkGather gather, int w, u32 threshold, const Mem& mem, u32 cap,
+                                               u32 max_cand, bool count_only, u32 parts, u32 part, BucketCtl& ctl,
+                                               u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out,
+                                               u64 out_capacity, u64* n_solid_global) {
     const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
-    const u32 lg = 31u - (u32)__clz(cap);
-    const u32 cmask = cap - 1u;
     const u32 kshift = 64u - 2u * (u32)w;
     const u32 n_seg = ctl.n_seg;
     const u64 nrec = ctl.seg_pre[n_seg];
-    const u64 n_batches = (nrec + 31u) / 32u;
-    // position of the bucket's idx-th record (segments are few: linear scan)
-    // `where(idx)`: position of the bucket's idx-th entry (segments are few: linear scan); in the index form
-    // that entry is a 32-bit index and the record sits at gather.base + index
+    // position of the bucket's idx-th entry (segments are few: linear scan); in the index form that entry is a
+    // 32-bit index and the record sits at gather.base + index
     auto where = [&](u64 idx) -> u64 {
         u32 sg = 0;
         while (sg + 1u < n_seg && idx >= ctl.seg_pre[sg + 1]) ++sg;
         return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
     };
-    auto locate = [&](u64 idx) -> u64 {
-        const u64 at = where(idx);
-        return gather.index ? gather.base + __ldg(gather.index + at) : at;
-    };
     // B. clear
-    const u32 n_flags = flag_all ? 0u : (u32)nrec;
-    tab.clear(cap, tid, T);
-    tab.clear_aux(cap, n_flags, tid, T);
+    mem.clear(cap, tid, T);
     if (tid == 0) {
         ctl.n_solid = 0;
+        ctl.n_cand = 0;
         ctl.overflow = 0;
         ctl.n_distinct = 0;
-        ctl.next_batch = W * 32u;      // count walk: records handed out so far (the warps' first spans are 32 each)
+        ctl.out_pos = 0;
+        ctl.next_batch = W * 32u;      // records handed out so far (the warps' first spans are 32 each)
     }
     __syncthreads();
     volatile u32* vovf = &ctl.overflow;
-    // batches are handed out dynamically (one shared-memory atomic per batch): with 3-4 batches per warp a
-    // static split leaves a quarter of the warps waiting at the barrier for one batch's time
-    auto next_batch = [&]() -> u64 {
-        u32 v = 0;
-        if (lane == 0) v = atomicAdd(&ctl.next_batch, 1u);
-        return __shfl_sync(FULL, v, 0);
-    };
     const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
-    // smallest ordinal of "solid window `sol` followed by symbol c"
-    auto stamp = [&](u32 sol, u64 top, u64 ord) {
-        const u32 at = 4u * (sol - 1u) + ((u32)(top >> (kshift - 2u)) & 3u);
-        if (ord < tab.stamp_ld(at)) tab.stamp_min(at, ord);
+    // smallest ordinal of "candidate `idx` followed by symbol c"
+    auto stamp = [&](u32 idx, u32 c, u64 ord) {
+        const u32 at = 4u * idx + c;
+        u64 cur = mem.stamp_ld(at);
+        while (ord < cur) {
+            const u64 old = mem.stamp_cas(at, cur, ord);
+            if (old == cur) break;
+            cur = old;
+        }
     };
-    // C. count (saturating just above the threshold: only "count > threshold" is asked).  A window that
-    //    is solid by the time it is visited takes its edge stamp right away; the occurrence that makes a
-    //    window solid gives it its solid index and stamp slots; records with an occurrence that could
-    //    not be stamped yet are flagged for the second walk.
+    // C. the walk.  Hand-out in RECORDS: a warp takes 32 records at a time while more than a round's worth is left
+    // and GA_SK_TAIL records at a time after that, so that the last round of a bucket is not left to a third of
+    // the warps.  A span is start | (short ? 1 << 31 : 0); ctl.next_batch counts records.
     u32 inserted = 0;
-    // In the index form the record is two dependent loads away (index entry, then the gather): the next
-    // batch's index entry is requested one batch ahead (one register; prefetching whole records measured
-    // slower, A/B on one B200).
-    // Count walk hand-out in RECORDS: a warp takes 32 records at a time while more than a round's worth is left and
-    // GA_SK_TAIL records at a time after that, so that the last round of a bucket is not left to a third of the warps
-    // (a bucket is ~53 batches for 16 warps; -2.5 % on the kernel, A/B on one B200; 8-record spans give it back).
-    // A span is start | (short ? 1 << 31 : 0); ctl.next_batch counts records during this walk.
     constexpr u32 TAIL = GA_SK_TAIL;
     const u32 nrec32 = (u32)min(nrec, (u64)0x7FFFFFFFu);
     auto next_span = [&]() -> u32 {
@@ -1048,12 +933,12 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         return __shfl_sync(FULL, v, 0);
     };
     auto span_take = [&](u32 sp) -> u32 { return (sp >> 31) ? TAIL : 32u; };
+    // In the index form the record is two dependent loads away (index entry, then the gather): the next
+    // span's index entry is requested one span ahead.
     auto entry = [&](u32 sp) -> u32 {
         const u32 idx = (sp & 0x7FFFFFFFu) + lane;
         return (gather.index && lane < span_take(sp) && idx < nrec32) ? __ldg(gather.index + where(idx)) : 0u;
     };
-    ulonglong2 b = make_ulonglong2(0, 0);
-    u64 mt = 0;
     u32 ent = entry(warp * 32u);
     for (u32 sp = warp * 32u, sp_next = 0; (sp & 0x7FFFFFFFu) < nrec32 && !*vovf; sp = sp_next) {
         const u32 bt = sp & 0x7FFFFFFFu;               // first record of the span
@@ -1061,8 +946,8 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         const bool have = lane < span_take(sp) && idx < nrec;
         sp_next = next_span();
         const u32 ent_next = entry(sp_next);
-        b = make_ulonglong2(0, 0);
-        mt = 0;
+        ulonglong2 b = make_ulonglong2(0, 0);
+        u64 mt = 0;
         if (have) {
             if (gather.index) {
                 sk_load_slot((const u64*)bases, gather.base + ent, b, mt);     // a 32-byte slot of the level-1 bucket
@@ -1073,36 +958,84 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             }
         }
         ent = ent_next;
-        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
+        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
-            u32 slot = 0;
-            const u32 st = tab.count(key, h, lg, cmask, threshold, slot);
-            inserted += st >> 2;
-            const u32 state = st & 3u;
-            if (state == CS_TABLE_FULL) {
-                *vovf = 1u;
-                return;
-            }
-            u32 sol = 0;
-            if (state == CS_BECAME_SOLID) {
-                const u32 at = atomicAdd(&ctl.n_solid, 1u);
-                if (at >= max_solid) {
-                    *vovf = 1u;
+            follows = follows && !count_only;
+            const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
+            u32 s = __umulhi(h, cap);                      // any table size: no power of two needed
+            for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
+                u64 K, A;
+                mem.ld_slot(s, K, A);
+                if (K == GA_NONE64) {
+                    K = mem.cas_k(s, GA_NONE64, key);
+                    if (K == GA_NONE64) {
+                        ++inserted;
+                        K = key;
+                        A = 0ull;
+                    } else if (K == key) {
+                        A = mem.ld_a(s);
+                    }
+                }
+                if (K == key) {
+                    u32 mine = GA_NONE32;                  // candidate slot this thread allocated and still holds
+                    for (;;) {
+                        if (sa_type(A) == 2u) {            // CAND: count (saturating), then the stamp
+                            const u32 cnt = sa_count(A);
+                            if (cnt <= threshold) {
+                                const u64 old = mem.cas_a(s, A, A + (1ull << SA_CNT_SHIFT));
+                                if (old != A) {
+                                    A = old;
+                                    continue;
+                                }
+                                if (cnt == threshold) atomicAdd(&ctl.n_solid, 1u);
+                            }
+                            if (follows) stamp(sa_index(A), c, ord);
+                            break;
+                        }
+                        if (A == 0ull && threshold != 0u) {   // first occurrence: remember it in the slot
+                            const u64 old = mem.cas_a(s, 0ull, SA_FIRST | (ord << 3) | ((u64)c << 1) | (u64)follows);
+                            if (old == 0ull) break;
+                            A = old;
+                            continue;
+                        }
+                        // second occurrence (first when the threshold is 0): the window becomes a candidate
+                        if (mine == GA_NONE32) {
+                            mine = atomicAdd(&ctl.n_cand, 1u);
+                            if (mine >= max_cand) {
+                                *vovf = 1u;
+                                return;
+                            }
+                            mem.ckey_st(mine, key);
+                            mem.cslot_st(mine, s);
+                        }
+                        const bool had = sa_type(A) == 1u && (A & 1ull);
+                        const u32 c1 = (u32)(A >> 1) & 3u;
+                        const u64 ord1 = (A >> 3) & ((1ull << 48) - 1ull);
+#pragma unroll
+                        for (u32 q = 0; q < 4u; ++q) {
+                            u64 v = GA_NONE64;
+                            if (follows && q == c) v = ord;
+                            if (had && q == c1) v = min(v, ord1);
+                            mem.stamp_st(4u * mine + q, v);
+                        }
+                        __threadfence_block();
+                        const u32 cnt_new = A == 0ull ? 1u : 2u;
+                        const u64 old = mem.cas_a(s, A, SA_CAND | ((u64)cnt_new << SA_CNT_SHIFT) | (u64)mine);
+                        if (old == A) {
+                            if (cnt_new > threshold) atomicAdd(&ctl.n_solid, 1u);
+                            mine = GA_NONE32;
+                            break;
+                        }
+                        A = old;                           // somebody else moved the slot on: go again
+                    }
+                    if (mine != GA_NONE32) mem.ckey_st(mine, GA_NONE64);   // allocated, lost the race: not a candidate
                     return;
                 }
-                tab.skey_st(at, key);
-                for (u32 c = 0; c < 4u; ++c) tab.stamp_st(4u * at + c, GA_NONE64);
-                __threadfence_block();
-                tab.sidx_st(slot, at + 1u);
-                sol = at + 1u;
-            } else if (state == CS_SOLID_BEFORE) {
-                sol = tab.sidx_ld(slot);          // 0: its index is still being published
+                s = s + 1u == cap ? 0u : s + 1u;
             }
-            if (!follows || count_only) return;
-            if (sol) stamp(sol, top, ord);
-            else if (!flag_all) tab.flag_set(bt + owner);
+            *vovf = 1u;                                    // probe limit: table full
         });
     }
     for (int off = 16; off > 0; off >>= 1) inserted += __shfl_down_sync(FULL, inserted, off);
@@ -1111,64 +1044,49 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     if (ctl.overflow) return false;
     const u32 n_solid = ctl.n_solid;
     if (n_solid == 0) return true;
-    if (tid == 0) {
-        ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
-        ctl.next_batch = W;
-    }
+    if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
     __syncthreads();
-    // E. second walk over the flagged records only (none when only the solid set is asked for)
-    for (u64 bt = count_only ? n_batches : (u64)warp; bt < n_batches; bt = next_batch()) {
-        // the flagged records of the batch move to the low lanes (sk_for_each_window wants the lanes
-        // that hold a record to be a prefix)
-        const u64 mine = bt * 32u + lane;
-        const u32 fmask = __ballot_sync(FULL, mine < nrec && (flag_all || tab.flag_ld((u32)mine)));
-        if (fmask == 0u) continue;
-        const bool have = lane < (u32)__popc(fmask);
-        ulonglong2 b = make_ulonglong2(0, 0);
-        u64 mt = 0;
-        if (have) {
-            const u64 i = locate(bt * 32u + __fns(fmask, 0, lane + 1));
-            if (gather.index) {
-                sk_load_slot((const u64*)bases, i, b, mt);
-            } else {
-                b = bases[i];
-                mt = meta[i];
+    // D. output: the candidates whose count ended above the threshold
+    const u64 base = ctl.out_base;
+    const u32 n_cand = min(ctl.n_cand, max_cand);
+    const bool room = base + n_solid <= out_capacity;
+    for (u32 i0 = 0; i0 < n_cand; i0 += T) {
+        const u32 i = i0 + tid;
+        u64 key = GA_NONE64;
+        bool solid = false;
+        if (i < n_cand) {
+            key = mem.ckey_ld(i);
+            if (key != GA_NONE64) solid = sa_count(mem.ld_a(mem.cslot_ld(i))) > threshold;
+        }
+        const u32 m = __ballot_sync(FULL, solid);
+        if (m == 0u) continue;
+        u32 at = 0;
+        if (lane == 0) at = atomicAdd(&ctl.out_pos, (u32)__popc(m));
+        at = __shfl_sync(FULL, at, 0) + (u32)__popc(m & ((1u << lane) - 1u));
+        if (solid && room) {
+            solid_keys_out[base + at] = key;
+            if (edge_stamp_out) {
+#pragma unroll
+                for (u32 q = 0; q < 4u; ++q) edge_stamp_out[4u * (base + at) + q] = mem.stamp_ld(4u * i + q);
             }
         }
-        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32) {
-            if (!follows) return;
-            const u64 key = top >> kshift;
-            const u32 h = sk_slot_hash(key);
-            if (((h >> 3) & pmask) != part) return;
-            const u32 sol = tab.solid_of(key, h, lg, cmask, threshold);
-            if (sol) stamp(sol, top, ord);
-        });
-    }
-    __syncthreads();
-    // F. output
-    const u64 base = ctl.out_base;
-    if (base + n_solid <= out_capacity) {
-        for (u32 s = tid; s < n_solid; s += T) solid_keys_out[base + s] = tab.skey_ld(s);
-        if (edge_stamp_out)
-            for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = tab.stamp_ld(s);
     }
     return true;
 }
 
 // counters: [0] next bucket, [1] solid windows so far, [2] passes listed for the spill path,
-// [3] passes run | failed passes << 32 (statistics)
+// [3] passes run | failed passes << 32, [4] distinct windows and [5] candidates over the passes that fitted (statistics)
 // hist: per bucket, records << 32 | windows
 //
 // A bucket is done in `parts` passes (a power of two), pass `part` taking the windows whose hash
-// bits select it, so that the distinct and the solid windows of one pass fit the CTA's pool.  parts
-// comes from running estimates of distinct / windows and solid / windows (the first buckets of a CTA
+// bits select it, so that the distinct windows and the candidates of one pass fit the CTA's pool.  parts
+// comes from running estimates of distinct / windows and candidates / windows (the first buckets of a CTA
 // start pessimistic); a pass that still does not fit is split in two; only passes that would need more
 // than 32 parts go to the spill list (entry = bucket | parts << 32 | part << 48).
-template <class Tab>
 __global__ void __launch_bounds__(SB_THREADS, SB_CTAS_PER_SM)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
                  u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
-                 u32 solid_limit,
+                 u32 cand_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
                  u64* __restrict__ spill_list, u64 spill_capacity, u32* status, const u32* __restrict__ index,
                  u64 l1_capacity, int l2_bits) {
@@ -1182,8 +1100,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         asm volatile("mov.u32 %0, %1;" : "=r"(pool) : "r"(raw));
     }
     if (threadIdx.x == 0) {
-        ctl.ratio_d = 4096u;
-        ctl.ratio_s = 1024u;
+        ctl.ratio_d = 1024u;
+        ctl.ratio_c = 512u;
     }
     for (;;) {
         __syncthreads();
@@ -1204,14 +1122,18 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
         }
-        const u64 est_d = (nw * ctl.ratio_d >> 12) * 9u / 8u + 64u, est_s = (nw * ctl.ratio_s >> 12) * 9u / 8u + 16u;
-        const u32 solid_room = min(solid_limit, (SB_POOL_BYTES - Tab::kSlotBytes * cap_limit - 2048u) / 40u);
+        // expected distinct windows and candidates of the bucket (running ratios + a margin), and the pool one pass
+        // needs for them: 16-byte slots at a load of at most ~0.75, 42 bytes per candidate
+        const u64 est_d = (nw * ctl.ratio_d >> 12) * 17u / 16u + 48u, est_c = (nw * ctl.ratio_c >> 12) * 9u / 8u + 24u;
         if (threadIdx.x == 0) {
-            // passes: expected distinct windows of a pass within 85 % of the largest table, solid ones within
-            // 85 % of what the pool holds next to it (a pass that overflows anyway is split below)
             u32 parts = 1;
-            while (parts < 32u && (est_d > (u64)parts * (cap_limit * 17u / 20u) || est_s > (u64)parts * (solid_room * 17u / 20u)))
+            while (parts < 32u) {
+                const u64 d = est_d / parts, c = est_c / parts;
+                if (d * 4u / 3u <= (u64)cap_limit && c <= (u64)cand_limit &&
+                    (d * 4u / 3u) * 16u + c * SB_CAND_BYTES <= (u64)SB_POOL_BYTES)
+                    break;
                 parts <<= 1;
+            }
             for (u32 q = 0; q < parts; ++q) ctl.stack[q] = (parts << 16) | (parts - 1u - q);
             ctl.sp = parts;
         }
@@ -1220,45 +1142,42 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             const u32 sp = ctl.sp;
             if (sp == 0) break;
             const u32 item = ctl.stack[sp - 1];
-            const u32 rd = ctl.ratio_d, rs = ctl.ratio_s;
+            const u32 rd = ctl.ratio_d, rc = ctl.ratio_c;
             __syncthreads();
             const u32 parts = item >> 16, part = item & 0xFFFFu;
-            // table sized for 2.5 x the expected distinct windows of this pass (short probe chains); the rest of the pool
-            // holds solid keys + 4 stamps each
-            const u64 want = ((nw * rd >> 12) / parts + 64u) * 5u / 2u;
-            u32 cap = 256;
-            while (cap < cap_limit && (u64)cap < want) cap <<= 1;
-            // pool: table (keys [+ counters] + solid indices), record flags, then solid keys + 4 stamps each
-            const u64 nrec = ctl.seg_pre[n_seg];
-            const bool flag_all = nrec > SB_MAX_FLAGS;
-            const u32 flag_bytes = flag_all ? 0u : ((u32)nrec + 7u) & ~7u;
-            Tab tab;
-            tab.keys = pool;
-            tab.cnt = pool + 8u * cap;
-            tab.sidx = pool + (Tab::kSlotBytes - 2u) * cap;
-            tab.flags = pool + Tab::kSlotBytes * cap;
-            tab.skeys = tab.flags + flag_bytes;
-            u32 max_solid = (SB_POOL_BYTES - Tab::kSlotBytes * cap - flag_bytes) / 40u;
-            if (max_solid > solid_limit) max_solid = solid_limit;
-            tab.stamps = tab.skeys + 8u * max_solid;
+            // the pool of this pass: candidates for the expected number + a margin, the table gets the rest up to
+            // 2.5 x the expected distinct windows (short probe chains; more would only cost clearing time)
+            const u64 want_c = min(((nw * rc >> 12) / parts) * 5u / 4u + 48u, (u64)cand_limit);
+            u32 max_cand = (u32)min(want_c, (u64)(SB_POOL_BYTES / 2u / SB_CAND_BYTES));
+            const u64 want_d = ((nw * rd >> 12) / parts) * 5u / 2u + 128u;
+            u32 cap = (u32)min(min(want_d, (u64)cap_limit), (u64)((SB_POOL_BYTES - max_cand * SB_CAND_BYTES) / 16u));
+            if (cap < 64u) cap = 64u;
+            max_cand = min(cand_limit, (SB_POOL_BYTES - 16u * cap) / SB_CAND_BYTES);     // whatever is left
+            MemShared mem;
+            mem.slots = pool;
+            mem.ckey = pool + 16u * cap;
+            mem.cstamp = mem.ckey + 8u * max_cand;
+            mem.cslot = mem.cstamp + 32u * max_cand;
             const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, max_solid, flag_all,
+            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, max_cand,
                                            edge_stamp_out == nullptr, parts, part, ctl,
                                            solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
                 atomicAdd((unsigned long long*)&counters[3], ok ? 1ull : (1ull << 32) + 1ull);   // passes, failed passes << 32
                 if (ok) {
+                    atomicAdd((unsigned long long*)&counters[4], (unsigned long long)ctl.n_distinct);   // statistics
+                    atomicAdd((unsigned long long*)&counters[5], (unsigned long long)ctl.n_cand);
                     // running means (weight 1/4) of what the passes actually held
                     const u32 d = (u32)min((u64)ctl.n_distinct * parts * 4096u / (nw + 1u), 4096ull);
-                    const u32 so = (u32)min((u64)ctl.n_solid * parts * 4096u / (nw + 1u), 4096ull);
+                    const u32 cd = (u32)min((u64)ctl.n_cand * parts * 4096u / (nw + 1u), 4096ull);
                     ctl.ratio_d = (3u * rd + d + 3u) >> 2;
-                    ctl.ratio_s = (3u * rs + so + 3u) >> 2;
+                    ctl.ratio_c = (3u * rc + cd + 3u) >> 2;
                 } else if (parts < 32u && top + 2u <= 40u) {
                     ctl.stack[top++] = ((parts * 2u) << 16) | (part + parts);
                     ctl.stack[top++] = ((parts * 2u) << 16) | part;
-                    ctl.ratio_d = min(4096u, rd + (rd >> 1) + 64u);
-                    ctl.ratio_s = min(4096u, rs + (rs >> 1) + 16u);
+                    ctl.ratio_d = min(4096u, rd + (rd >> 3) + 16u);     // mild: one odd bucket must not split the next ones
+                    ctl.ratio_c = min(4096u, rc + (rc >> 3) + 8u);
                 } else {
                     const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
                     if (at < spill_capacity) spill_list[at] = b | ((u64)parts << 32) | ((u64)part << 48);
@@ -1280,13 +1199,13 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
                        u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
                        u64* counters, u32* status, const u32* __restrict__ index, u64 l1_capacity, int l2_bits) {
     __shared__ BucketCtl ctl;
-    TabGlobal tab;
+    MemGlobal mem;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
-    tab.keys = reinterpret_cast<u64*>(mine);
-    tab.skeys = tab.keys + cap;
-    tab.stamps = tab.skeys + cap;
-    tab.cnt = reinterpret_cast<u32*>(tab.stamps + 4 * (size_t)cap);
-    tab.sidx = tab.cnt + cap;
+    const u32 max_cand = min(cap, SA_IDX_MASK);
+    mem.slots = reinterpret_cast<u64*>(mine);
+    mem.ckey = mem.slots + 2 * (size_t)cap;
+    mem.cstamp = mem.ckey + cap;
+    mem.cslot = reinterpret_cast<u32*>(mem.cstamp + 4 * (size_t)cap);
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
         const u64 entry = spill_list[oi];
@@ -1305,8 +1224,8 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         }
         __syncthreads();
         const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, tab, cap, cap, true, edge_stamp_out == nullptr, parts, part, ctl,
-                                       solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, max_cand, edge_stamp_out == nullptr,
+                                       parts, part, ctl, solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
     }
@@ -1337,6 +1256,15 @@ sk_resolve_kernel(const u64* __restrict__ keys, u64 n, int w, const Slot<u64>* _
 }
 
 bool is_pow2(u64 v) { return v && !(v & (v - 1)); }
+
+// SMs of the current device (persistent grids are sized in multiples of it)
+int ga_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+        n = 148;
+    return n;
+}
 
 }  // namespace
 
@@ -1384,27 +1312,22 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     rv, w, m, l1_bits, l2_bits, (u64*)records_dev, l1_capacity, (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev
     if (w - m + 1 == 16 && variant != 0) {
         // persistent grid: as many CTAs as fit (registers and the bucket columns in shared memory decide)
-        static int per_sm[2] = {0, 0};
-        if (!per_sm[0]) {
-            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], sk_scatter_reads_lane_kernel<256, 4>, 256, 0));
-            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], sk_scatter_reads_lane_kernel<128, 4>, 128, 0));
-        }
+        int per_sm = 0;
+        if (variant == 1) GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk_scatter_reads_lane_kernel<256, 4>, 256, 0));
+        else GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk_scatter_reads_lane_kernel<128, 4>, 128, 0));
         const unsigned threads = variant == 1 ? 256 : 128;
-        const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = 148ull * (u64)per_sm[variant == 1 ? 0 : 1];
+        const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = (u64)ga_sm_count() * (u64)(per_sm > 0 ? per_sm : 1);
         const unsigned grid = (unsigned)(n_ctas < most ? n_ctas : most);
         if (variant == 1) sk_scatter_reads_lane_kernel<256, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
         else sk_scatter_reads_lane_kernel<128, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
-            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(S1Shared)));
-            GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(S1Shared)));
-            attr_set = true;
-        }
+        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(S1Shared)));
+        GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(S1Shared)));
         const u64 n_tiles = (rv.n_reads + S1_WARPS - 1) / S1_WARPS;
-        const unsigned grid = (unsigned)(n_tiles < 148ull * 2 ? n_tiles : 148ull * 2);
+        const u64 most = (u64)ga_sm_count() * 2;
+        const unsigned grid = (unsigned)(n_tiles < most ? n_tiles : most);
         if (w - m + 1 == 16) sk_scatter_reads_kernel<16><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
         else sk_scatter_reads_kernel<0><<<grid, S1_THREADS, sizeof(S1Shared), (cudaStream_t)stream>>>(GA_SK_ARGS);
     }
@@ -1445,20 +1368,16 @@ extern "C" int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capaci
     }
     const u32 n_l1 = 1u << l1_bits;
     const u64 total = (u64)n_l1 * ((l1_capacity + S2_CHUNK - 1) / S2_CHUNK);
-    const unsigned grid = (unsigned)(total < 148ull * 8 ? total : 148ull * 8);
+    const u64 most = (u64)ga_sm_count() * 8;
+    const unsigned grid = (unsigned)(total < most ? total : most);
     if (index && !getenv("GA_SK_INDEX_STAGED")) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            GA_CUDA(cudaFuncSetAttribute(sk_index_buckets_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(S3Shared)));
-            attr_set = true;
-        }
+        GA_CUDA(cudaFuncSetAttribute(sk_index_buckets_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(S3Shared)));
         const u64 total3 = (u64)n_l1 * ((l1_capacity + S3_CHUNK - 1) / S3_CHUNK);
-        static int per_sm3 = 0;
-        if (!per_sm3)
-            GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, sk_index_buckets_sorted_kernel, S3_THREADS,
-                                                                  sizeof(S3Shared)));
-        const u64 most3 = 148ull * (u64)(per_sm3 > 0 ? per_sm3 : 1);
+        int per_sm3 = 0;
+        GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, sk_index_buckets_sorted_kernel, S3_THREADS,
+                                                              sizeof(S3Shared)));
+        const u64 most3 = (u64)ga_sm_count() * (u64)(per_sm3 > 0 ? per_sm3 : 1);
         const unsigned grid3 = (unsigned)(total3 < most3 ? total3 : most3);
         sk_index_buckets_sorted_kernel<<<grid3, S3_THREADS, sizeof(S3Shared), (cudaStream_t)stream>>>(
             (const u64*)records_dev, l1_capacity, (const u64*)l1_cursors_dev, n_l1, l2_bits, (u64*)cursors_dev,
@@ -1491,32 +1410,23 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
                      "256..%u, max_solid >= 1)", SB_MAX_SLOTS);
         return GA_ERR_BAD_ARG;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<TabPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
-        GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<TabShared>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
-        attr_set = true;
-    }
-    if (max_solid > 16000) max_solid = 16000;          // solid index + 1 lives in 16 bits
-    const unsigned grid = (unsigned)(n_buckets < 148ull * SB_CTAS_PER_SM ? n_buckets : 148ull * SB_CTAS_PER_SM);
-    // count rides in the key word; (key << 4 | 15) is kept free so that it can never look like an empty slot
-    const bool packed = 2 * w + 4 <= 64 && threshold <= 13;
-#define GA_SK_BUCKET(TAB)                                                                                          \
-    sk_bucket_kernel<TAB><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                              \
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,                   \
-        (const u64*)hist_dev, n_buckets, w,                                                                        \
-        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity, \
-        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits)
-    if (packed) GA_SK_BUCKET(TabPacked);
-    else GA_SK_BUCKET(TabShared);
-#undef GA_SK_BUCKET
+    // the attribute is per device: set it on every call (cheap) instead of caching a process-wide flag
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    if (max_solid > 16000) max_solid = 16000;
+    const u64 most = (u64)ga_sm_count() * SB_CTAS_PER_SM;
+    const unsigned grid = (unsigned)(n_buckets < most ? n_buckets : most);
+    sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,
+        (const u64*)hist_dev, n_buckets, w,
+        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits);
     GA_LAUNCH_CHECK("sk_bucket");
     return GA_OK;
 }
 
 extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
-    // keys + solid keys (8 B each) + 4 stamps (32 B) + a 32-bit counter and a 32-bit solid index per slot
-    return (uint64_t)table_slots * (8 + 8 + 32 + 4 + 4);
+    // 16-byte slots {key, state} + per candidate (as many as slots): key 8 B, 4 stamps 32 B, slot number 4 B
+    return (uint64_t)table_slots * (16 + 8 + 32 + 4);
 }
 
 extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,

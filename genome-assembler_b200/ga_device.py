@@ -30,13 +30,14 @@ SUPERKMER_MIN_OCC = 1 << 22             # smaller inputs stay on the table path 
 SUPERKMER_MIN_OCC_PAIRS = 1 << 28       # read pairs: bucketed counting only pays once the tables outgrow the L2
                                         # (C3, 1.0e8 occurrences: 4.5 ms through the buckets, 3.9 ms through the tables)
 SUPERKMER_TARGET = int(_os_early.environ.get("GA_SK_TARGET", "8192"))    # windows per bucket aimed for (C2 sweep: 8192 beats 16384 by 38 % on the bucket kernel; C4 sits at the 2^20-bucket cap either way)
-SUPERKMER_TABLE_SLOTS = 8192            # shared-memory table slots per bucket (tests shrink it to force spills)
+SUPERKMER_TABLE_SLOTS = int(_os_early.environ.get("GA_SK_SLOTS", "8192"))   # shared-memory table slots (16 bytes each) per bucket pass (tests shrink it to force spills)
 SUPERKMER_INDEX_FORM = _os_early.environ.get("GA_SK_DENSE", "0") != "1"   # single GPU: sort 32-bit indices, not records
-SUPERKMER_MAX_SOLID = 16000             # solid windows per bucket (further bounded by the shared-memory pool)
+SUPERKMER_MAX_SOLID = 16000             # candidate windows (seen twice) per bucket pass (further bounded by the shared-memory pool)
 TIMERS = None   # bench.py sets this to {"count": [], "build": []}: CUDA-event pairs around the two hot kernels
 
 
 import os as _os
+import sys as _sys
 import time as _time
 _TRACE = int(_os.environ.get("GA_TRACE", "0") or 0)
 _last = [0.0]
@@ -54,7 +55,8 @@ def _mark(name):
         if _TRACE == 1:
             torch.cuda.synchronize()
         now = _time.perf_counter()
-        print("  [trace r%s] %-28s %8.3f ms" % (_os.environ.get("RANK", "0"), name, (now - _last[0]) * 1e3), flush=True)
+        print("  [trace r%s] %-28s %8.3f ms" % (_os.environ.get("RANK", "0"), name, (now - _last[0]) * 1e3),
+              file=_sys.stderr, flush=True)
         _last[0] = _time.perf_counter()
 
 
@@ -652,7 +654,7 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16
     while True:
-        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
         spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
         solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
         edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64) if want_stamps else None
@@ -663,10 +665,11 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
                                          gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
                                          gn.ptr(spill_list), spill_cap, gn.ptr(status), gn.ptr(index), l1_capacity,
                                          l2_bits, _stream()))
-        _, n_solid, n_spill, n_pass = (int(v) for v in counters.cpu().tolist())
+        _, n_solid, n_spill, n_pass, n_distinct, n_cand = (int(v) for v in counters.cpu().tolist()[:6])
         if _TRACE:
-            print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled" %
-                  (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill), flush=True)
+            print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled, %d distinct, "
+                  "%d candidates" % (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill, n_distinct,
+                                     n_cand), file=_sys.stderr, flush=True)
         if n_spill > spill_cap:
             spill_cap = n_spill
             continue

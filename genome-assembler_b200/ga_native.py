@@ -53,6 +53,8 @@ SIGNATURES = {
     "ga_fill_bytes": (_i32, [_vp, _i32, _u64, _vp]),
     "ga_key_words": (_i32, [_i32, _i32]),
     "ga_slot_bytes": (_i32, [_i32]),
+    "ga_parse_reads": (_i32, [_vp, _u64, _vp, _vp, _u64, C.POINTER(C.c_uint64), C.POINTER(C.c_int),
+                              C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]),
     "ga_pack_reads": (_i32, [_vp, _vp, _u64, _u32, _vp, _i32, _vp, _vp, _u32, _vp, _vp]),
     "ga_unpack_reads": (_i32, [_vp, _u64, _u32, _u32, _i32, _vp, _vp, _vp]),
     "ga_gen_genome": (_i32, [_vp, _u64, _u64, _vp]),
@@ -116,7 +118,12 @@ def lib():
                 "`make -C genome-assembler_b200` (there is no CPU fallback)")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if os.environ.get("GA_LIB"):       # an older A/B build of the library: entries added since are absent
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = handle

@@ -198,15 +198,18 @@ int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capacity, const u
  * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev is
  * then records_dev of ga_sk_scatter_reads (32-byte slots; meta_dev is not used and may be NULL), offsets
  * address index_dev, and the record of entry e of bucket b is slot (b >> l2_bits) * l1_capacity + index_dev[e].
- * A bucket must hold fewer than 2^31 records (the kernel hands them out through a 31-bit counter; the host checks).
- * One CTA per bucket: exact counts in a shared-memory table of at most table_slots slots (at most
- * max_solid solid windows per bucket, bounded by what is left of the 208 KB pool); every
- * window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
+ * A bucket must hold fewer than 2^27 records (the kernel hands them out through a 31-bit counter and the
+ * histogram packs records << 32 | windows; the host checks).
+ * One CTA per bucket and ONE walk over its records: exact counts in a shared-memory table of at most
+ * table_slots 16-byte slots {key, state} (a power of two, 256..4096); a window seen twice
+ * becomes a candidate with 4 stamp slots (at most max_solid candidates per pass, bounded by what is left of
+ * the 110 KB pool), the occurrence seen before that is remembered in the slot's state word, so no record is
+ * ever walked twice.  Every window with count > threshold is appended to solid_keys_out_dev together with 4 candidate edge
  * stamps (edge_stamp_out_dev[4*i + c] = smallest occurrence ordinal of "window i followed by symbol
- * c", all-ones if never; edge_stamp_out_dev == NULL: counting only, just the solid windows).  counters_dev[3] (zeroed by the caller): [0] scheduling cursor, [1] solid
+ * c", all-ones if never; edge_stamp_out_dev == NULL: counting only, just the solid windows).  counters_dev[8] (zeroed by the caller): [0] scheduling cursor, [1] solid
  * windows found (may exceed out_capacity: nothing is written beyond it, the caller retries with
  * that many), [2] passes that did not fit and were listed in spill_list_dev.  A bucket whose distinct
- * or solid windows exceed the pool is done in 2, 4, ... 32 passes over disjoint hash ranges of its
+ * or candidate windows exceed the pool is done in 2, 4, ... 32 passes over disjoint hash ranges of its
  * windows, still in shared memory; only what would need more is listed (entry = bucket | passes << 32
  * | pass << 48). */
 int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
@@ -327,6 +330,17 @@ int ga_csr_emit(ga_csr_plan* plan, int32_t* rowptr_dev, int32_t* col_dev, int32_
                 uint8_t* branching_dev, uint8_t* last_sym_dev, void* node_keys_a_dev,
                 void* node_keys_b_dev, ga_stream stream);
 void ga_csr_plan_free(ga_csr_plan* plan);
+
+/* ---- raw ingest (replaces IOHandler.read_input, assemble.py:40-71) --------------------------------------- */
+/* HOST pointers.  Parses the bytes of stdin with the reference's rules (first line = number of reads n;
+ * max(n, 1) read lines, each stripped; "read" or "read1|read2|distance", the kind decided by the first read
+ * line; missing lines are empty reads, or GA_ERR_BAD_ARG for pairs; trailing lines ignored) into one buffer
+ * of symbols (mates of a pair back to back) and one length per read / mate -- no per-read objects.
+ * symbols_out == NULL: sizing call, only *n_reads_out, *paired_out and *n_symbols_out (an upper bound) are
+ * set.  GA_ERR_ALPHABET: the input is not plain ASCII (the caller parses it as text instead). */
+int ga_parse_reads(const uint8_t* text, uint64_t n_bytes, uint8_t* symbols_out, int32_t* lens_out,
+                   uint64_t lens_capacity, uint64_t* n_reads_out, int* paired_out, int64_t* distance_out,
+                   uint64_t* n_symbols_out);
 
 /* ---- host-side contig traversal over the CSR (debruijn_graph.py:72-111, 222-267) ----------- */
 /* Arrays are HOST pointers.  last_char: the byte each node contributes.  Allocates *text_out

@@ -1,6 +1,6 @@
-"""Times ga_sk_count_build alone on a quarter-size C4 instance.  With a probe build of the library (GA_SK_DBG:
-1 no second walk, 3 counting only, 7 window walk + hash only, 15 record loads only) it shows what each stage of
-the bucket kernel costs; results with GA_SK_DBG != 0 are garbage."""
+"""Times ga_sk_count_build alone on a quarter-size C4 instance (same coverage, same windows per bucket) and
+prints what the buckets hold: windows / records per bucket (percentiles), distinct windows and candidates per
+pass.  GA_LIB picks another build of the library (A/B of kernel variants)."""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,29 +20,34 @@ words = torch.empty(n * stride, dtype=torch.int64, device=dev)
 gn.check(L.ga_gen_reads(gn.ptr(genome), G, 0, n, rl, 4, 100, gn.ptr(words), stride, 0, 0, None))
 reads = gd.DeviceReads.from_packed(words, n, rl, False, estride=rl)
 n_occ = reads.windows_total(k)
-l1_bits, l2_bits = 8, 10            # 2^18 buckets: the windows per bucket of the full workload
+l1_bits, l2_bits = int(os.environ.get("PROBE_L1", "8")), 10            # 2^18 buckets: the windows per bucket of the full workload
 n_buckets = 1 << (l1_bits + l2_bits)
 rec, _, offsets, hist, total, index, cap1 = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, dense=False)
+win = (hist & 0xFFFFFFFF).float()
+recs = (hist >> 32).float()
+q = torch.tensor([0.01, 0.1, 0.5, 0.9, 0.99, 1.0], device=dev)
+print("windows per bucket  mean %.0f  pct(1,10,50,90,99,100) %s" % (win.mean().item(), [int(v) for v in torch.quantile(win, q).tolist()]))
+print("records per bucket  mean %.0f  pct %s" % (recs.mean().item(), [int(v) for v in torch.quantile(recs, q).tolist()]))
 out_cap = n_occ // 48 + 1024
 solid_keys = torch.empty((out_cap, 1), dtype=torch.int64, device=dev)
 edge_stamp = torch.empty(4 * out_cap, dtype=torch.int64, device=dev)
 spill_list = torch.empty(1 << 16, dtype=torch.int64, device=dev)
 status = reads.status
-for spec in (sys.argv[1:] or ["0"]):
-    os.environ["GA_SK_DBG"] = spec
+for slots in [int(v) for v in (sys.argv[1:] or [str(gd.SUPERKMER_TABLE_SLOTS)])]:
     best = 1e9
     for _ in range(3):
-        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
         status.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         gn.check(L.ga_sk_count_build(gn.ptr(rec), None, gn.ptr(offsets), 1, gn.ptr(hist), n_buckets, k, F,
-                                     gd.SUPERKMER_TABLE_SLOTS, gd.SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
+                                     slots, gd.SUPERKMER_MAX_SOLID, gn.ptr(solid_keys),
                                      gn.ptr(edge_stamp), out_cap, gn.ptr(counters), gn.ptr(spill_list), 1 << 16,
                                      gn.ptr(status), gn.ptr(index), cap1, l2_bits, None))
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
     c = counters.cpu().tolist()
-    print("dbg=%-3s %7.2f ms  solid=%d spilled=%d passes=%d failed=%d" %
-          (spec, best, c[1], c[2], c[3] & 0xFFFFFFFF, c[3] >> 32), flush=True)
+    passes = max(c[3] & 0xFFFFFFFF, 1)
+    print("slots=%-5d %7.2f ms  solid=%d spilled=%d passes=%d failed=%d distinct/pass=%.0f cands/pass=%.0f" %
+          (slots, best, c[1], c[2], passes, c[3] >> 32, c[4] / passes, c[5] / passes), flush=True)
