@@ -657,31 +657,28 @@ sk_index_buckets_sorted_kernel(const u64* __restrict__ in_rec, u64 cap1, const u
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps -- in ONE walk
+// 3. one CTA per bucket: exact counts, solid windows, candidate edge stamps -- ONE walk over the records
 //
 // Work is flattened per warp: each lane loads one record, the warp prefix-sums the window counts and
 // then walks the windows of its 32 records 32 at a time, so every lane probes an independent window
 // (full lanes, no serial key roll, balanced warps).  Table and stamps live in shared memory and are
 // addressed with explicit ld/atom.shared.
 //
-// Table slot = 16 bytes {K, A}, read with one 128-bit load:
-//   K  the window's key (all ones: empty), claimed with one 64-bit CAS;
-//   A  the window's state, advanced with 64-bit CAS only:
-//        0                                   nothing recorded yet
-//        FIRST | ordinal << 3 | c << 1 | f   seen once: the ordinal of that occurrence, the symbol c after it,
-//                                            f = whether a symbol follows (count is 1 by construction)
-//        CAND  | count << 24 | index         seen at least twice (or once when the threshold is 0): `index`
-//                                            names its key + 4 stamp slots in the candidate area; count
-//                                            saturates just above the threshold
-// The occurrence that takes a window from FIRST to CAND allocates the candidate, folds the remembered first
-// occurrence and its own into the (still private) stamps and publishes everything with the one CAS that also
-// moves the count to 2 -- so whoever sees CAND sees initialised stamps, and no occurrence ever has to be
-// revisited: the flagged second walk of the previous generation (23 % of the kernel, 35 % of all records on
-// C4, nearly all of them because of sequencing-error windows that never become solid) is gone, and so are
-// the per-record flags and the separate solid-index array.  Stamps are taken for every window seen twice
-// (a superset of the solid ones); at the end the candidates whose count is above the threshold are written
-// out.  cand[p][c] = min ordinal of "p followed by c" is kept with a compare + 64-bit CAS (taken only when
-// the stored ordinal is larger: a handful of times per stamp).
+// Table = two arrays over the same slots: K[slot] the window's 64-bit key (all ones: empty), claimed with one
+// 64-bit CAS, and A[slot] a 32-bit state word that only ever moves forward, by 32-bit CAS:
+//     0                   nothing recorded yet
+//     FIRST  | rec + 1    seen once, in record `rec` of the bucket (0: that occurrence has no next symbol)
+//     REPEAT | count      seen `count` times, 2 <= count <= threshold: still below the filter
+//     SOLID  | index      count > threshold: `index` names its key + 4 stamp slots (PENDING while they are set up)
+// cand[p][c] = min ordinal of "p followed by c" is taken on the spot for every occurrence that finds its window
+// SOLID (compare, then a 64-bit CAS only when the stored ordinal is larger).  An occurrence that comes earlier
+// cannot know whether its window will pass the filter: it leaves a 4-byte note (slot, record) in a queue -- the
+// first occurrence through the FIRST state, written to the queue by the second one.  After the walk the notes
+// whose slot ended SOLID (a few hundred per bucket: the first `threshold` occurrences of each solid window)
+// re-read their one record and fold in the stamp; all the others (sequencing-error windows seen two or three
+// times) are dropped after one look at A.  No record is walked twice: the flagged second walk of the previous
+// generation (23 % of the kernel: 35 % of all records on C4, nearly all of them because of error windows that
+// never become solid) is gone, together with the per-record flags.
 #ifndef GA_SB_THREADS
 #define GA_SB_THREADS 512
 #endif
@@ -690,12 +687,14 @@ sk_index_buckets_sorted_kernel(const u64* __restrict__ in_rec, u64 cap1, const u
 #endif
 constexpr int SB_THREADS = GA_SB_THREADS;
 constexpr int SB_CTAS_PER_SM = GA_SB_CTAS;
-// dynamic shared memory per CTA (table + candidates): what is left of the SM's 227 KB after the per-CTA static
-// control block and the 1 KB the system reserves per CTA
+// dynamic shared memory per CTA (table + queue + solid windows): what is left of the SM's 227 KB after the
+// per-CTA static control block and the 1 KB the system reserves per CTA
 constexpr u32 SB_POOL_BYTES = ((232448u / GA_SB_CTAS - 1024u - 1536u) / 1024u) * 1024u;
-constexpr u32 SB_MAX_SLOTS = 8192;             // upper bound of the table_slots argument (16-byte slots)
+constexpr u32 SB_MAX_SLOTS = 8192;             // upper bound of the table_slots argument
 constexpr u32 SB_PROBE_MAX = 192;
-constexpr u32 SB_CAND_BYTES = 42;              // key 8 + 4 stamps 32 + slot number 2
+constexpr u32 SB_SLOT_BYTES = 12;              // key 8 + state 4
+constexpr u32 SB_SOLID_BYTES = 40;             // key 8 + 4 stamps
+constexpr u32 SB_MAX_REC = 65536;              // records of a bucket a 4-byte note can name
 #ifndef GA_SK_TAIL
 #define GA_SK_TAIL 16
 #endif
@@ -710,113 +709,120 @@ __device__ __forceinline__ u32 sk_slot_hash(u64 key) {
     return h * 0xC2B2AE3Du;                     // use the TOP bits
 }
 
-constexpr u64 SA_FIRST = 1ull << 62, SA_CAND = 2ull << 62;
-constexpr u32 SA_CNT_SHIFT = 24;
-constexpr u32 SA_IDX_MASK = (1u << SA_CNT_SHIFT) - 1u;
-__device__ __forceinline__ u32 sa_type(u64 a) { return (u32)(a >> 62); }
-__device__ __forceinline__ u32 sa_count(u64 a) { return (u32)(a >> SA_CNT_SHIFT); }     // bits 55..24
-__device__ __forceinline__ u32 sa_index(u64 a) { return (u32)a & SA_IDX_MASK; }
+constexpr u32 SA_FIRST = 1u << 30, SA_REPEAT = 2u << 30, SA_SOLID = 3u << 30, SA_PAYLOAD = (1u << 30) - 1u;
+constexpr u32 SA_PENDING = SA_SOLID | SA_PAYLOAD;
 
-// ---- table + candidate storage: shared memory (byte addresses in the shared window) or global scratch
+// ---- table, queue and solid storage: shared memory (byte addresses in the shared window) or global scratch
 struct MemShared {
-    u32 slots, ckey, cstamp, cslot;             // shared byte addresses
-    __device__ __forceinline__ void ld_slot(u32 s, u64& k, u64& a) const {
-        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(a) : "r"(slots + 16u * s));
-    }
-    __device__ __forceinline__ u64 ld_a(u32 s) const {
+    u32 keys, state, queue, skeys, stamps;      // shared byte addresses
+    static constexpr u32 kMaxRec = SB_MAX_REC;
+    __device__ __forceinline__ u64 ld_k(u32 s) const {
         u64 v;
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(slots + 16u * s + 8u));
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(keys + 8u * s));
         return v;
     }
     __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
         u64 old;
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(slots + 16u * s), "l"(cmp), "l"(val) : "memory");
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(keys + 8u * s), "l"(cmp), "l"(val) : "memory");
         return old;
     }
-    __device__ __forceinline__ u64 cas_a(u32 s, u64 cmp, u64 val) const {
-        u64 old;
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(slots + 16u * s + 8u), "l"(cmp), "l"(val) : "memory");
-        return old;
-    }
-    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
-        for (u32 s = tid; s < cap; s += T)
-            asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(slots + 16u * s), "l"(GA_NONE64), "l"(0ull) : "memory");
-    }
-    __device__ __forceinline__ void ckey_st(u32 i, u64 v) const {
-        asm volatile("st.shared.u64 [%0], %1;" ::"r"(ckey + 8u * i), "l"(v) : "memory");
-    }
-    __device__ __forceinline__ u64 ckey_ld(u32 i) const {
-        u64 v;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(ckey + 8u * i));
+    __device__ __forceinline__ u32 ld_a(u32 s) const {
+        u32 v;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(state + 4u * s));
         return v;
     }
-    __device__ __forceinline__ void cslot_st(u32 i, u32 s) const {
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(cslot + 2u * i), "h"((u16)s) : "memory");
+    __device__ __forceinline__ u32 cas_a(u32 s, u32 cmp, u32 val) const {
+        u32 old;
+        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(state + 4u * s), "r"(cmp), "r"(val) : "memory");
+        return old;
     }
-    __device__ __forceinline__ u32 cslot_ld(u32 i) const {
-        u16 v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(cslot + 2u * i));
+    __device__ __forceinline__ void st_a(u32 s, u32 v) const {
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(state + 4u * s), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
+        for (u32 s = tid; s < cap; s += T) {
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(keys + 8u * s), "l"(GA_NONE64) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(state + 4u * s), "r"(0u) : "memory");
+        }
+    }
+    __device__ __forceinline__ void q_st(u32 i, u32 slot, u32 rec) const {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(queue + 4u * i), "r"((slot << 16) | rec) : "memory");
+    }
+    __device__ __forceinline__ void q_ld(u32 i, u32& slot, u32& rec) const {
+        u32 v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(queue + 4u * i));
+        slot = v >> 16;
+        rec = v & 0xFFFFu;
+    }
+    __device__ __forceinline__ void skey_st(u32 i, u64 v) const {
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(skeys + 8u * i), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ u64 skey_ld(u32 i) const {
+        u64 v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(skeys + 8u * i));
         return v;
     }
     __device__ __forceinline__ void stamp_st(u32 i, u64 v) const {
-        asm volatile("st.shared.u64 [%0], %1;" ::"r"(cstamp + 8u * i), "l"(v) : "memory");
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(stamps + 8u * i), "l"(v) : "memory");
     }
     __device__ __forceinline__ u64 stamp_ld(u32 i) const {
         u64 v;
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(cstamp + 8u * i));
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(stamps + 8u * i));
         return v;
     }
     __device__ __forceinline__ u64 stamp_cas(u32 i, u64 cmp, u64 val) const {
         u64 old;
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(cstamp + 8u * i), "l"(cmp), "l"(val) : "memory");
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(stamps + 8u * i), "l"(cmp), "l"(val) : "memory");
         return old;
     }
 };
 
 struct MemGlobal {
-    u64* slots;                                 // {K, A} pairs
-    u64* ckey;
-    u64* cstamp;
-    u32* cslot;
-    __device__ __forceinline__ void ld_slot(u32 s, u64& k, u64& a) const {
-        k = ((volatile u64*)slots)[2u * (size_t)s];
-        a = ((volatile u64*)slots)[2u * (size_t)s + 1u];
-    }
-    __device__ __forceinline__ u64 ld_a(u32 s) const { return ((volatile u64*)slots)[2u * (size_t)s + 1u]; }
+    u64* keys;
+    u32* state;
+    u64* queue;                                 // slot << 32 | record
+    u64* skeys;
+    u64* stamps;
+    static constexpr u32 kMaxRec = 0xFFFFFFFFu;
+    __device__ __forceinline__ u64 ld_k(u32 s) const { return ((volatile u64*)keys)[s]; }
     __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
-        return atomicCAS((unsigned long long*)(slots + 2u * (size_t)s), cmp, val);
+        return atomicCAS((unsigned long long*)(keys + s), cmp, val);
     }
-    __device__ __forceinline__ u64 cas_a(u32 s, u64 cmp, u64 val) const {
-        return atomicCAS((unsigned long long*)(slots + 2u * (size_t)s + 1u), cmp, val);
-    }
+    __device__ __forceinline__ u32 ld_a(u32 s) const { return ((volatile u32*)state)[s]; }
+    __device__ __forceinline__ u32 cas_a(u32 s, u32 cmp, u32 val) const { return atomicCAS(state + s, cmp, val); }
+    __device__ __forceinline__ void st_a(u32 s, u32 v) const { ((volatile u32*)state)[s] = v; }
     __device__ __forceinline__ void clear(u32 cap, u32 tid, u32 T) const {
         for (u32 s = tid; s < cap; s += T) {
-            slots[2u * (size_t)s] = GA_NONE64;
-            slots[2u * (size_t)s + 1u] = 0ull;
+            keys[s] = GA_NONE64;
+            state[s] = 0u;
         }
     }
-    __device__ __forceinline__ void ckey_st(u32 i, u64 v) const { ckey[i] = v; }
-    __device__ __forceinline__ u64 ckey_ld(u32 i) const { return ckey[i]; }
-    __device__ __forceinline__ void cslot_st(u32 i, u32 s) const { cslot[i] = s; }
-    __device__ __forceinline__ u32 cslot_ld(u32 i) const { return cslot[i]; }
-    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { cstamp[i] = v; }
-    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return ((volatile u64*)cstamp)[i]; }
+    __device__ __forceinline__ void q_st(u32 i, u32 slot, u32 rec) const { queue[i] = ((u64)slot << 32) | rec; }
+    __device__ __forceinline__ void q_ld(u32 i, u32& slot, u32& rec) const {
+        const u64 v = queue[i];
+        slot = (u32)(v >> 32);
+        rec = (u32)v;
+    }
+    __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
+    __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
+    __device__ __forceinline__ void stamp_st(u32 i, u64 v) const { stamps[i] = v; }
+    __device__ __forceinline__ u64 stamp_ld(u32 i) const { return ((volatile u64*)stamps)[i]; }
     __device__ __forceinline__ u64 stamp_cas(u32 i, u64 cmp, u64 val) const {
-        return atomicCAS((unsigned long long*)(cstamp + i), cmp, val);
+        return atomicCAS((unsigned long long*)(stamps + i), cmp, val);
     }
 };
 
 struct BucketCtl {     // shared-memory control block of one CTA
-    u32 n_solid;       // windows whose count went above the threshold (this pass)
-    u32 n_cand;        // candidate slots handed out (this pass)
+    u32 n_solid;       // solid windows of this pass
+    u32 n_q;           // notes in the queue
     u32 overflow;
     u32 bucket;
     u32 n_distinct;
-    u32 out_pos;       // solid windows written so far (this pass)
     u64 out_base;
     u32 sp;            // pending (parts << 16 | part) items of the current bucket
-    u32 ratio_d;       // running estimates, in 1/4096: distinct windows / windows, candidates / windows
-    u32 ratio_c;
+    u32 ratio_d;       // running estimates, in 1/4096 of the bucket's windows: distinct windows, notes, solid windows
+    u32 ratio_q;
+    u32 ratio_s;
     u32 n_seg;
     u32 next_batch;    // dynamic record hand-out of the walk
     u32 stack[40];
@@ -840,9 +846,9 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
 
 // One batch = up to 32 records, one per lane, held by lanes 0..n-1.  The windows of the batch are dealt to
 // the lanes 32 at a time (warp prefix sum + ballot/REDUX find the owner record of each window).
-// f(top, ord, follows) is called once per window: `top` holds the window's symbols from bit 63
+// f(top, ord, follows, owner) is called once per window: `top` holds the window's symbols from bit 63
 // down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
-// whether a next symbol exists.
+// whether a next symbol exists, `owner` the lane whose record it belongs to.
 template <class F>
 __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
@@ -869,20 +875,21 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
         if (active) {
             const u32 nwin = meta_windows(om);
             const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om));
+            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), owner);
         }
         __syncwarp();
     }
 }
 
-// returns false when the pass does not fit (table or candidate area full): the caller splits it or lists it
+// returns false when the pass does not fit (table, queue or solid area full): the caller splits it or lists it
 // for the spill path
 template <class Mem>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                SkGather gather, int w, u32 threshold, const Mem& mem, u32 cap,
-                                               u32 max_cand, bool count_only, u32 parts, u32 part, BucketCtl& ctl,
-                                               u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out,
-                                               u64 out_capacity, u64* n_solid_global) {
+                                               u32 q_cap, u32 max_solid, bool count_only, u32 parts, u32 part,
+                                               BucketCtl& ctl, u64* __restrict__ solid_keys_out,
+                                               u64* __restrict__ edge_stamp_out, u64 out_capacity,
+                                               u64* n_solid_global) {
     const u32 tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, W = T >> 5;
     const u32 kshift = 64u - 2u * (u32)w;
     const u32 n_seg = ctl.n_seg;
@@ -898,16 +905,15 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     mem.clear(cap, tid, T);
     if (tid == 0) {
         ctl.n_solid = 0;
-        ctl.n_cand = 0;
-        ctl.overflow = 0;
+        ctl.n_q = 0;
+        ctl.overflow = (u64)Mem::kMaxRec < nrec ? 1u : 0u;     // more records than a note can name
         ctl.n_distinct = 0;
-        ctl.out_pos = 0;
         ctl.next_batch = W * 32u;      // records handed out so far (the warps' first spans are 32 each)
     }
     __syncthreads();
     volatile u32* vovf = &ctl.overflow;
     const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
-    // smallest ordinal of "candidate `idx` followed by symbol c"
+    // smallest ordinal of "solid window `idx` followed by symbol c"
     auto stamp = [&](u32 idx, u32 c, u64 ord) {
         const u32 at = 4u * idx + c;
         u64 cur = mem.stamp_ld(at);
@@ -916,6 +922,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             if (old == cur) break;
             cur = old;
         }
+    };
+    auto note = [&](u32 slot, u32 rec) {
+        const u32 at = atomicAdd(&ctl.n_q, 1u);
+        if (at < q_cap) mem.q_st(at, slot, rec);
+        else *vovf = 2u;
     };
     // C. the walk.  Hand-out in RECORDS: a warp takes 32 records at a time while more than a round's worth is left
     // and GA_SK_TAIL records at a time after that, so that the last round of a bucket is not left to a third of
@@ -958,84 +969,76 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             }
         }
         ent = ent_next;
-        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows) {
+        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
             follows = follows && !count_only;
-            const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
             u32 s = __umulhi(h, cap);                      // any table size: no power of two needed
-            for (u32 probes = 0; probes <= SB_PROBE_MAX; ++probes) {
-                u64 K, A;
-                mem.ld_slot(s, K, A);
+            u32 probes = 0;
+            for (;; ++probes) {
+                if (probes > SB_PROBE_MAX) {
+                    *vovf = 1u;                            // probe limit: table full
+                    return;
+                }
+                u64 K = mem.ld_k(s);
                 if (K == GA_NONE64) {
                     K = mem.cas_k(s, GA_NONE64, key);
                     if (K == GA_NONE64) {
                         ++inserted;
-                        K = key;
-                        A = 0ull;
-                    } else if (K == key) {
-                        A = mem.ld_a(s);
+                        break;
                     }
                 }
-                if (K == key) {
-                    u32 mine = GA_NONE32;                  // candidate slot this thread allocated and still holds
-                    for (;;) {
-                        if (sa_type(A) == 2u) {            // CAND: count (saturating), then the stamp
-                            const u32 cnt = sa_count(A);
-                            if (cnt <= threshold) {
-                                const u64 old = mem.cas_a(s, A, A + (1ull << SA_CNT_SHIFT));
-                                if (old != A) {
-                                    A = old;
-                                    continue;
-                                }
-                                if (cnt == threshold) atomicAdd(&ctl.n_solid, 1u);
-                            }
-                            if (follows) stamp(sa_index(A), c, ord);
-                            break;
-                        }
-                        if (A == 0ull && threshold != 0u) {   // first occurrence: remember it in the slot
-                            const u64 old = mem.cas_a(s, 0ull, SA_FIRST | (ord << 3) | ((u64)c << 1) | (u64)follows);
-                            if (old == 0ull) break;
-                            A = old;
-                            continue;
-                        }
-                        // second occurrence (first when the threshold is 0): the window becomes a candidate
-                        if (mine == GA_NONE32) {
-                            mine = atomicAdd(&ctl.n_cand, 1u);
-                            if (mine >= max_cand) {
-                                *vovf = 1u;
-                                return;
-                            }
-                            mem.ckey_st(mine, key);
-                            mem.cslot_st(mine, s);
-                        }
-                        const bool had = sa_type(A) == 1u && (A & 1ull);
-                        const u32 c1 = (u32)(A >> 1) & 3u;
-                        const u64 ord1 = (A >> 3) & ((1ull << 48) - 1ull);
-#pragma unroll
-                        for (u32 q = 0; q < 4u; ++q) {
-                            u64 v = GA_NONE64;
-                            if (follows && q == c) v = ord;
-                            if (had && q == c1) v = min(v, ord1);
-                            mem.stamp_st(4u * mine + q, v);
-                        }
-                        __threadfence_block();
-                        const u32 cnt_new = A == 0ull ? 1u : 2u;
-                        const u64 old = mem.cas_a(s, A, SA_CAND | ((u64)cnt_new << SA_CNT_SHIFT) | (u64)mine);
-                        if (old == A) {
-                            if (cnt_new > threshold) atomicAdd(&ctl.n_solid, 1u);
-                            mine = GA_NONE32;
-                            break;
-                        }
-                        A = old;                           // somebody else moved the slot on: go again
-                    }
-                    if (mine != GA_NONE32) mem.ckey_st(mine, GA_NONE64);   // allocated, lost the race: not a candidate
-                    return;
-                }
+                if (K == key) break;
                 s = s + 1u == cap ? 0u : s + 1u;
             }
-            *vovf = 1u;                                    // probe limit: table full
+            const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
+            const u32 rec = bt + owner;
+            u32 a = mem.ld_a(s);
+            for (;;) {
+                if (a >= SA_SOLID) {                       // SOLID: the stamp, or a note while the slots are set up
+                    if (follows) {
+                        if (a != SA_PENDING) stamp(a & SA_PAYLOAD, c, ord);
+                        else note(s, rec);
+                    }
+                    return;
+                }
+                const u32 cnt = a == 0u ? 0u : (a < SA_REPEAT ? 1u : a & SA_PAYLOAD);
+                if (cnt == threshold) {                    // this occurrence takes the window above the threshold
+                    const u32 old = mem.cas_a(s, a, SA_PENDING);
+                    if (old != a) {
+                        a = old;
+                        continue;
+                    }
+                    const u32 at = atomicAdd(&ctl.n_solid, 1u);
+                    if (at >= max_solid) {
+                        *vovf = 4u;
+                        return;
+                    }
+                    mem.skey_st(at, key);
+#pragma unroll
+                    for (u32 q = 0; q < 4u; ++q) mem.stamp_st(4u * at + q, (follows && q == c) ? ord : GA_NONE64);
+                    __threadfence_block();
+                    mem.st_a(s, SA_SOLID | at);
+                    if (a >= SA_FIRST && a < SA_REPEAT && (a & SA_PAYLOAD)) note(s, (a & SA_PAYLOAD) - 1u);
+                    return;
+                }
+                if (a == 0u) {                             // first occurrence: remember its record in the slot
+                    const u32 old = mem.cas_a(s, 0u, SA_FIRST | (follows ? rec + 1u : 0u));
+                    if (old == 0u) return;
+                    a = old;
+                    continue;
+                }
+                // second .. threshold-th occurrence: count, leave a note (and move the first one to the queue)
+                const u32 old = mem.cas_a(s, a, SA_REPEAT | (cnt + 1u));
+                if (old != a) {
+                    a = old;
+                    continue;
+                }
+                if (a < SA_REPEAT && (a & SA_PAYLOAD)) note(s, (a & SA_PAYLOAD) - 1u);
+                if (follows) note(s, rec);
+                return;
+            }
         });
     }
     for (int off = 16; off > 0; off >>= 1) inserted += __shfl_down_sync(FULL, inserted, off);
@@ -1045,48 +1048,58 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u32 n_solid = ctl.n_solid;
     if (n_solid == 0) return true;
     if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
+    // D. the notes whose window ended solid: re-read the one record and fold in the stamp of every occurrence of
+    //    the window in it (a window can repeat inside a record; min is idempotent)
+    const u32 n_q = ctl.n_q;
+    for (u32 i = tid; i < n_q; i += T) {
+        u32 s, rec;
+        mem.q_ld(i, s, rec);
+        const u32 a = mem.ld_a(s);
+        if (a < SA_SOLID) continue;
+        const u32 idx = a & SA_PAYLOAD;
+        const u64 key = mem.ld_k(s);
+        ulonglong2 b;
+        u64 mt;
+        const u64 at = where(rec);
+        if (gather.index) {
+            sk_load_slot((const u64*)bases, gather.base + __ldg(gather.index + at), b, mt);
+        } else {
+            b = bases[at];
+            mt = meta[at];
+        }
+        const u32 nwin = meta_windows(mt);
+        const u64 ord0 = meta_ordinal(mt);
+        const bool has_next = meta_has_next(mt);
+        for (u32 j = 0; j < nwin; ++j) {
+            const u64 top = j ? (b.x << (2u * j)) | (b.y >> (64u - 2u * j)) : b.x;
+            if ((top >> kshift) == key && (j + 1u < nwin || has_next))
+                stamp(idx, (u32)(top >> (kshift - 2u)) & 3u, ord0 + j);
+        }
+    }
     __syncthreads();
-    // D. output: the candidates whose count ended above the threshold
+    // E. output
     const u64 base = ctl.out_base;
-    const u32 n_cand = min(ctl.n_cand, max_cand);
-    const bool room = base + n_solid <= out_capacity;
-    for (u32 i0 = 0; i0 < n_cand; i0 += T) {
-        const u32 i = i0 + tid;
-        u64 key = GA_NONE64;
-        bool solid = false;
-        if (i < n_cand) {
-            key = mem.ckey_ld(i);
-            if (key != GA_NONE64) solid = sa_count(mem.ld_a(mem.cslot_ld(i))) > threshold;
-        }
-        const u32 m = __ballot_sync(FULL, solid);
-        if (m == 0u) continue;
-        u32 at = 0;
-        if (lane == 0) at = atomicAdd(&ctl.out_pos, (u32)__popc(m));
-        at = __shfl_sync(FULL, at, 0) + (u32)__popc(m & ((1u << lane) - 1u));
-        if (solid && room) {
-            solid_keys_out[base + at] = key;
-            if (edge_stamp_out) {
-#pragma unroll
-                for (u32 q = 0; q < 4u; ++q) edge_stamp_out[4u * (base + at) + q] = mem.stamp_ld(4u * i + q);
-            }
-        }
+    if (base + n_solid <= out_capacity) {
+        for (u32 s = tid; s < n_solid; s += T) solid_keys_out[base + s] = mem.skey_ld(s);
+        if (edge_stamp_out)
+            for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = mem.stamp_ld(s);
     }
     return true;
 }
 
 // counters: [0] next bucket, [1] solid windows so far, [2] passes listed for the spill path,
-// [3] passes run | failed passes << 32, [4] distinct windows and [5] candidates over the passes that fitted (statistics)
+// [3] passes run | failed passes << 32, [4] distinct windows and [5] notes over the passes that fitted (statistics)
 // hist: per bucket, records << 32 | windows
 //
 // A bucket is done in `parts` passes (a power of two), pass `part` taking the windows whose hash
-// bits select it, so that the distinct windows and the candidates of one pass fit the CTA's pool.  parts
-// comes from running estimates of distinct / windows and candidates / windows (the first buckets of a CTA
-// start pessimistic); a pass that still does not fit is split in two; only passes that would need more
-// than 32 parts go to the spill list (entry = bucket | parts << 32 | part << 48).
+// bits select it, so that the distinct windows, the notes and the solid windows of one pass fit the CTA's pool.
+// parts comes from running estimates of the three per window of the bucket (the first buckets of a CTA start
+// pessimistic); a pass that still does not fit is split in two; only passes that would need more than 32 parts
+// (or buckets of more than 65536 records) go to the spill list (entry = bucket | parts << 32 | part << 48).
 __global__ void __launch_bounds__(SB_THREADS, SB_CTAS_PER_SM)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
                  u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
-                 u32 cand_limit,
+                 u32 solid_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
                  u64* __restrict__ spill_list, u64 spill_capacity, u32* status, const u32* __restrict__ index,
                  u64 l1_capacity, int l2_bits) {
@@ -1100,8 +1113,9 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         asm volatile("mov.u32 %0, %1;" : "=r"(pool) : "r"(raw));
     }
     if (threadIdx.x == 0) {
-        ctl.ratio_d = 1024u;
-        ctl.ratio_c = 512u;
+        ctl.ratio_d = 1280u;
+        ctl.ratio_q = 768u;
+        ctl.ratio_s = 128u;
     }
     for (;;) {
         __syncthreads();
@@ -1121,66 +1135,79 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
-        }
-        // expected distinct windows and candidates of the bucket (running ratios + a margin), and the pool one pass
-        // needs for them: 16-byte slots at a load of at most ~0.75, 42 bytes per candidate
-        const u64 est_d = (nw * ctl.ratio_d >> 12) * 17u / 16u + 48u, est_c = (nw * ctl.ratio_c >> 12) * 9u / 8u + 24u;
-        if (threadIdx.x == 0) {
+            // passes: the expected solid windows (x 2), notes (x 2.5) and distinct windows (table at a load of at
+            // most 0.6) of one pass must fit the pool (a pass that overflows anyway is split below)
+            const u64 est_d = (nw * ctl.ratio_d >> 12) + 32u, est_q = (nw * ctl.ratio_q >> 12) + 64u,
+                      est_s = (nw * ctl.ratio_s >> 12) + 16u;
             u32 parts = 1;
             while (parts < 32u) {
-                const u64 d = est_d / parts, c = est_c / parts;
-                if (d * 4u / 3u <= (u64)cap_limit && c <= (u64)cand_limit &&
-                    (d * 4u / 3u) * 16u + c * SB_CAND_BYTES <= (u64)SB_POOL_BYTES)
+                const u64 d = est_d / parts * 5u / 3u, q = est_q / parts * 5u / 2u + 256u, so = est_s / parts * 2u + 32u;
+                if (d <= (u64)cap_limit && est_s / parts <= (u64)solid_limit &&
+                    d * SB_SLOT_BYTES + q * 4u + min(so, (u64)solid_limit) * SB_SOLID_BYTES + 16u <= (u64)SB_POOL_BYTES)
                     break;
                 parts <<= 1;
             }
             for (u32 q = 0; q < parts; ++q) ctl.stack[q] = (parts << 16) | (parts - 1u - q);
             ctl.sp = parts;
+            if (run > (u64)SB_MAX_REC) {                       // a note names a record in 16 bits: straight to the spill list
+                ctl.stack[0] = 64u << 16;
+                ctl.sp = 1;
+            }
         }
         for (;;) {
             __syncthreads();
             const u32 sp = ctl.sp;
             if (sp == 0) break;
             const u32 item = ctl.stack[sp - 1];
-            const u32 rd = ctl.ratio_d, rc = ctl.ratio_c;
+            const u32 rd = ctl.ratio_d, rq = ctl.ratio_q, rs = ctl.ratio_s;
             __syncthreads();
             const u32 parts = item >> 16, part = item & 0xFFFFu;
-            // the pool of this pass: candidates for the expected number + a margin, the table gets the rest up to
-            // 2.5 x the expected distinct windows (short probe chains; more would only cost clearing time)
-            const u64 want_c = min(((nw * rc >> 12) / parts) * 5u / 4u + 48u, (u64)cand_limit);
-            u32 max_cand = (u32)min(want_c, (u64)(SB_POOL_BYTES / 2u / SB_CAND_BYTES));
-            const u64 want_d = ((nw * rd >> 12) / parts) * 5u / 2u + 128u;
-            u32 cap = (u32)min(min(want_d, (u64)cap_limit), (u64)((SB_POOL_BYTES - max_cand * SB_CAND_BYTES) / 16u));
-            if (cap < 64u) cap = 64u;
-            max_cand = min(cand_limit, (SB_POOL_BYTES - 16u * cap) / SB_CAND_BYTES);     // whatever is left
-            MemShared mem;
-            mem.slots = pool;
-            mem.ckey = pool + 16u * cap;
-            mem.cstamp = mem.ckey + 8u * max_cand;
-            mem.cslot = mem.cstamp + 32u * max_cand;
-            const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-            const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, max_cand,
-                                           edge_stamp_out == nullptr, parts, part, ctl,
-                                           solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+            bool ok = false;
+            if (parts <= 32u) {
+                // the pool of this pass: solid windows and notes for the expected numbers + a margin, the table gets
+                // the rest up to 2.5 x the expected distinct windows (short probe chains; more only costs clearing)
+                const u32 max_solid = (u32)min(min(((nw * rs >> 12) / parts) * 2u + 64u, (u64)solid_limit),
+                                               (u64)(SB_POOL_BYTES / 4u / SB_SOLID_BYTES));
+                const u32 q_cap = (u32)min(((nw * rq >> 12) / parts) * 5u / 2u + 320u, (u64)(SB_POOL_BYTES / 4u / 4u));
+                const u64 want_d = ((nw * rd >> 12) / parts) * 5u / 2u + 128u;
+                u32 cap = (u32)min(min(want_d, (u64)cap_limit),
+                                   (u64)((SB_POOL_BYTES - max_solid * SB_SOLID_BYTES - q_cap * 4u - 16u) / SB_SLOT_BYTES));
+                if (cap < 64u) cap = 64u;
+                MemShared mem;
+                mem.keys = pool;
+                mem.skeys = pool + 8u * cap;
+                mem.stamps = mem.skeys + 8u * max_solid;
+                mem.state = mem.stamps + 32u * max_solid;
+                mem.queue = mem.state + 4u * cap;
+                const SkGather gather{index, (b >> l2_bits) * l1_capacity};
+                ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, q_cap, max_solid,
+                                    edge_stamp_out == nullptr, parts, part, ctl,
+                                    solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+            }
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
                 atomicAdd((unsigned long long*)&counters[3], ok ? 1ull : (1ull << 32) + 1ull);   // passes, failed passes << 32
                 if (ok) {
                     atomicAdd((unsigned long long*)&counters[4], (unsigned long long)ctl.n_distinct);   // statistics
-                    atomicAdd((unsigned long long*)&counters[5], (unsigned long long)ctl.n_cand);
+                    atomicAdd((unsigned long long*)&counters[5], (unsigned long long)ctl.n_q);
                     // running means (weight 1/4) of what the passes actually held
                     const u32 d = (u32)min((u64)ctl.n_distinct * parts * 4096u / (nw + 1u), 4096ull);
-                    const u32 cd = (u32)min((u64)ctl.n_cand * parts * 4096u / (nw + 1u), 4096ull);
+                    const u32 q = (u32)min((u64)ctl.n_q * parts * 4096u / (nw + 1u), 8192ull);
+                    const u32 so = (u32)min((u64)ctl.n_solid * parts * 4096u / (nw + 1u), 4096ull);
                     ctl.ratio_d = (3u * rd + d + 3u) >> 2;
-                    ctl.ratio_c = (3u * rc + cd + 3u) >> 2;
+                    ctl.ratio_q = (3u * rq + q + 3u) >> 2;
+                    ctl.ratio_s = (3u * rs + so + 3u) >> 2;
                 } else if (parts < 32u && top + 2u <= 40u) {
+                    atomicAdd((unsigned long long*)&counters[ctl.overflow == 2u ? 7 : 6], ctl.overflow == 4u ? 1ull << 32 : 1ull);
                     ctl.stack[top++] = ((parts * 2u) << 16) | (part + parts);
                     ctl.stack[top++] = ((parts * 2u) << 16) | part;
                     ctl.ratio_d = min(4096u, rd + (rd >> 3) + 16u);     // mild: one odd bucket must not split the next ones
-                    ctl.ratio_c = min(4096u, rc + (rc >> 3) + 8u);
+                    ctl.ratio_q = min(8192u, rq + (rq >> 3) + 16u);
+                    ctl.ratio_s = min(4096u, rs + (rs >> 3) + 8u);
                 } else {
                     const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
-                    if (at < spill_capacity) spill_list[at] = b | ((u64)parts << 32) | ((u64)part << 48);
+                    const u32 lp = parts > 32u ? 1u : parts, lq = parts > 32u ? 0u : part;
+                    if (at < spill_capacity) spill_list[at] = b | ((u64)lp << 32) | ((u64)lq << 48);
                     else atomicOr(status, GA_ST_TABLE_FULL);
                 }
                 ctl.sp = top;
@@ -1201,11 +1228,12 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
     __shared__ BucketCtl ctl;
     MemGlobal mem;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
-    const u32 max_cand = min(cap, SA_IDX_MASK);
-    mem.slots = reinterpret_cast<u64*>(mine);
-    mem.ckey = mem.slots + 2 * (size_t)cap;
-    mem.cstamp = mem.ckey + cap;
-    mem.cslot = reinterpret_cast<u32*>(mem.cstamp + 4 * (size_t)cap);
+    // per slot: key 8, solid key 8 + 4 stamps 32, two notes 16, state 4
+    mem.keys = reinterpret_cast<u64*>(mine);
+    mem.skeys = mem.keys + cap;
+    mem.stamps = mem.skeys + cap;
+    mem.queue = mem.stamps + 4 * (size_t)cap;
+    mem.state = reinterpret_cast<u32*>(mem.queue + 2 * (size_t)cap);
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
         const u64 entry = spill_list[oi];
@@ -1224,8 +1252,9 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         }
         __syncthreads();
         const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, max_cand, edge_stamp_out == nullptr,
-                                       parts, part, ctl, solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, 2u * cap, cap,
+                                       edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
+                                       out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
     }
@@ -1425,8 +1454,8 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
 }
 
 extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
-    // 16-byte slots {key, state} + per candidate (as many as slots): key 8 B, 4 stamps 32 B, slot number 4 B
-    return (uint64_t)table_slots * (16 + 8 + 32 + 4);
+    // per slot: key 8 B + state 4 B, a solid key 8 B + 4 stamps 32 B, two 8-byte notes
+    return (uint64_t)table_slots * (8 + 4 + 8 + 32 + 16);
 }
 
 extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,

@@ -49,5 +49,5 @@ for slots in [int(v) for v in (sys.argv[1:] or [str(gd.SUPERKMER_TABLE_SLOTS)])]
         best = min(best, a.elapsed_time(b))
     c = counters.cpu().tolist()
     passes = max(c[3] & 0xFFFFFFFF, 1)
-    print("slots=%-5d %7.2f ms  solid=%d spilled=%d passes=%d failed=%d distinct/pass=%.0f cands/pass=%.0f" %
-          (slots, best, c[1], c[2], passes, c[3] >> 32, c[4] / passes, c[5] / passes), flush=True)
+    print("slots=%-5d %7.2f ms  solid=%d spilled=%d passes=%d failed=%d (table %d, queue %d, solid %d) distinct/pass=%.0f notes/pass=%.0f" %
+          (slots, best, c[1], c[2], passes, c[3] >> 32, c[6] & 0xFFFFFFFF, c[7], c[6] >> 32, c[4] / passes, c[5] / passes), flush=True)

@@ -164,8 +164,8 @@ def test_bucketed_entries_reject_bad_arguments():
     args = (ptr, ptr, ptr, 1, ptr, 4, 31, 3)
     tail = (ptr, ptr, 16, ptr, ptr, 16, ptr, None, 0, 0, None)
     assert L.ga_sk_count_build(*args, 3000, 16, *tail) == gn.GA_ERR_BAD_ARG
-    assert L.ga_sk_count_build(*args, 8192, 16, *tail) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_count_build(*args, 1 << 20, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_count_build(ptr, ptr, ptr, 1, ptr, 4, 31, 70000, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_count_build(ptr, ptr, ptr, 99, ptr, 4, 31, 3, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_resolve(None, 5, 31, ptr, 16, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
-    assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 60
+    assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 68
