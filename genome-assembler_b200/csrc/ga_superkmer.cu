@@ -694,7 +694,8 @@ constexpr u32 SB_MAX_SLOTS = 8192;             // upper bound of the table_slots
 constexpr u32 SB_PROBE_MAX = 192;
 constexpr u32 SB_SLOT_BYTES = 12;              // key 8 + state 4
 constexpr u32 SB_SOLID_BYTES = 40;             // key 8 + 4 stamps
-constexpr u32 SB_MAX_REC = 65536;              // records of a bucket a 4-byte note can name
+constexpr u32 SB_NOTE_BYTES = 8;
+constexpr u32 SB_NOTE_SPILL = 16384;           // notes per CTA in the global overflow buffer (256 KB)
 #ifndef GA_SK_TAIL
 #define GA_SK_TAIL 16
 #endif
@@ -715,7 +716,6 @@ constexpr u32 SA_PENDING = SA_SOLID | SA_PAYLOAD;
 // ---- table, queue and solid storage: shared memory (byte addresses in the shared window) or global scratch
 struct MemShared {
     u32 keys, state, queue, skeys, stamps;      // shared byte addresses
-    static constexpr u32 kMaxRec = SB_MAX_REC;
     __device__ __forceinline__ u64 ld_k(u32 s) const {
         u64 v;
         asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(keys + 8u * s));
@@ -745,14 +745,21 @@ struct MemShared {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(state + 4u * s), "r"(0u) : "memory");
         }
     }
-    __device__ __forceinline__ void q_st(u32 i, u32 slot, u32 rec) const {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(queue + 4u * i), "r"((slot << 16) | rec) : "memory");
+    __device__ __forceinline__ void ld_k2(u32 s0, u64& k0, u64& k1) const {     // slots s0 (even) and s0 + 1
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "r"(keys + 8u * s0));
     }
-    __device__ __forceinline__ void q_ld(u32 i, u32& slot, u32& rec) const {
-        u32 v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(queue + 4u * i));
-        slot = v >> 16;
-        rec = v & 0xFFFFu;
+    // notes, 8 bytes: first << 63 | slot << 49 | payload (c << 47 | ordinal, or what the FIRST state held)
+    static constexpr u32 kNoteBytes = 8;
+    __device__ __forceinline__ void q_st(u32 i, bool first, u32 slot, u64 payload) const {
+        const u64 v = ((u64)first << 63) | ((u64)slot << 49) | payload;
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(queue + 8u * i), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ void q_ld(u32 i, bool& first, u32& slot, u64& payload) const {
+        u64 v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(queue + 8u * i));
+        first = v >> 63;
+        slot = (u32)(v >> 49) & 0x3FFFu;
+        payload = v & ((1ull << 49) - 1ull);
     }
     __device__ __forceinline__ void skey_st(u32 i, u64 v) const {
         asm volatile("st.shared.u64 [%0], %1;" ::"r"(skeys + 8u * i), "l"(v) : "memory");
@@ -780,10 +787,9 @@ struct MemShared {
 struct MemGlobal {
     u64* keys;
     u32* state;
-    u64* queue;                                 // slot << 32 | record
+    u64* queue;
     u64* skeys;
     u64* stamps;
-    static constexpr u32 kMaxRec = 0xFFFFFFFFu;
     __device__ __forceinline__ u64 ld_k(u32 s) const { return ((volatile u64*)keys)[s]; }
     __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
         return atomicCAS((unsigned long long*)(keys + s), cmp, val);
@@ -797,11 +803,20 @@ struct MemGlobal {
             state[s] = 0u;
         }
     }
-    __device__ __forceinline__ void q_st(u32 i, u32 slot, u32 rec) const { queue[i] = ((u64)slot << 32) | rec; }
-    __device__ __forceinline__ void q_ld(u32 i, u32& slot, u32& rec) const {
-        const u64 v = queue[i];
-        slot = (u32)(v >> 32);
-        rec = (u32)v;
+    __device__ __forceinline__ void ld_k2(u32 s0, u64& k0, u64& k1) const {
+        k0 = ((volatile u64*)keys)[s0];
+        k1 = ((volatile u64*)keys)[s0 + 1u];
+    }
+    static constexpr u32 kNoteBytes = 16;       // tables beyond 2^14 slots: two words per note
+    __device__ __forceinline__ void q_st(u32 i, bool first, u32 slot, u64 payload) const {
+        queue[2u * (size_t)i] = ((u64)first << 63) | slot;
+        queue[2u * (size_t)i + 1u] = payload;
+    }
+    __device__ __forceinline__ void q_ld(u32 i, bool& first, u32& slot, u64& payload) const {
+        const u64 v = queue[2u * (size_t)i];
+        first = v >> 63;
+        slot = (u32)v;
+        payload = queue[2u * (size_t)i + 1u];
     }
     __device__ __forceinline__ void skey_st(u32 i, u64 v) const { skeys[i] = v; }
     __device__ __forceinline__ u64 skey_ld(u32 i) const { return skeys[i]; }
@@ -820,9 +835,14 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u32 n_distinct;
     u64 out_base;
     u32 sp;            // pending (parts << 16 | part) items of the current bucket
-    u32 ratio_d;       // running estimates, in 1/4096 of the bucket's windows: distinct windows, notes, solid windows
-    u32 ratio_q;
-    u32 ratio_s;
+    // what a bucket of x windows will hold -- distinct windows, notes, solid windows -- is predicted by a running
+    // straight-line fit y = a + b x per quantity over the buckets this CTA has done: sequencing-error windows
+    // whose minimizer was hit by the error land in a random bucket, so every bucket gets about the same number of
+    // them whatever its size, and a plain ratio over-estimates the large buckets (needless passes) and
+    // under-estimates the small ones (failed passes)
+    float mx, mxx, my[3], mxy[3];
+    u32 n_obs;
+    u32 est[3];        // the prediction for the current bucket (all its passes together)
     u32 n_seg;
     u32 next_batch;    // dynamic record hand-out of the walk
     u32 stack[40];
@@ -846,11 +866,12 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
 
 // One batch = up to 32 records, one per lane, held by lanes 0..n-1.  The windows of the batch are dealt to
 // the lanes 32 at a time (warp prefix sum + ballot/REDUX find the owner record of each window).
-// f(top, ord, follows, owner) is called once per window: `top` holds the window's symbols from bit 63
+// f(top, ord, follows, where) is called once per window: `top` holds the window's symbols from bit 63
 // down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
-// whether a next symbol exists, `owner` the lane whose record it belongs to.
+// whether a next symbol exists, `where` = (record tag + 1) << 5 | window number inside the record (the tag is
+// what finds the record again: its index entry, or its number inside the bucket in the dense form).
 template <class F>
-__device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, bool have, F&& f) {
+__device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u32 rtag, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
     const u32 npiece = have ? meta_windows(meta) : 0u;
     u32 incl = npiece;
@@ -872,10 +893,11 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
         const u32 j = x - __shfl_sync(FULL, start, owner);
         const u64 ohi = shfl64(rhi, owner), olo = shfl64(rlo, owner);
         const u64 om = shfl64(meta, owner);
+        const u32 otag = __shfl_sync(FULL, rtag, owner);
         if (active) {
             const u32 nwin = meta_windows(om);
             const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), owner);
+            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), ((otag + 1u) << 5) | j);
         }
         __syncwarp();
     }
@@ -886,7 +908,8 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, b
 template <class Mem>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                SkGather gather, int w, u32 threshold, const Mem& mem, u32 cap,
-                                               u32 q_cap, u32 max_solid, bool count_only, u32 parts, u32 part,
+                                               u32 q_cap, u64* __restrict__ q_spill, u32 q_spill_cap, u32 max_solid,
+                                               bool count_only, u32 parts, u32 part,
                                                BucketCtl& ctl, u64* __restrict__ solid_keys_out,
                                                u64* __restrict__ edge_stamp_out, u64 out_capacity,
                                                u64* n_solid_global) {
@@ -906,7 +929,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     if (tid == 0) {
         ctl.n_solid = 0;
         ctl.n_q = 0;
-        ctl.overflow = (u64)Mem::kMaxRec < nrec ? 1u : 0u;     // more records than a note can name
+        ctl.overflow = 0;
         ctl.n_distinct = 0;
         ctl.next_batch = W * 32u;      // records handed out so far (the warps' first spans are 32 each)
     }
@@ -923,10 +946,18 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
             cur = old;
         }
     };
-    auto note = [&](u32 slot, u32 rec) {
+    // notes beyond the queue's room in the pool go to this CTA's slice of a global buffer (two words each): the
+    // queue is sized from a running estimate, and one bucket with many repeated error windows must not cost a pass
+    auto note = [&](bool first, u32 slot, u64 payload) {
         const u32 at = atomicAdd(&ctl.n_q, 1u);
-        if (at < q_cap) mem.q_st(at, slot, rec);
-        else *vovf = 2u;
+        if (at < q_cap) {
+            mem.q_st(at, first, slot, payload);
+        } else if (at - q_cap < q_spill_cap) {
+            q_spill[2u * (size_t)(at - q_cap)] = ((u64)first << 63) | slot;
+            q_spill[2u * (size_t)(at - q_cap) + 1u] = payload;
+        } else {
+            *vovf = 2u;
+        }
     };
     // C. the walk.  Hand-out in RECORDS: a warp takes 32 records at a time while more than a round's worth is left
     // and GA_SK_TAIL records at a time after that, so that the last round of a bucket is not left to a third of
@@ -968,38 +999,52 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                 mt = meta[i];
             }
         }
+        const u32 ent_cur = ent;
         ent = ent_next;
-        sk_for_each_window(b.x, b.y, mt, have, [&](u64 top, u64 ord, bool follows, u32 owner) {
+        sk_for_each_window(b.x, b.y, mt, gather.index ? ent_cur : bt + lane, have,
+                           [&](u64 top, u64 ord, bool follows, u32 where_j) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
             follows = follows && !count_only;
-            u32 s = __umulhi(h, cap);                      // any table size: no power of two needed
-            u32 probes = 0;
-            for (;; ++probes) {
+            // probe two neighbouring slots at a time (one 128-bit load): half the iterations, and the warp waits
+            // for its slowest lane
+            u32 s0 = __umulhi(h, cap >> 1) << 1, s;
+            for (u32 probes = 0;; ++probes) {
                 if (probes > SB_PROBE_MAX) {
                     *vovf = 1u;                            // probe limit: table full
                     return;
                 }
-                u64 K = mem.ld_k(s);
-                if (K == GA_NONE64) {
-                    K = mem.cas_k(s, GA_NONE64, key);
-                    if (K == GA_NONE64) {
+                u64 K0, K1;
+                mem.ld_k2(s0, K0, K1);
+                if (K0 == key) {
+                    s = s0;
+                    break;
+                }
+                if (K1 == key) {
+                    s = s0 + 1u;
+                    break;
+                }
+                if (K0 == GA_NONE64 || K1 == GA_NONE64) {
+                    s = K0 == GA_NONE64 ? s0 : s0 + 1u;
+                    const u64 old = mem.cas_k(s, GA_NONE64, key);
+                    if (old == GA_NONE64) {
                         ++inserted;
                         break;
                     }
+                    if (old == key) break;
+                    continue;                              // somebody else's key landed there: look at the pair again
                 }
-                if (K == key) break;
-                s = s + 1u == cap ? 0u : s + 1u;
+                s0 = s0 + 2u >= cap ? 0u : s0 + 2u;
             }
             const u32 c = (u32)(top >> (kshift - 2u)) & 3u;
-            const u32 rec = bt + owner;
+            const u64 mine = ((u64)c << 47) | ord;         // what a note about this occurrence holds
             u32 a = mem.ld_a(s);
             for (;;) {
                 if (a >= SA_SOLID) {                       // SOLID: the stamp, or a note while the slots are set up
                     if (follows) {
                         if (a != SA_PENDING) stamp(a & SA_PAYLOAD, c, ord);
-                        else note(s, rec);
+                        else note(false, s, mine);
                     }
                     return;
                 }
@@ -1020,11 +1065,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                     for (u32 q = 0; q < 4u; ++q) mem.stamp_st(4u * at + q, (follows && q == c) ? ord : GA_NONE64);
                     __threadfence_block();
                     mem.st_a(s, SA_SOLID | at);
-                    if (a >= SA_FIRST && a < SA_REPEAT && (a & SA_PAYLOAD)) note(s, (a & SA_PAYLOAD) - 1u);
+                    if (a >= SA_FIRST && a < SA_REPEAT && (a & SA_PAYLOAD)) note(true, s, a & SA_PAYLOAD);
                     return;
                 }
-                if (a == 0u) {                             // first occurrence: remember its record in the slot
-                    const u32 old = mem.cas_a(s, 0u, SA_FIRST | (follows ? rec + 1u : 0u));
+                if (a == 0u) {                             // first occurrence: where to find it again goes in the slot
+                    const u32 old = mem.cas_a(s, 0u, SA_FIRST | (follows ? where_j : 0u));
                     if (old == 0u) return;
                     a = old;
                     continue;
@@ -1035,8 +1080,8 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                     a = old;
                     continue;
                 }
-                if (a < SA_REPEAT && (a & SA_PAYLOAD)) note(s, (a & SA_PAYLOAD) - 1u);
-                if (follows) note(s, rec);
+                if (a < SA_REPEAT && (a & SA_PAYLOAD)) note(true, s, a & SA_PAYLOAD);
+                if (follows) note(false, s, mine);
                 return;
             }
         });
@@ -1048,33 +1093,40 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u32 n_solid = ctl.n_solid;
     if (n_solid == 0) return true;
     if (tid == 0) ctl.out_base = atomicAdd((unsigned long long*)n_solid_global, (unsigned long long)n_solid);
-    // D. the notes whose window ended solid: re-read the one record and fold in the stamp of every occurrence of
-    //    the window in it (a window can repeat inside a record; min is idempotent)
+    // D. the notes whose window ended solid.  A note of the occurrence itself carries (c, ordinal); the note that
+    //    moved a FIRST state to the queue names the record and the window number: one 32-byte load.
     const u32 n_q = ctl.n_q;
     for (u32 i = tid; i < n_q; i += T) {
-        u32 s, rec;
-        mem.q_ld(i, s, rec);
+        bool first;
+        u32 s;
+        u64 payload;
+        if (i < q_cap) {
+            mem.q_ld(i, first, s, payload);
+        } else {
+            const u64 v = q_spill[2u * (size_t)(i - q_cap)];
+            first = v >> 63;
+            s = (u32)v;
+            payload = q_spill[2u * (size_t)(i - q_cap) + 1u];
+        }
         const u32 a = mem.ld_a(s);
         if (a < SA_SOLID) continue;
         const u32 idx = a & SA_PAYLOAD;
-        const u64 key = mem.ld_k(s);
+        if (!first) {
+            stamp(idx, (u32)(payload >> 47) & 3u, payload & ((1ull << 47) - 1ull));
+            continue;
+        }
+        const u32 tag = (u32)(payload >> 5) - 1u, j = (u32)payload & 31u;
         ulonglong2 b;
         u64 mt;
-        const u64 at = where(rec);
         if (gather.index) {
-            sk_load_slot((const u64*)bases, gather.base + __ldg(gather.index + at), b, mt);
+            sk_load_slot((const u64*)bases, gather.base + tag, b, mt);
         } else {
+            const u64 at = where(tag);
             b = bases[at];
             mt = meta[at];
         }
-        const u32 nwin = meta_windows(mt);
-        const u64 ord0 = meta_ordinal(mt);
-        const bool has_next = meta_has_next(mt);
-        for (u32 j = 0; j < nwin; ++j) {
-            const u64 top = j ? (b.x << (2u * j)) | (b.y >> (64u - 2u * j)) : b.x;
-            if ((top >> kshift) == key && (j + 1u < nwin || has_next))
-                stamp(idx, (u32)(top >> (kshift - 2u)) & 3u, ord0 + j);
-        }
+        const u64 top = j ? (b.x << (2u * j)) | (b.y >> (64u - 2u * j)) : b.x;
+        stamp(idx, (u32)(top >> (kshift - 2u)) & 3u, meta_ordinal(mt) + j);
     }
     __syncthreads();
     // E. output
@@ -1102,7 +1154,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                  u32 solid_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
                  u64* __restrict__ spill_list, u64 spill_capacity, u32* status, const u32* __restrict__ index,
-                 u64 l1_capacity, int l2_bits) {
+                 u64 l1_capacity, int l2_bits, u64* __restrict__ note_spill, u32 note_spill_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BucketCtl ctl;
     // keep the pool's shared address in a register: left to itself the compiler re-derives it from the
@@ -1112,11 +1164,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         const u32 raw = (u32)__cvta_generic_to_shared(smem_raw);
         asm volatile("mov.u32 %0, %1;" : "=r"(pool) : "r"(raw));
     }
-    if (threadIdx.x == 0) {
-        ctl.ratio_d = 1280u;
-        ctl.ratio_q = 768u;
-        ctl.ratio_s = 128u;
-    }
+    if (threadIdx.x == 0) ctl.n_obs = 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) ctl.bucket = (u32)min((u64)atomicAdd((unsigned long long*)&counters[0], 1ull), n_buckets);
@@ -1135,52 +1183,67 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
-            // passes: the expected solid windows (x 2), notes (x 2.5) and distinct windows (table at a load of at
-            // most 0.6) of one pass must fit the pool (a pass that overflows anyway is split below)
-            const u64 est_d = (nw * ctl.ratio_d >> 12) + 32u, est_q = (nw * ctl.ratio_q >> 12) + 64u,
-                      est_s = (nw * ctl.ratio_s >> 12) + 16u;
+            // prediction for this bucket: pessimistic ratios until the fit has seen a few buckets
+            const float x = (float)nw;
+            const float first_guess[3] = {0.32f, 0.2f, 0.03f};
+            for (int q = 0; q < 3; ++q) {
+                float y = first_guess[q] * x + 256.f;
+                if (ctl.n_obs >= 4u) {
+                    const float var = ctl.mxx - ctl.mx * ctl.mx;
+                    float bq = var > 1e-4f * ctl.mx * ctl.mx ? (ctl.mxy[q] - ctl.mx * ctl.my[q]) / var : 0.f;
+                    float aq = ctl.my[q] - bq * ctl.mx;
+                    if (bq < 0.f || aq < 0.f) {               // degenerate fit: fall back to the plain ratio
+                        bq = ctl.my[q] / fmaxf(ctl.mx, 1.f);
+                        aq = 0.f;
+                    }
+                    y = aq + bq * x;
+                }
+                ctl.est[q] = (u32)fminf(fmaxf(y, 0.f), 4.0e9f);
+            }
+            // passes: the expected solid windows (x 2), notes (x 1.25: what does not fit goes to the global note
+            // buffer) and distinct windows (table at a load of at most 0.62) of one pass must fit the pool (a pass
+            // that overflows anyway is split below)
+            const u64 est_d = (u64)ctl.est[0] + 48u, est_q = (u64)ctl.est[1] + 32u, est_s = (u64)ctl.est[2] + 16u;
             u32 parts = 1;
             while (parts < 32u) {
-                const u64 d = est_d / parts * 5u / 3u, q = est_q / parts * 5u / 2u + 256u, so = est_s / parts * 2u + 32u;
+                const u64 d = est_d / parts * 13u / 8u, q = est_q / parts * 5u / 4u + 64u, so = est_s / parts * 2u + 32u;
                 if (d <= (u64)cap_limit && est_s / parts <= (u64)solid_limit &&
-                    d * SB_SLOT_BYTES + q * 4u + min(so, (u64)solid_limit) * SB_SOLID_BYTES + 16u <= (u64)SB_POOL_BYTES)
+                    d * SB_SLOT_BYTES + q * SB_NOTE_BYTES + min(so, (u64)solid_limit) * SB_SOLID_BYTES + 32u <= (u64)SB_POOL_BYTES)
                     break;
                 parts <<= 1;
             }
             for (u32 q = 0; q < parts; ++q) ctl.stack[q] = (parts << 16) | (parts - 1u - q);
             ctl.sp = parts;
-            if (run > (u64)SB_MAX_REC) {                       // a note names a record in 16 bits: straight to the spill list
-                ctl.stack[0] = 64u << 16;
-                ctl.sp = 1;
-            }
         }
         for (;;) {
             __syncthreads();
             const u32 sp = ctl.sp;
             if (sp == 0) break;
             const u32 item = ctl.stack[sp - 1];
-            const u32 rd = ctl.ratio_d, rq = ctl.ratio_q, rs = ctl.ratio_s;
+            const u64 ed = (u64)ctl.est[0] + 48u, eq = (u64)ctl.est[1] + 32u, es = (u64)ctl.est[2] + 16u;
             __syncthreads();
             const u32 parts = item >> 16, part = item & 0xFFFFu;
             bool ok = false;
             if (parts <= 32u) {
                 // the pool of this pass: solid windows and notes for the expected numbers + a margin, the table gets
                 // the rest up to 2.5 x the expected distinct windows (short probe chains; more only costs clearing)
-                const u32 max_solid = (u32)min(min(((nw * rs >> 12) / parts) * 2u + 64u, (u64)solid_limit),
+                const u32 max_solid = (u32)min(min(es / parts * 2u + 64u, (u64)solid_limit),
                                                (u64)(SB_POOL_BYTES / 4u / SB_SOLID_BYTES));
-                const u32 q_cap = (u32)min(((nw * rq >> 12) / parts) * 5u / 2u + 320u, (u64)(SB_POOL_BYTES / 4u / 4u));
-                const u64 want_d = ((nw * rd >> 12) / parts) * 5u / 2u + 128u;
+                const u32 q_cap = (u32)min(eq / parts * 5u / 4u + 96u, (u64)(SB_POOL_BYTES / 4u / SB_NOTE_BYTES));
+                const u64 want_d = ed / parts * 5u / 2u + 128u;
                 u32 cap = (u32)min(min(want_d, (u64)cap_limit),
-                                   (u64)((SB_POOL_BYTES - max_solid * SB_SOLID_BYTES - q_cap * 4u - 16u) / SB_SLOT_BYTES));
+                                   (u64)((SB_POOL_BYTES - max_solid * SB_SOLID_BYTES - q_cap * SB_NOTE_BYTES - 32u) / SB_SLOT_BYTES));
+                cap &= ~1u;                                    // slots are probed in pairs
                 if (cap < 64u) cap = 64u;
                 MemShared mem;
                 mem.keys = pool;
                 mem.skeys = pool + 8u * cap;
                 mem.stamps = mem.skeys + 8u * max_solid;
-                mem.state = mem.stamps + 32u * max_solid;
-                mem.queue = mem.state + 4u * cap;
+                mem.queue = mem.stamps + 32u * max_solid;
+                mem.state = mem.queue + SB_NOTE_BYTES * q_cap;
                 const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-                ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, q_cap, max_solid,
+                ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, q_cap,
+                                    note_spill + 2u * (size_t)blockIdx.x * note_spill_cap, note_spill_cap, max_solid,
                                     edge_stamp_out == nullptr, parts, part, ctl,
                                     solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
             }
@@ -1190,20 +1253,25 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                 if (ok) {
                     atomicAdd((unsigned long long*)&counters[4], (unsigned long long)ctl.n_distinct);   // statistics
                     atomicAdd((unsigned long long*)&counters[5], (unsigned long long)ctl.n_q);
-                    // running means (weight 1/4) of what the passes actually held
-                    const u32 d = (u32)min((u64)ctl.n_distinct * parts * 4096u / (nw + 1u), 4096ull);
-                    const u32 q = (u32)min((u64)ctl.n_q * parts * 4096u / (nw + 1u), 8192ull);
-                    const u32 so = (u32)min((u64)ctl.n_solid * parts * 4096u / (nw + 1u), 4096ull);
-                    ctl.ratio_d = (3u * rd + d + 3u) >> 2;
-                    ctl.ratio_q = (3u * rq + q + 3u) >> 2;
-                    ctl.ratio_s = (3u * rs + so + 3u) >> 2;
+                    if (parts == 1u) {                         // a whole bucket in one pass: a clean observation for the fit
+                        const float x = (float)nw, y[3] = {(float)ctl.n_distinct, (float)ctl.n_q, (float)ctl.n_solid};
+                        const float wgt = ctl.n_obs < 8u ? 1.f / (float)(ctl.n_obs + 1u) : 0.125f;
+                        if (ctl.n_obs == 0u) ctl.mx = ctl.mxx = 0.f;
+                        ctl.mx += (x - ctl.mx) * wgt;
+                        ctl.mxx += (x * x - ctl.mxx) * wgt;
+                        for (int q = 0; q < 3; ++q) {
+                            if (ctl.n_obs == 0u) ctl.my[q] = ctl.mxy[q] = 0.f;
+                            ctl.my[q] += (y[q] - ctl.my[q]) * wgt;
+                            ctl.mxy[q] += (x * y[q] - ctl.mxy[q]) * wgt;
+                        }
+                        ++ctl.n_obs;
+                    }
                 } else if (parts < 32u && top + 2u <= 40u) {
                     atomicAdd((unsigned long long*)&counters[ctl.overflow == 2u ? 7 : 6], ctl.overflow == 4u ? 1ull << 32 : 1ull);
                     ctl.stack[top++] = ((parts * 2u) << 16) | (part + parts);
                     ctl.stack[top++] = ((parts * 2u) << 16) | part;
-                    ctl.ratio_d = min(4096u, rd + (rd >> 3) + 16u);     // mild: one odd bucket must not split the next ones
-                    ctl.ratio_q = min(8192u, rq + (rq >> 3) + 16u);
-                    ctl.ratio_s = min(4096u, rs + (rs >> 3) + 8u);
+                    // this bucket holds more than predicted: size its remaining passes for half as much again
+                    for (int q = 0; q < 3; ++q) ctl.est[q] += (ctl.est[q] >> 1) + 64u;
                 } else {
                     const u64 at = atomicAdd((unsigned long long*)&counters[2], 1ull);
                     const u32 lp = parts > 32u ? 1u : parts, lq = parts > 32u ? 0u : part;
@@ -1228,12 +1296,12 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
     __shared__ BucketCtl ctl;
     MemGlobal mem;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
-    // per slot: key 8, solid key 8 + 4 stamps 32, two notes 16, state 4
+    // per slot: key 8, solid key 8 + 4 stamps 32, two 16-byte notes, state 4
     mem.keys = reinterpret_cast<u64*>(mine);
     mem.skeys = mem.keys + cap;
     mem.stamps = mem.skeys + cap;
     mem.queue = mem.stamps + 4 * (size_t)cap;
-    mem.state = reinterpret_cast<u32*>(mem.queue + 2 * (size_t)cap);
+    mem.state = reinterpret_cast<u32*>(mem.queue + 4 * (size_t)cap);
     for (u64 oi = blockIdx.x; oi < n_spill; oi += gridDim.x) {
         __syncthreads();
         const u64 entry = spill_list[oi];
@@ -1252,7 +1320,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         }
         __syncthreads();
         const SkGather gather{index, (b >> l2_bits) * l1_capacity};
-        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, 2u * cap, cap,
+        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
                                        edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
                                        out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
@@ -1444,18 +1512,25 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
     if (max_solid > 16000) max_solid = 16000;
     const u64 most = (u64)ga_sm_count() * SB_CTAS_PER_SM;
     const unsigned grid = (unsigned)(n_buckets < most ? n_buckets : most);
+    // notes that do not fit a CTA's queue in shared memory: SB_NOTE_SPILL two-word notes per CTA, stream-ordered
+    u64* note_spill = nullptr;
+    GA_CUDA(cudaMallocAsync((void**)&note_spill, (size_t)grid * SB_NOTE_SPILL * 16u, (cudaStream_t)stream));
     sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,
         (const u64*)hist_dev, n_buckets, w,
         (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits);
-    GA_LAUNCH_CHECK("sk_bucket");
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits,
+        note_spill, SB_NOTE_SPILL);
+    ga_note_launches(1);
+    const cudaError_t launched = cudaGetLastError();
+    GA_CUDA(cudaFreeAsync(note_spill, (cudaStream_t)stream));
+    GA_CUDA(launched);
     return GA_OK;
 }
 
 extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
-    // per slot: key 8 B + state 4 B, a solid key 8 B + 4 stamps 32 B, two 8-byte notes
-    return (uint64_t)table_slots * (8 + 4 + 8 + 32 + 16);
+    // per slot: key 8 B + state 4 B, a solid key 8 B + 4 stamps 32 B, two 16-byte notes
+    return (uint64_t)table_slots * (8 + 4 + 8 + 32 + 32);
 }
 
 extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,

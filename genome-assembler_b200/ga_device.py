@@ -645,11 +645,12 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
     L = gn.lib()
     dev = bases.device
-    # the bucket kernel hands out a bucket's records through a 31-bit counter that every warp bumps once more
-    # after the last record, and hist packs records << 32 | windows with at most 32 windows per record: 2^27
-    # records keep both fields (and the hand-out counter) inside their bits
-    if n_occ >= (1 << 27) and bool((((hist >> 32) >= (1 << 27)) | (hist < 0)).any().item()):
-        raise gn.GaError("bucketed count: a bucket holds 2^27 records or more (one repeated window?)")
+    # the state word of a table slot names a record (its number inside the bucket, or its slot inside the level-1
+    # bucket) in 25 bits; that also keeps the 31-bit hand-out counter and the packed histogram inside their bits
+    if n_occ >= (1 << 25) and bool((((hist >> 32) >= (1 << 25)) | (hist < 0)).any().item()):
+        raise gn.GaError("bucketed count: a bucket holds 2^25 records or more (one repeated window?)")
+    if l1_capacity >= (1 << 25):
+        raise gn.GaError("bucketed count: level-1 buckets of 2^25 slots or more")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16

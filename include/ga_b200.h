@@ -198,8 +198,8 @@ int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capacity, const u
  * of bucket b over all segments.  index_dev != NULL selects the index form (single segment): bases_dev is
  * then records_dev of ga_sk_scatter_reads (32-byte slots; meta_dev is not used and may be NULL), offsets
  * address index_dev, and the record of entry e of bucket b is slot (b >> l2_bits) * l1_capacity + index_dev[e].
- * A bucket must hold fewer than 2^27 records (the kernel hands them out through a 31-bit counter and the
- * histogram packs records << 32 | windows; the host checks).
+ * A bucket must hold fewer than 2^25 records and l1_capacity must be below 2^25 (a table slot names a record
+ * in 25 bits; the host checks).
  * One CTA per bucket and ONE walk over its records: exact counts in a shared-memory table of at most
  * table_slots 16-byte slots {key, state} (a power of two, 256..4096); a window seen twice
  * becomes a candidate with 4 stamp slots (at most max_solid candidates per pass, bounded by what is left of

@@ -168,4 +168,4 @@ def test_bucketed_entries_reject_bad_arguments():
     assert L.ga_sk_count_build(ptr, ptr, ptr, 1, ptr, 4, 31, 70000, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_count_build(ptr, ptr, ptr, 99, ptr, 4, 31, 3, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_resolve(None, 5, 31, ptr, 16, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
-    assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 68
+    assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 84
