@@ -49,7 +49,18 @@ class IOHandler:
         """(reads, paired, distance, number of bases) from stdin; one bulk read instead of a
         ``readline`` per read, same parsing rules (assemble.py:45-71)."""
         stream = sys.stdin if stream is None else stream
-        lines = stream.read().split("\n")
+        raw = IOHandler._raw_bytes(stream)
+        if raw is not None:
+            # plain ASCII input: parsed by libga_b200 into one symbol buffer + one length per read (pinned
+            # host memory when a GPU is present) -- no Python string per read; ``reads`` decodes on demand
+            import ga_ingest
+            parsed = ga_ingest.parse(raw)
+            if parsed is not None:
+                return parsed
+            text = raw.decode(getattr(stream, "encoding", None) or "utf-8", getattr(stream, "errors", None) or "strict")
+            lines = text.replace("\r\n", "\n").replace("\r", "\n").split("\n")    # universal newlines, as text mode
+        else:
+            lines = stream.read().split("\n")
         wanted = int(lines[0].strip())
         body = lines[1:]
 
@@ -67,6 +78,22 @@ class IOHandler:
             return (reads, True, int(distance), bases)
         reads = [line(i) for i in range(count)]
         return (reads, False, 0, sum(map(len, reads)))
+
+    @staticmethod
+    def _raw_bytes(stream):
+        """The whole input as bytes when the stream can give them (stdin's buffer, a binary file object)."""
+        binary = getattr(stream, "buffer", None)
+        if binary is not None:
+            return binary.read()
+        if isinstance(stream, (bytes, bytearray)):
+            return bytes(stream)
+        mode = getattr(stream, "mode", "")
+        if isinstance(mode, str) and "b" in mode:
+            return stream.read()
+        import io
+        if isinstance(stream, io.BytesIO):
+            return stream.read()
+        return None
 
     @staticmethod
     def _report(contigs, start_time, sep):

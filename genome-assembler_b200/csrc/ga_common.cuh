@@ -187,10 +187,15 @@ struct __align__(16) StampSlot {
     u64 stamp;
 };
 // Returns the slot index (GA_NONE64 when full) after folding `stamp` in with atomicMin.
+// A table that is too small must fail fast (the caller doubles it and runs again): the probe chain is cut at
+// GA_STAMP_PROBES slots -- at the <= 50 % load the callers size for, chains stay far below that; walking a full
+// table slot by slot for every insert is what made an undersized first attempt take hundreds of milliseconds.
+#define GA_STAMP_PROBES 512ull
 __device__ __forceinline__ u64 ga_stamp_upsert(StampSlot* __restrict__ table, u64 capacity, u64 key,
                                                u64 stamp) {
     u64 s = ga_slot_of(ga_mix64(key), capacity);
-    for (u64 probes = 0; probes < capacity; ++probes) {
+    const u64 limit = capacity < GA_STAMP_PROBES ? capacity : GA_STAMP_PROBES;
+    for (u64 probes = 0; probes < limit; ++probes) {
         u64 cur = __ldcg(&table[s].key);
         if (cur == GA_NONE64) {
             u64 old = atomicCAS(&table[s].key, GA_NONE64, key);

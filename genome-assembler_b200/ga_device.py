@@ -210,20 +210,32 @@ class DeviceReads:
         gn.require_gpu()
         self.source = reads
         self.paired = bool(paired)
-        if self.paired:
-            flat = [s for pair in reads for s in (pair[0], pair[1])]
+        pinned = None
+        if type(reads).__name__ == "RawReads" and reads.paired == self.paired:
+            # raw ingest (ga_ingest.parse): the symbols already sit in one (pinned) buffer, lengths in an array
+            n = int(reads.lens.size)
+            lens = reads.lens.astype(np.int64)
+            buf = reads.symbols
+            pinned = reads._keep
         else:
-            flat = reads if isinstance(reads, list) else list(reads)
-        n = len(flat)
+            if self.paired:
+                flat = [s for pair in reads for s in (pair[0], pair[1])]
+            else:
+                flat = reads if isinstance(reads, list) else list(reads)
+            n = len(flat)
+            lens = np.fromiter(map(len, flat), dtype=np.int64, count=n)
+            try:
+                raw = "".join(flat).encode("latin-1")
+            except UnicodeEncodeError:
+                raise ValueError("reads contain characters above U+00FF; the GPU path hashes symbols "
+                                 "as single bytes and refuses to alias them") from None
+            buf = np.frombuffer(raw, dtype=np.uint8)
         self.n_reads = n
-        lens = np.fromiter(map(len, flat), dtype=np.int64, count=n)
-        try:
-            raw = "".join(flat).encode("latin-1")
-        except UnicodeEncodeError:
-            raise ValueError("reads contain characters above U+00FF; the GPU path hashes symbols "
-                             "as single bytes and refuses to alias them") from None
-        buf = np.frombuffer(raw, dtype=np.uint8)
-        self.alphabet = Alphabet(np.flatnonzero(np.bincount(buf, minlength=256)) if buf.size else np.zeros(0))
+        # raw ingest: try the DNA coding first (the packer flags any other symbol) instead of a histogram of
+        # every byte on the host; other inputs get the smallest code that separates the symbols present
+        guess_dna = pinned is not None
+        self.alphabet = Alphabet(np.zeros(0) if guess_dna or not buf.size else
+                                 np.flatnonzero(np.bincount(buf, minlength=256)))
         if self.paired and n and np.any(lens[1::2] < lens[0::2]):
             raise ValueError("paired reads: mate 2 shorter than mate 1 is not supported "
                              "(the reference would slice truncated k-mers)")
@@ -236,29 +248,39 @@ class DeviceReads:
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         uniform = n > 0 and int(lens.min()) == self.max_len
         self.uniform = uniform
-        ascii_dev = _to_device(buf) if buf.size else torch.zeros(1, dtype=torch.uint8, device=dev)
-        if uniform or n == 0:
-            self.stride_words = max(1, -(-self.max_len // spw))
-            self.words = torch.empty(max(1, n * self.stride_words), dtype=torch.int64, device=dev)
-            self.offsets = self.lengths = None
-            in_off = out_off = None
+        if pinned is not None and buf.size:
+            ascii_dev = pinned[:buf.size].to(dev, non_blocking=True)
         else:
-            words_per = -(-lens // spw)
-            off_words = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(words_per, out=off_words[1:])
-            off_bytes = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(lens, out=off_bytes[1:])
-            self.stride_words = 0
-            self.words = torch.empty(max(1, int(off_words[-1])), dtype=torch.int64, device=dev)
-            self.offsets = torch.from_numpy(off_words).to(dev)
-            self.lengths = torch.from_numpy(lens.astype(np.int32)).to(dev)
-            in_off = torch.from_numpy(off_bytes).to(dev)
-            out_off = self.offsets
-        if n:
-            gn.check(gn.lib().ga_pack_reads(
-                gn.ptr(ascii_dev), gn.ptr(in_off), n, self.max_len if uniform else 0,
-                gn.ptr(self.alphabet.lut_dev), self.alphabet.storage_bits, gn.ptr(self.words),
-                gn.ptr(out_off), self.stride_words, gn.ptr(self.status), _stream()))
+            ascii_dev = _to_device(buf) if buf.size else torch.zeros(1, dtype=torch.uint8, device=dev)
+        while True:
+            spw = 64 // self.alphabet.storage_bits
+            if uniform or n == 0:
+                self.stride_words = max(1, -(-self.max_len // spw))
+                self.words = torch.empty(max(1, n * self.stride_words), dtype=torch.int64, device=dev)
+                self.offsets = self.lengths = None
+                in_off = out_off = None
+            else:
+                words_per = -(-lens // spw)
+                off_words = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(words_per, out=off_words[1:])
+                off_bytes = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(lens, out=off_bytes[1:])
+                self.stride_words = 0
+                self.words = torch.empty(max(1, int(off_words[-1])), dtype=torch.int64, device=dev)
+                self.offsets = torch.from_numpy(off_words).to(dev)
+                self.lengths = torch.from_numpy(lens.astype(np.int32)).to(dev)
+                in_off = torch.from_numpy(off_bytes).to(dev)
+                out_off = self.offsets
+            if n:
+                gn.check(gn.lib().ga_pack_reads(
+                    gn.ptr(ascii_dev), gn.ptr(in_off), n, self.max_len if uniform else 0,
+                    gn.ptr(self.alphabet.lut_dev), self.alphabet.storage_bits, gn.ptr(self.words),
+                    gn.ptr(out_off), self.stride_words, gn.ptr(self.status), _stream()))
+            if not (guess_dna and n and _check_status(self.status) & gn.ST_BAD_SYMBOL):
+                break
+            guess_dna = False                  # not DNA after all: code the symbols that are there, pack again
+            self.status.zero_()
+            self.alphabet = Alphabet(np.flatnonzero(np.bincount(buf, minlength=256)))
         self._struct = None
 
     @classmethod

@@ -1,0 +1,74 @@
+"""Raw ingest (ga_parse_reads / ga_ingest.parse) against the text parser it replaces: same reads, kind,
+distance and base count as IOHandler.read_input's text path for every rule of SURVEY App. A-17
+(assemble.py:40-71 of the reference).  Host-only: no GPU needed."""
+import io
+
+import pytest
+
+import assemble
+import ga_ingest
+
+
+def _text_path(text: str):
+    return assemble.IOHandler.read_input(io.StringIO(text, newline=None))     # universal newlines, as sys.stdin
+
+
+CASES = [
+    "3\nACGT\nGGCA\nTTTT\n",
+    "3\nACGT\nGGCA\nTTTT",                          # no trailing newline
+    "2\r\nACGT\r\nGGCA\r\n",                        # CRLF
+    "2\rACGT\rGGCA\r",                              # lone CR (universal newlines)
+    " 2 \n  ACGT \t\n\tGG CA\x0b\n",                # white space around lines, kept inside
+    "4\nACGT\nGG\n",                                # missing lines are empty reads
+    "0\nACGT\nGGCA\n",                              # n = 0 still consumes one read
+    "1\nACGT\nGGCA\nTTTT\n",                        # trailing lines ignored
+    "2\nACGT|TTGA|125\nGGCA|CCAT|125\n",
+    "2\n ACGT|TTGA|125 \r\nGGCA|CCAT| 7 \r\n",
+    "1\nAC_GT;|x y|3\n",
+    "3\n\n\n\n",
+    "2\nnnabe_Lee;|_Lee;By_th|5\nBy_the_nam|e_name_of_|5\n",
+    "+2\nAC\nGT\n",
+]
+
+
+@pytest.mark.parametrize("text", CASES)
+def test_raw_parse_matches_text_parse(text):
+    want = _text_path(text)
+    got = ga_ingest.parse(text.encode("ascii"))
+    assert got is not None
+    reads, paired, distance, bases = got
+    assert (list(reads), paired, distance, bases) == (list(want[0]), want[1], want[2], want[3])
+    assert len(reads) == len(want[0])
+    if len(reads):
+        assert reads[0] == want[0][0] and reads[-1] == want[0][-1]
+    # the CLI entry takes the raw route when it is handed bytes
+    via_cli = assemble.IOHandler.read_input(io.BytesIO(text.encode("ascii")))
+    assert (list(via_cli[0]), via_cli[1], via_cli[2], via_cli[3]) == (list(want[0]), want[1], want[2], want[3])
+
+
+@pytest.mark.parametrize("text", ["2\nACGT|TT|1\nGGCA\n", "2\nAC|GT|1|9\nAA|CC|1\n", "3\nAC|GT|1\nAA|CC|1\n"])
+def test_raw_parse_rejects_malformed_pairs_like_the_reference(text):
+    with pytest.raises(ValueError):
+        _text_path(text)
+    with pytest.raises(ValueError):
+        ga_ingest.parse(text.encode("ascii"))
+
+
+def test_raw_parse_defers_to_text_for_what_it_does_not_cover():
+    assert ga_ingest.parse("2\nACéT\nGG\n".encode("utf-8")) is None     # not plain ASCII
+    assert ga_ingest.parse(b"two\nAC\nGG\n") is None                          # header is not an integer
+    assert ga_ingest.parse(b"") is None
+    with pytest.raises(ValueError):
+        assemble.IOHandler.read_input(io.BytesIO(b"two\nAC\nGG\n"))           # Python's own error from the text path
+    reads, paired, _, _ = assemble.IOHandler.read_input(io.BytesIO("1\nACéT\n".encode("utf-8")))
+    assert list(reads) == ["ACéT"] and not paired
+
+
+def test_raw_reads_sequence_surface():
+    reads, paired, distance, bases = ga_ingest.parse(b"3\nAAAA|CCCC|9\nGG|TT|9\nA|C|9\n")
+    assert paired and distance == 9 and bases == 14
+    assert len(reads) == 3 and reads[1] == ("GG", "TT") and reads[-1] == ("A", "C")
+    assert reads[0:2] == [("AAAA", "CCCC"), ("GG", "TT")]
+    assert [r for r in reads] == [("AAAA", "CCCC"), ("GG", "TT"), ("A", "C")]
+    with pytest.raises(IndexError):
+        reads[3]
