@@ -40,6 +40,7 @@ WORKLOADS = {
 SEED = 2026
 # algorithmic bytes per (k-1)-mer occurrence, 64-bit keys (SURVEY 8d / DESIGN.md)
 B_TOTAL = 40.0
+B_TOTAL_SKETCH = 100.0     # -c route: + d = 10 rows x (u16 RMW on update 4 B + 2 B read on estimate) per occurrence
 # per kernel: packed bases (0.35) + what the kernel itself must touch per occurrence
 B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
             "prefilter": 1.35,     # sketch cell read-modify-write (4-bit cell, counted as 1 B)
@@ -48,6 +49,9 @@ B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
             "build_tail": 22.35,   # same pass, the reads after the prefix
             # bucketed path (csrc/ga_superkmer.cu): the two base reads of the reference's two loops
             # happen in the scatter, every probe / count / stamp access in the bucket kernel
+            # -c route: the sketch is poured from the exact table (one update per DISTINCT window and row) and asked
+            # once per distinct window: SURVEY 8d charges 40 B (update) + 20 B (estimate) per OCCURRENCE
+            "sketch_update": 40.0, "select_solid": 20.0,
             "sk_scatter1": 0.7, "sk_scatter2": 0.0,
             "sk_bucket": 38.0}     # count probe + RMW 16, build probe + count read 12, stamp RMW 10
 
@@ -324,7 +328,8 @@ def run_gpu_arm(args):
         import ga_multi
         step_fn = lambda timers=None: ga_multi.sharded_step(reads, k, F, timers=timers)   # noqa: E731
     else:
-        step_fn = lambda timers=None: gd.device_step(reads, k, F, timers=timers)           # noqa: E731
+        step_fn = lambda timers=None: gd.device_step(reads, k, F, timers=timers,            # noqa: E731
+                                                     sketch_rows=10 if args.sketch else 0)
 
     def barrier():
         if world > 1:
@@ -378,16 +383,24 @@ def run_gpu_arm(args):
     alg_bytes = launch_occ * B_KERNEL.get(dominant, B_TOTAL)
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    b_total = B_TOTAL_SKETCH if args.sketch else B_TOTAL
+    traffic = measured_traffic(args.workload, dominant, launch_occ)
+    limiter = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("limiter", {}).get(dominant) \
+        if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")) else None
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic(args.workload, dominant, launch_occ),
+                "frac": achieved / peak, "traffic": traffic,
+                # `achieved` is an EQUIVALENT bandwidth (the bytes the roofline model charges per occurrence / time):
+                # what the kernel really moves through DRAM, and what ncu says holds it back, stand next to it
+                "dram_gbs_measured": traffic / (launch_ms * 1e-3) / 1e9 if traffic and launch_ms > 0 else None,
+                "limiter": limiter,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per occurrence (profiles/traffic.json) "
                                   "x occurrences of this launch",
                 "peak_source": peak_src,
                 "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": stage_ms, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_occurrence": B_KERNEL.get(dominant, B_TOTAL),
-                "whole_path": {"achieved": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9,
-                               "frac": occ_total / world * B_TOTAL / (ms_per_step * 1e-3) / 1e9 / peak,
-                               "bytes_per_occurrence": B_TOTAL}}
+                "whole_path": {"achieved": occ_total / world * b_total / (ms_per_step * 1e-3) / 1e9,
+                               "frac": occ_total / world * b_total / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "bytes_per_occurrence": b_total}}
 
     # end to end through the host-buffer entry (ASCII reads in pinned memory -> CSR on the host)
     e2e = None
@@ -428,14 +441,14 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         del ascii_dev
         for _ in range(max(1, min(args.warmup, 2))):
-            gd.host_step(pinned, n_local * mates, read_len, paired, k, F)
+            gd.host_step(pinned, n_local * mates, read_len, paired, k, F, 10 if args.sketch else 0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d2h = 0
         graph = None
         for _ in range(args.steps):
             graph = None      # drop the previous result first: its pinned CSR buffers are then reused
-            graph = gd.host_step(pinned, n_local * mates, read_len, paired, k, F)
+            graph = gd.host_step(pinned, n_local * mates, read_len, paired, k, F, 10 if args.sketch else 0)
             d2h = sum(a.nbytes for a in (graph.rowptr, graph.col, graph.indeg, graph.branching,
                                          graph.last_char, graph.keys_a))
         torch.cuda.synchronize()
@@ -443,7 +456,7 @@ def run_gpu_arm(args):
         e2e = {"value": occ_total / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(pinned.numel()),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                "input": "ASCII reads, one byte per base, in pinned host memory"}
-        if not paired:
+        if not paired and not args.sketch:
             # the same with the host buffer already in the 2-bit ingest format (reported next to e2e, not instead)
             del pinned
             packed = torch.empty(words.shape, dtype=torch.int64, pin_memory=True)

@@ -130,12 +130,14 @@ class CountMinSketch:
         """update(kmer, count) for every entry of a ga_device.KmerCounts, on the device
         (the loop of _make_sketch, debruijn_graph.py:186-187)."""
         import ga_native as gn
-        from ga_device import _stream
+        from ga_device import _stream, _timed
         self._flush()
         sk = self._struct()
-        gn.check(gn.lib().ga_sketch_update_table(gn.ptr(counts.table), counts.capacity, counts.key_words,
-                                                 counts.k, counts.alphabet.sym_bits,
-                                                 gn.ptr(counts.alphabet.inv_dev), C.byref(sk), _stream()))
+        table = counts.table                       # counts every window if that has not happened yet
+        with _timed("sketch_update", counts.n_occ):
+            gn.check(gn.lib().ga_sketch_update_table(gn.ptr(table), counts.capacity, counts.key_words,
+                                                     counts.k, counts.alphabet.sym_bits,
+                                                     gn.ptr(counts.alphabet.inv_dev), C.byref(sk), _stream()))
         self._rows_cache = None
         self.source_counts = counts
         self._check_overflow()

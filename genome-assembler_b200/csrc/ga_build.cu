@@ -465,3 +465,102 @@ extern "C" int ga_build_paired(const ga_reads* reads, int k, const void* solid_d
     GA_LAUNCH_CHECK("build_paired");
     return GA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Paired build across GPUs: every rank fills its own query / query-edge tables from its read shard
+// (ga_build_paired; stamps carry global read indices, ids come from the replicated solid table).  The
+// tables are exported as plain lists -- query-edge keys re-expressed by the two QUERY KEYS they join, because
+// slot numbers mean nothing in another rank's table -- gathered, and folded into one pair of tables with
+// min(stamp), which is what one GPU walking all reads would have built (min is associative).
+namespace {
+
+__global__ void __launch_bounds__(256)
+stamp_export_kernel(const StampSlot* __restrict__ table, u64 cap, const StampSlot* __restrict__ queries,
+                    u64* __restrict__ key_out, u64* __restrict__ key2_out, u64* __restrict__ stamp_out,
+                    u64 out_cap, u64* __restrict__ n_out) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < cap + ((32u - (cap & 31u)) & 31u);
+         i += (u64)gridDim.x * blockDim.x) {
+        const bool take = i < cap && table[i].key != GA_NONE64;
+        const u64 at = ga_warp_append(n_out, take);
+        if (!take || at >= out_cap) continue;
+        const u64 key = table[i].key;
+        if (queries) {       // a query-edge: slots of the two queries -> their keys
+            key_out[at] = queries[key >> 32].key;
+            key2_out[at] = queries[key & 0xFFFFFFFFull].key;
+        } else {
+            key_out[at] = key;
+        }
+        stamp_out[at] = table[i].stamp;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+merge_queries_kernel(const u64* __restrict__ keys, const u64* __restrict__ stamps, u64 n, StampSlot* __restrict__ queries,
+                     u64 qcap, u32* status) {
+    bool full = false;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (ga_stamp_upsert(queries, qcap, keys[i], stamps[i]) == GA_NONE64) full = true;
+    if (full) atomicOr(status, GA_ST_STAMP_FULL);
+}
+
+__global__ void __launch_bounds__(256)
+merge_qedges_kernel(const u64* __restrict__ pkeys, const u64* __restrict__ skeys, const u64* __restrict__ stamps, u64 n,
+                    const StampSlot* __restrict__ queries, u64 qcap, StampSlot* __restrict__ qedges, u64 qecap,
+                    u32* status) {
+    bool full = false;
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 qp = ga_stamp_find(queries, qcap, pkeys[i]), qs = ga_stamp_find(queries, qcap, skeys[i]);
+        if (qp == GA_NONE64 || qs == GA_NONE64 ||
+            ga_stamp_upsert(qedges, qecap, (qp << 32) | qs, stamps[i]) == GA_NONE64)
+            full = true;
+    }
+    if (full) atomicOr(status, GA_ST_STAMP_FULL);
+}
+
+}  // namespace
+
+extern "C" int ga_stamp_table_export(const void* table_dev, uint64_t capacity, const void* query_table_dev,
+                                     uint64_t* key_out_dev, uint64_t* key2_out_dev, uint64_t* stamp_out_dev,
+                                     uint64_t out_capacity, uint64_t* n_out_dev, ga_stream stream) {
+    if (!table_dev || capacity == 0 || !key_out_dev || !stamp_out_dev || !n_out_dev ||
+        (query_table_dev && !key2_out_dev)) {
+        ga_set_error("ga_stamp_table_export: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    unsigned grid = ga_grid(capacity, 256);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    stamp_export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const StampSlot*)table_dev, capacity,
+                                                                (const StampSlot*)query_table_dev, (u64*)key_out_dev,
+                                                                (u64*)key2_out_dev, (u64*)stamp_out_dev, out_capacity,
+                                                                (u64*)n_out_dev);
+    GA_LAUNCH_CHECK("stamp_table_export");
+    return GA_OK;
+}
+
+extern "C" int ga_paired_merge(const uint64_t* query_keys_dev, const uint64_t* query_stamps_dev, uint64_t n_queries,
+                               const uint64_t* edge_pkeys_dev, const uint64_t* edge_skeys_dev,
+                               const uint64_t* edge_stamps_dev, uint64_t n_edges, void* query_table_dev,
+                               uint64_t query_capacity, void* qedge_table_dev, uint64_t qedge_capacity,
+                               uint32_t* status_dev, ga_stream stream) {
+    if (!query_table_dev || !qedge_table_dev || !status_dev || query_capacity == 0 || qedge_capacity == 0 ||
+        query_capacity >= 0xFFFFFFFFull || (n_queries && (!query_keys_dev || !query_stamps_dev)) ||
+        (n_edges && (!edge_pkeys_dev || !edge_skeys_dev || !edge_stamps_dev))) {
+        ga_set_error("ga_paired_merge: bad arguments");
+        return GA_ERR_BAD_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_queries) {
+        merge_queries_kernel<<<ga_grid(n_queries, 256), 256, 0, st>>>((const u64*)query_keys_dev, (const u64*)query_stamps_dev,
+                                                                    n_queries, (StampSlot*)query_table_dev, query_capacity,
+                                                                    status_dev);
+        GA_LAUNCH_CHECK("paired_merge_queries");
+    }
+    if (n_edges) {
+        merge_qedges_kernel<<<ga_grid(n_edges, 256), 256, 0, st>>>((const u64*)edge_pkeys_dev, (const u64*)edge_skeys_dev,
+                                                                 (const u64*)edge_stamps_dev, n_edges,
+                                                                 (const StampSlot*)query_table_dev, query_capacity,
+                                                                 (StampSlot*)qedge_table_dev, qedge_capacity, status_dev);
+        GA_LAUNCH_CHECK("paired_merge_qedges");
+    }
+    return GA_OK;
+}

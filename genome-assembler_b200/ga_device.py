@@ -832,9 +832,10 @@ def _solid_keys(counts: KmerCounts, threshold: int, sketch=None):
     keys = torch.empty((max(n_max, 1), counts.key_words), dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int64, device=dev)
     sk = C.byref(sketch) if sketch is not None else None
-    gn.check(L.ga_select_solid(gn.ptr(table), capacity, counts.key_words, counts.k,
-                               counts.alphabet.sym_bits, int(threshold), sk, gn.ptr(counts.alphabet.inv_dev),
-                               gn.ptr(keys), None, gn.ptr(n_out), _stream()))
+    with _timed("select_solid", counts.n_occ):
+        gn.check(L.ga_select_solid(gn.ptr(table), capacity, counts.key_words, counts.k,
+                                   counts.alphabet.sym_bits, int(threshold), sk, gn.ptr(counts.alphabet.inv_dev),
+                                   gn.ptr(keys), None, gn.ptr(n_out), _stream()))
     if sketch is None:
         return keys, n_max           # exact filter: the summary already counted them (no sync)
     return keys, int(n_out.item())
@@ -1080,15 +1081,89 @@ def emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_c
     return graph
 
 
+def paired_tables(reads, k, solid, solid_cap, n_solid, status):
+    """This rank's query / query-edge / homopolymer tables of a paired read set (ga_build_paired), grown until
+    they fit: (queries, qedges, capacity, dh)."""
+    L = gn.lib()
+    dev = solid.device
+    free = _free_bytes()
+    cap_limit = min(0xFFFFFFF0, max(4096, int(free * 0.4) // 32))
+    cap = min(cap_limit, max(1024, 3 * n_solid))
+    while True:
+        status.zero_()
+        queries = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+        qedges = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+        dh = torch.full((256 * 256 * 2,), -1, dtype=torch.int64, device=dev)
+        with _timed("build"):
+            gn.check(L.ga_build_paired(C.byref(reads.struct()), k, gn.ptr(solid), solid_cap, gn.ptr(queries),
+                                       cap, gn.ptr(qedges), cap, gn.ptr(dh), gn.ptr(status), _stream()))
+        if not _check_status(status) & gn.ST_STAMP_FULL:
+            return queries, qedges, cap, dh
+        if cap >= cap_limit:
+            raise MemoryError("edge tables do not fit in device memory")
+        del queries, qedges
+        cap = min(cap * 2, cap_limit)
+
+
+def emit_paired(graph, solid, solid_cap, solid_keys, n_solid, kw, k, alphabet, queries, qedges, cap, dh, to_host):
+    """CSR of a paired graph from (merged) query tables; used by the multi-GPU path on rank 0."""
+    L = gn.lib()
+    dev = solid.device
+    n_nodes, n_edges, attr, plan = C.c_int64(), C.c_int64(), C.c_int64(), C.c_void_p()
+    gn.check(L.ga_csr_plan_paired(gn.ptr(solid), solid_cap, gn.ptr(solid_keys), n_solid, kw, k, alphabet.sym_bits,
+                                  gn.ptr(queries), cap, gn.ptr(qedges), cap, gn.ptr(dh), _stream(), C.byref(plan),
+                                  C.byref(n_nodes), C.byref(n_edges), C.byref(attr)))
+    try:
+        nn, ne = n_nodes.value, n_edges.value
+        rowptr = torch.empty(nn + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
+        indeg = torch.empty(max(nn, 1), dtype=torch.int32, device=dev)
+        branching = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        last_sym = torch.empty(max(nn, 1), dtype=torch.uint8, device=dev)
+        keys_a = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
+        keys_b = torch.empty((max(nn, 1), kw), dtype=torch.int64, device=dev)
+        gn.check(L.ga_csr_emit(plan, gn.ptr(rowptr), gn.ptr(col), gn.ptr(indeg), gn.ptr(branching),
+                               gn.ptr(last_sym), gn.ptr(keys_a), gn.ptr(keys_b), _stream()))
+        torch.cuda.current_stream().synchronize()
+    finally:
+        L.ga_csr_plan_free(plan)
+    graph.n_nodes, graph.n_edges, graph.num_edges_attr = nn, ne, attr.value
+    if not to_host:
+        graph.device = dict(rowptr=rowptr, col=col, indeg=indeg, branching=branching, last_sym=last_sym,
+                            keys_a=keys_a, keys_b=keys_b)
+        return graph
+    last_char = alphabet.inv_dev[last_sym[:nn].long()] if nn else last_sym[:0]
+    host = [_to_host(rowptr, nn + 1), _to_host(col, ne), _to_host(indeg, nn), _to_host(branching, nn),
+            _to_host(last_char, nn), _to_host(keys_a, nn), _to_host(keys_b, nn)]
+    torch.cuda.current_stream().synchronize()
+    graph._pinned = host
+    graph.rowptr, graph.col, graph.indeg, graph.branching, graph.last_char = (t.numpy() for t in host[:5])
+    graph.keys_a = host[5].numpy().view(np.uint64)
+    graph.keys_b = host[6].numpy().view(np.uint64)
+    return graph
+
+
 # ----------------------------------------------------------------------------------- whole path
-def device_step(reads: DeviceReads, k: int, threshold: int, timers=None):
-    """One pass of the hot path over device-resident packed reads; the CSR stays on the device."""
+def _poured_sketch(counts: KmerCounts, rows: int):
+    """The -c route (debruijn_graph.py:181-188, debug_graph.py:66-85): every distinct window's exact count
+    poured into a `rows`-row CountMinSketch (uint16 overflow checked as the reference's array('H') would)."""
+    from countminsketch import CountMinSketch
+    sketch = CountMinSketch(rows)
+    sketch.pour_counts(counts)
+    return sketch
+
+
+def device_step(reads: DeviceReads, k: int, threshold: int, timers=None, sketch_rows: int = 0):
+    """One pass of the hot path over device-resident packed reads; the CSR stays on the device.
+    sketch_rows > 0: the CountMinSketch route (exact table -> sketch -> filter on the estimate -> build)."""
     global TIMERS
     TIMERS = timers
     try:
         _mark("step begin")
         counts = KmerCounts(k, reads)
-        out = build_graph(counts, reads, threshold, to_host=False)
+        sketch = _poured_sketch(counts, sketch_rows) if sketch_rows else None
+        out = build_graph(counts, reads, threshold, to_host=False,
+                          sketch=sketch._struct() if sketch is not None else None)
         _mark("step end")
         return out
     finally:
@@ -1169,7 +1244,8 @@ def host_step_packed(words_pinned: torch.Tensor, n_reads: int, read_len: int, k:
     return build_graph(counts, reads, threshold, to_host=True)
 
 
-def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: bool, k: int, threshold: int):
+def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: bool, k: int, threshold: int,
+              sketch_rows: int = 0):
     """The same from host memory: ASCII reads (pinned) -> H2D -> pack -> count -> filter -> build ->
     CSR arrays on the host.  This is the call bench.py times as `e2e`.  Unpaired DNA streams in by
     chunks so that the copy overlaps the scatter kernel; other inputs copy first."""
@@ -1179,7 +1255,7 @@ def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: b
     probe = DeviceReads.from_packed(torch.empty(0, dtype=torch.int64, device=_dev()), n_reads, read_len, paired,
                                     estride=read_len, alphabet=alphabet)
     n_occ = probe.windows_total(k)
-    if not paired and n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(probe, k, threshold):
+    if not paired and not sketch_rows and n_occ >= SUPERKMER_MIN_OCC and superkmer_supported(probe, k, threshold):
         words = torch.empty(max(1, n_reads * stride), dtype=torch.int64, device=_dev())
         reads = DeviceReads.from_packed(words, n_reads, read_len, False, estride=read_len, alphabet=alphabet)
         counts = KmerCounts(k, reads)
@@ -1188,4 +1264,5 @@ def host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, paired: b
     counts = KmerCounts(k, reads)
     if _check_status(reads.status) & gn.ST_BAD_SYMBOL:
         raise ValueError("read symbol outside the alphabet")
-    return build_graph(counts, reads, threshold, to_host=True)
+    sketch = _poured_sketch(counts, sketch_rows) if sketch_rows else None
+    return build_graph(counts, reads, threshold, to_host=True, sketch=sketch._struct() if sketch is not None else None)

@@ -118,20 +118,33 @@ def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = Fal
     BuiltGraph whose CSR stays on the device unless to_host) and None elsewhere."""
     import ga_native as gn
     import ga_device as gd
-    if reads.paired or reads.alphabet.sym_bits > 2:
-        raise NotImplementedError("multi-GPU build currently covers unpaired reads over <= 4 symbols")
-    if threshold < 0 or (threshold + 1) * dist.get_world_size() > 255:
-        raise NotImplementedError("multi-GPU pre-filter needs 0 <= threshold and (threshold+1)*ranks <= 255")
+    if reads.alphabet.sym_bits > 2 and not reads.paired:
+        raise NotImplementedError("multi-GPU build of unpaired reads covers alphabets of <= 4 symbols")
     gd.TIMERS = timers
     try:
-        if gd.superkmer_supported(reads, k, threshold) and USE_BUCKETS:
+        if not reads.paired and gd.superkmer_supported(reads, k, threshold) and USE_BUCKETS:
             return _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed)
+        # the table route all-reduces 8-bit pre-filter cells that each rank clamps at threshold + 1
+        if threshold < 0 or (threshold + 1) * dist.get_world_size() > 255:
+            raise NotImplementedError("multi-GPU pre-filter needs 0 <= threshold and (threshold+1)*ranks <= 255")
         if feed is not None:
             for _ in feed:      # the table route walks resident reads: drain the stream first
                 pass
         return _sharded_step(reads, k, threshold, to_host, gn, gd)
     finally:
         gd.TIMERS = None
+
+
+def raise_together(error, group=None):
+    """Collective error check between phases: if any rank holds an exception, every rank raises (the failing
+    rank its own, the others a RuntimeError naming it) instead of hanging in the next collective."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    flag = torch.tensor([0 if error is None else dist.get_rank(group) + 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if error is not None:
+        raise error
+    if int(flag.item()):
+        raise RuntimeError("sharded build: rank %d failed (see its own traceback)" % (int(flag.item()) - 1))
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
@@ -311,6 +324,8 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
     gn.check(L.ga_table_clear(gn.ptr(solid), solid_cap, kw, stream()))
     gn.check(L.ga_table_insert_ids(gn.ptr(solid_keys), n_solid, kw, 0, gn.ptr(solid), solid_cap, gn.ptr(status),
                                    stream()))
+    if reads.paired:
+        return _paired_tail(reads, k, to_host, gn, gd, graph, solid, solid_cap, solid_keys, n_solid, kw)
     # 5. stamps of the local shard, then the global minimum
     stamps = torch.full((5 * n_solid,), -1, dtype=torch.int64, device=dev)
     node_stamp, edge_stamp = stamps[:n_solid], stamps[n_solid:]
@@ -323,6 +338,71 @@ def _sharded_step(reads, k, threshold, to_host, gn, gd):
     # 6. CSR on rank 0
     return gd.emit_dna4(graph, node_stamp, edge_stamp, n_solid, solid_keys, solid, solid_cap, kw, k, reads.alphabet,
                         to_host)
+
+
+def _export_stamp_table(L, gd, gn, table, cap, queries=None):
+    """Occupied slots of a query (queries=None) or query-edge table as (keys[, keys2], stamps) device lists."""
+    dev = table.device
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    room = cap
+    keys = torch.empty(room, dtype=torch.int64, device=dev)
+    keys2 = torch.empty(room, dtype=torch.int64, device=dev) if queries is not None else None
+    stamps = torch.empty(room, dtype=torch.int64, device=dev)
+    gn.check(L.ga_stamp_table_export(gn.ptr(table), cap, gn.ptr(queries), gn.ptr(keys), gn.ptr(keys2),
+                                     gn.ptr(stamps), room, gn.ptr(n_out), gd._stream()))
+    n = int(n_out.item())
+    return (keys[:n], stamps[:n]) if queries is None else (keys[:n], keys2[:n], stamps[:n])
+
+
+def _paired_tail(reads, k, to_host, gn, gd, graph, solid, solid_cap, solid_keys, n_solid, kw):
+    """Steps 5-6 for read pairs: every rank builds its query / query-edge tables from its own pairs against
+    the replicated solid table, the tables travel to rank 0 as key lists and are folded with min(stamp)
+    (ga_paired_merge); rank 0 then resolves the fuzzy node groups and emits the CSR exactly as one GPU would
+    (debruijn_graph.py:269-347)."""
+    L = gn.lib()
+    rank = dist.get_rank()
+    status = reads.status
+    error = None
+    try:
+        queries, qedges, cap, dh = gd.paired_tables(reads, k, solid, solid_cap, n_solid, status)
+        if gd._check_status(status) & (gn.ST_TABLE_FULL | gn.ST_BAD_SYMBOL):
+            raise gn.GaError("table overflow or bad symbol in the sharded build")
+        q_keys, q_stamps = _export_stamp_table(L, gd, gn, queries, cap)
+        e_pk, e_sk, e_stamps = _export_stamp_table(L, gd, gn, qedges, cap, queries)
+    except Exception as exc:            # noqa: BLE001  -- reported on every rank below
+        error = exc
+    raise_together(error)
+    del queries, qedges
+    q_keys, rows_q = gather_rows(q_keys, want_rows=True)
+    q_stamps = gather_rows(q_stamps, recv_rows=rows_q)
+    e_pk, rows_e = gather_rows(e_pk, want_rows=True)
+    e_sk = gather_rows(e_sk, recv_rows=rows_e)
+    e_stamps = gather_rows(e_stamps, recv_rows=rows_e)
+    all_dh = gather_rows(dh.view(1, -1))
+    if rank != 0:
+        return None
+    dev = solid.device
+    # the two smallest occurrences per (symbol A, symbol B) over all ranks (stamps < 2^63: signed order is fine
+    # once "none" = -1 is moved to the top)
+    world = all_dh.shape[0]
+    pairs = all_dh.view(world, -1, 2).permute(1, 0, 2).reshape(-1, 2 * world)
+    pairs = torch.where(pairs < 0, torch.full_like(pairs, (1 << 63) - 1), pairs)
+    pairs = torch.sort(pairs, dim=1).values[:, :2]
+    dh_all = torch.where(pairs == (1 << 63) - 1, torch.full_like(pairs, -1), pairs).contiguous().view(-1)
+    n_q, n_e = q_keys.shape[0], e_pk.shape[0]
+    cap = max(1024, 3 * max(n_q, n_e))
+    while True:
+        status.zero_()
+        queries = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+        qedges = torch.full((cap, 2), -1, dtype=torch.int64, device=dev)
+        gn.check(L.ga_paired_merge(gn.ptr(q_keys.contiguous()), gn.ptr(q_stamps.contiguous()), n_q,
+                                   gn.ptr(e_pk.contiguous()), gn.ptr(e_sk.contiguous()), gn.ptr(e_stamps.contiguous()),
+                                   n_e, gn.ptr(queries), cap, gn.ptr(qedges), cap, gn.ptr(status), gd._stream()))
+        if not gd._check_status(status) & gn.ST_STAMP_FULL:
+            break
+        cap *= 2
+    return gd.emit_paired(graph, solid, solid_cap, solid_keys, n_solid, kw, k, reads.alphabet, queries, qedges, cap,
+                          dh_all, to_host)
 
 
 def sharded_host_step(ascii_pinned: torch.Tensor, n_reads: int, read_len: int, first_read: int, k: int,

@@ -92,6 +92,8 @@ SIGNATURES = {
     "ga_unstamped_table_build": (_i32, [_vp, _vp, _u64, _i32, _vp, _u64, _vp, _u64, _vp, _vp]),
     "ga_build_unpaired_dna_tail": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "ga_build_paired": (_i32, [_PR, _i32, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "ga_stamp_table_export": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "ga_paired_merge": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp]),
     "ga_csr_plan_unpaired": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _u64, _vp,
                                     C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64)]),
     "ga_csr_plan_unpaired_dna": (_i32, [_vp, _vp, _u64, _vp, _i32, _i32, _i32, _vp, _u64, _vp,

@@ -303,6 +303,21 @@ int ga_build_paired(const ga_reads* reads, int k, const void* solid_dev, uint64_
                     uint64_t qedge_capacity, uint64_t* dh_dev, uint32_t* status_dev,
                     ga_stream stream);
 
+/* Paired build across GPUs (each rank runs ga_build_paired over its read shard against the same replicated solid
+ * table; stamps carry global read indices).  ga_stamp_table_export lists the occupied slots of a query table
+ * (query_table_dev == NULL: key_out = idA << 32 | idB) or of a query-edge table (query_table_dev = the rank's own
+ * query table: key_out / key2_out = the keys of the two queries the edge joins -- slot numbers do not travel);
+ * *n_out_dev (zeroed by the caller) may exceed out_capacity, nothing is written beyond it.  ga_paired_merge folds
+ * such lists (of any number of ranks) into one pair of 0xFF-filled tables with min(stamp): first every query, then
+ * the edges re-keyed by the merged table's slots.  GA_ST_STAMP_FULL in status_dev: a table was too small. */
+int ga_stamp_table_export(const void* table_dev, uint64_t capacity, const void* query_table_dev,
+                          uint64_t* key_out_dev, uint64_t* key2_out_dev, uint64_t* stamp_out_dev,
+                          uint64_t out_capacity, uint64_t* n_out_dev, ga_stream stream);
+int ga_paired_merge(const uint64_t* query_keys_dev, const uint64_t* query_stamps_dev, uint64_t n_queries,
+                    const uint64_t* edge_pkeys_dev, const uint64_t* edge_skeys_dev, const uint64_t* edge_stamps_dev,
+                    uint64_t n_edges, void* query_table_dev, uint64_t query_capacity, void* qedge_table_dev,
+                    uint64_t qedge_capacity, uint32_t* status_dev, ga_stream stream);
+
 /* ---- CSR emission in the reference's insertion order --------------------- */
 typedef struct ga_csr_plan ga_csr_plan;
 /* Both plan calls synchronise `stream` and report the graph size; ga_csr_emit then fills

@@ -39,6 +39,29 @@ def main():
             print("multi_check world=%d k=%d: nodes %d/%d edges %d/%d identical=%s" %
                   (world, k, got.n_nodes, want.n_nodes, got.n_edges, want.n_edges, same), flush=True)
             ok = ok and same and got.n_nodes > 0
+    # read pairs (table route: replicated solid set, per-rank query tables merged on rank 0)
+    for genome_size, n_pairs, read_len, k, F in ((150000, 40000, 100, 29, 3), (30000, 9001, 100, 41, 2)):
+        stride = (read_len + 31) // 32
+        genome = torch.empty(genome_size, dtype=torch.uint8, device=dev)
+        gn.check(L.ga_gen_genome(gn.ptr(genome), genome_size, 6, None))
+        lo, hi = n_pairs * rank // world, n_pairs * (rank + 1) // world
+        words = torch.empty(max(1, 2 * (hi - lo) * stride), dtype=torch.int64, device=dev)
+        gn.check(L.ga_gen_reads(gn.ptr(genome), genome_size, 2 * lo, 2 * (hi - lo), read_len, 6, 100, gn.ptr(words),
+                                stride, 1, 125, None))
+        shard = gd.DeviceReads.from_packed(words, 2 * (hi - lo), read_len, True, first_read=lo, estride=read_len)
+        got = ga_multi.sharded_step(shard, k, F, to_host=True)
+        if rank == 0:
+            allw = torch.empty(2 * n_pairs * stride, dtype=torch.int64, device=dev)
+            gn.check(L.ga_gen_reads(gn.ptr(genome), genome_size, 0, 2 * n_pairs, read_len, 6, 100, gn.ptr(allw), stride,
+                                    1, 125, None))
+            whole = gd.DeviceReads.from_packed(allw, 2 * n_pairs, read_len, True, estride=read_len)
+            want = gd.build_graph(gd.KmerCounts(k, whole), whole, F, to_host=True)
+            same = all(np.array_equal(getattr(got, f), getattr(want, f))
+                       for f in ("rowptr", "col", "indeg", "branching", "last_char", "keys_a", "keys_b"))
+            same = same and got.num_edges_attr == want.num_edges_attr
+            print("multi_check paired world=%d k=%d: nodes %d/%d edges %d/%d identical=%s" %
+                  (world, k, got.n_nodes, want.n_nodes, got.n_edges, want.n_edges, same), flush=True)
+            ok = ok and same and got.n_nodes > 0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
