@@ -52,7 +52,7 @@ B_KERNEL = {"count_full": 16.35,   # v1 full table: key probe 8 + count RMW 8
             # -c route: the sketch is poured from the exact table (one update per DISTINCT window and row) and asked
             # once per distinct window: SURVEY 8d charges 40 B (update) + 20 B (estimate) per OCCURRENCE
             "sketch_update": 40.0, "select_solid": 20.0,
-            "sk_scatter1": 0.7, "sk_scatter2": 0.0,
+            "sk_scatter1": 0.7, "sk_scatter2": 0.0, "sk_push": 0.0,
             "sk_bucket": 38.0}     # count probe + RMW 16, build probe + count read 12, stamp RMW 10
 
 
@@ -539,6 +539,8 @@ def run_gpu_arm(args):
                 "graph": {"nodes": result.n_nodes, "edges": result.n_edges} if result is not None else None}
         print(json.dumps(line))
     if world > 1:
+        import ga_multi
+        ga_multi.release_peers()           # collective: unmap and free the NVLink exchange buffers
         dist.destroy_process_group()
 
 

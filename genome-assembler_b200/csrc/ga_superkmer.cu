@@ -311,7 +311,7 @@ template <int THREADS, int BATCH>
 __global__ void __launch_bounds__(THREADS)
 sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bits, u64* __restrict__ out_rec, u64 cap1,
                                u64* __restrict__ cursors, u64* __restrict__ ghist, u32* status) {
-    __shared__ u32 bk[32][THREADS];                      // bucket of this thread's i-th record of the current chunk
+    __shared__ u32 bk[32][THREADS];                      // bucket of the record that starts at window j of this thread's chunk
     const u32 tid = threadIdx.x;
     const int bits = l1_bits + l2_bits;
     const u32 l2_mask = (1u << l2_bits) - 1u;
@@ -339,12 +339,13 @@ sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bit
                     return sk_mmer_hash(__funnelshift_r(R[j >> 4], R[(j >> 4) + 1], 2u * ((u32)j & 15u)) & mmask);
                 };
                 u32 prev = 0;
-                u32* col = &bk[0][tid];
+                // the bucket of a record start goes to row j of this thread's column: a fixed address per j (a
+                // running pointer bumped under the same predicate made every bump wait for the store before it
+                // to read its address register -- 22 % of this kernel's stall samples, profiles/r02)
                 auto window = [&](int j, u32 min_hash) {
                     const u32 bkt = sk_bucket_of(min_hash, bits);
                     if (j == 0 || bkt != prev) {
-                        *col = bkt;
-                        col += THREADS;
+                        bk[j][tid] = bkt;
                         mask |= 1u << j;
                     }
                     prev = bkt;
@@ -384,7 +385,7 @@ sk_scatter_reads_lane_kernel(ReadsView rv, int w, int m, int l1_bits, int l2_bit
                         const u32 j = (u32)__ffs(rest) - 1u;
                         rest &= rest - 1u;
                         const u32 nwin = (rest ? (u32)__ffs(rest) - 1u : nv) - j;
-                        const u32 b = bk[done + q][tid];
+                        const u32 b = bk[j][tid];
                         what[q] = j | ((nwin - 1u) << 5) | (b << 12);
                         pos[q] = atomicAdd((unsigned long long*)&cursors[(b >> l2_bits) * SK_CURSOR_STRIDE], 1ull);
                         atomicAdd((unsigned long long*)&ghist[b], (1ull << 32) | (unsigned long long)nwin);
@@ -1403,7 +1404,7 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
     // compares their records)
     const int variant = [&] {
         const char* e = getenv("GA_SK_SCATTER");
-        return !e ? (l1_bits >= 5 ? 1 : 0) : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : 1));
+        return !e ? (l1_bits >= 5 ? 1 : 0) : (!strcmp(e, "warp") ? 0 : (!strcmp(e, "lane128") ? 2 : (!strcmp(e, "lane8") ? 3 : 1)));
     }();
 #define GA_SK_ARGS \
     rv, w, m, l1_bits, l2_bits, (u64*)records_dev, l1_capacity, (u64*)l1_cursors_dev, (u64*)hist_dev, status_dev
@@ -1411,11 +1412,13 @@ extern "C" int ga_sk_scatter_reads(const ga_reads* reads, int k, int l1_bits, in
         // persistent grid: as many CTAs as fit (registers and the bucket columns in shared memory decide)
         int per_sm = 0;
         if (variant == 1) GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk_scatter_reads_lane_kernel<256, 4>, 256, 0));
+        else if (variant == 3) GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk_scatter_reads_lane_kernel<256, 8>, 256, 0));
         else GA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk_scatter_reads_lane_kernel<128, 4>, 128, 0));
-        const unsigned threads = variant == 1 ? 256 : 128;
+        const unsigned threads = variant == 2 ? 128 : 256;
         const u64 n_ctas = (rv.n_reads + threads - 1) / threads, most = (u64)ga_sm_count() * (u64)(per_sm > 0 ? per_sm : 1);
         const unsigned grid = (unsigned)(n_ctas < most ? n_ctas : most);
         if (variant == 1) sk_scatter_reads_lane_kernel<256, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
+        else if (variant == 3) sk_scatter_reads_lane_kernel<256, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
         else sk_scatter_reads_lane_kernel<128, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(GA_SK_ARGS);
     } else {
         GA_CUDA(cudaFuncSetAttribute(sk_scatter_reads_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -20,8 +20,12 @@ Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_bucke
   1. each rank cuts its read shard into super-k-mer records sorted by bucket (the bucket of a window
      depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
   2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
-     records of that range (`all_to_all_single` per record array, plus the per-bucket histograms, issued
-     asynchronously; PHASES = 2 would send a second half while the first is counted -- no gain measured);
+     records of that range.  EXCHANGE = "push" (default): the owners' receive buffers are mapped into every
+     rank over NVLink (CUDA IPC, `PeerBuffers`) and ONE kernel per rank (`ga_sk_push_records`,
+     csrc/ga_peer.cu) sorts its records by bucket and stores them straight into the owners' buffers -- no
+     dense local copy, no NCCL call on the data path (NCCL carries the 8 MB of histograms and the
+     barriers).  EXCHANGE = "nccl": the round-1 route, a dense local copy + `all_to_all_single` per record
+     array (PHASES = 2 would send a second half while the first is counted -- no gain measured);
   3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
      segment per source rank;
   4. solid keys + candidate edge stamps are gathered on rank 0, which resolves them into the CSR.
@@ -30,6 +34,7 @@ Ordinals are global (read index * stride + position), so the graph is bit-identi
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -113,6 +118,100 @@ def all_reduce_min_u64(stamps: torch.Tensor, group=None):
     return stamps
 
 
+def push_plan(matrix, rank: int):
+    """matrix[s][g] = records source rank s sends to owner g (every rank holds the same matrix).  Returns
+    (dst_start, seg_start, recv_total): dst_start[g] = row of rank g's receive arrays where THIS rank's
+    segment begins (sources are laid out in rank order), seg_start[s] = row of this rank's receive arrays
+    where source s's segment begins, recv_total = rows this rank receives."""
+    world = len(matrix)
+    dst_start = [sum(matrix[s][g] for s in range(rank)) for g in range(world)]
+    seg_start = [sum(matrix[t][rank] for t in range(s)) for s in range(world)]
+    return dst_start, seg_start, sum(matrix[s][rank] for s in range(world))
+
+
+class _RawBuffer:
+    """A device range outside torch's allocator, as far as ga_device needs one (data_ptr + device)."""
+
+    def __init__(self, address: int, device):
+        self._address, self.device = int(address), device
+
+    def data_ptr(self) -> int:
+        return self._address
+
+
+class PeerBuffers:
+    """The receive arrays of the record exchange (bases 16 B + meta 8 B per row), allocated with
+    ga_peer_alloc on every rank and mapped into every other rank with ga_peer_open.  `ensure(rows)` is
+    collective: every rank passes the same row count (the largest any rank receives), so all ranks decide
+    alike whether to reallocate; reallocation is rare (the buffers only grow)."""
+
+    def __init__(self):
+        self.rows = 0
+        self.local = None            # this rank's buffer (raw address)
+        self.mapped = []             # per rank: address of that rank's buffer in this process
+
+    def close(self):
+        import ga_native as gn
+        L = gn.lib()
+        rank = dist.get_rank()
+        torch.cuda.synchronize()
+        dist.barrier()                                   # nobody still writes into a buffer about to go
+        for g, address in enumerate(self.mapped):
+            if g != rank and address:
+                gn.check(L.ga_peer_close(C.c_void_p(address)))
+        torch.cuda.synchronize()
+        dist.barrier()                                   # every mapping is gone before the owners free
+        if self.local:
+            gn.check(L.ga_peer_free(C.c_void_p(self.local)))
+        self.rows, self.local, self.mapped = 0, None, []
+
+    def ensure(self, rows: int):
+        import ga_native as gn
+        if rows <= self.rows:
+            return
+        L = gn.lib()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self.local:
+            self.close()
+        rows = rows + rows // 16 + 1024
+        handle = (C.c_uint8 * 64)()
+        address = C.c_void_p()
+        if L.ga_peer_alloc(rows * 24, C.byref(address), handle) != gn.GA_OK:
+            torch.cuda.empty_cache()                     # the caching allocator may sit on the room
+            gn.check(L.ga_peer_alloc(rows * 24, C.byref(address), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        everyone = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine)
+        everyone = everyone.cpu().numpy().reshape(world, 64)
+        self.mapped = []
+        for g in range(world):
+            if g == rank:
+                self.mapped.append(address.value)
+                continue
+            peer = C.c_void_p()
+            raw = (C.c_uint8 * 64)(*[int(x) for x in everyone[g]])
+            gn.check(L.ga_peer_open(raw, C.byref(peer)))
+            self.mapped.append(peer.value)
+        self.local, self.rows = address.value, rows
+
+    def bases_at(self, g: int, row: int) -> int:
+        return self.mapped[g] + 16 * row
+
+    def meta_at(self, g: int, row: int) -> int:
+        return self.mapped[g] + 16 * self.rows + 8 * row
+
+
+_PEERS = {}
+
+
+def release_peers():
+    """Unmap and free the exchange buffers (collective)."""
+    for peers in _PEERS.values():
+        peers.close()
+    _PEERS.clear()
+
+
 def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = False, feed=None):
     """One pass of the hot path over this rank's read shard; returns the graph on rank 0 (a
     BuiltGraph whose CSR stays on the device unless to_host) and None elsewhere."""
@@ -122,6 +221,7 @@ def sharded_step(reads, k: int, threshold: int, timers=None, to_host: bool = Fal
         raise NotImplementedError("multi-GPU build of unpaired reads covers alphabets of <= 4 symbols")
     gd.TIMERS = timers
     try:
+        gd._mark("step begin")
         if not reads.paired and gd.superkmer_supported(reads, k, threshold) and USE_BUCKETS:
             return _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed)
         # the table route all-reduces 8-bit pre-filter cells that each rank clamps at threshold + 1
@@ -148,23 +248,20 @@ def raise_together(error, group=None):
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
+EXCHANGE = os.environ.get("GA_MULTI_EXCHANGE", "push")     # "push": one kernel over NVLink peer memory; "nccl": round 1
 PHASES = 1              # 2 cuts the exchange in two halves so that the second overlaps the counting of the first;
                         # measured on 2 and 8 B200s it gains nothing (77.2 vs 75.4 ms at N=8: the second bucket
                         # pass and its host round trip cost what the overlap saves), so one phase is the default
 
 
-def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
+def _exchange_nccl(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
+    """Round-1 exchange: dense local copy of the records in bucket order, then all_to_all_single per record
+    array.  Returns [(bases, meta, per-source hist [world, mine], seg_start, mine)] per phase."""
     dev = reads.words.device
     world, rank = dist.get_world_size(), dist.get_rank()
-    occ = torch.tensor([reads.windows_total(k)], dtype=torch.int64, device=dev)
-    dist.all_reduce(occ)
-    n_occ = int(occ.item())
-    l1_bits, l2_bits = gd.sk_geometry(n_occ)
-    n_buckets = 1 << (l1_bits + l2_bits)
-    # 1. local records sorted by bucket
     bases, meta, offsets, hist, total = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed)
-    # 2. ownership: the bucket ids are cut into PHASES halves, each half is split over the ranks, so that
-    #    the exchange of the second half runs on the NCCL stream while the first half is being counted
+    # ownership: the bucket ids are cut into PHASES halves, each half is split over the ranks, so that
+    # the exchange of the second half runs on the NCCL stream while the first half is being counted
     phases = PHASES if n_buckets >= PHASES * world else 1
     per_phase = n_buckets // phases
     bounds = [[h * per_phase + g * per_phase // world for g in range(world + 1)] for h in range(phases)]
@@ -182,7 +279,7 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     recv_cnt = recv_cnt.tolist()
     recv_rows = [[int(recv_cnt[s][h]) for s in range(world)] for h in range(phases)]
     bases2 = bases.view(-1, 2)
-    pending = []
+    received = []
     with gd._timed("exchange_issue"):
         for h in range(phases):
             lo, hi = int(cut[h][0]), int(cut[h][world])
@@ -197,33 +294,83 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
                                             output_split_sizes=[mine[h]] * world,
                                             input_split_sizes=[bounds[h][g + 1] - bounds[h][g] for g in range(world)],
                                             async_op=True)]
-            pending.append((works, got_bases, got_meta, got_hist))
+            starts = [0]
+            for rows in recv_rows[h][:-1]:
+                starts.append(starts[-1] + rows)
+            received.append((works, got_bases.view(-1), got_meta, got_hist, starts, mine[h]))
+    return received
+
+
+def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
+    """Sort + send in one kernel over NVLink peer memory (csrc/ga_peer.cu).  Same return shape as
+    _exchange_nccl, one phase."""
+    L = gn.lib()
+    dev = reads.words.device
+    world, rank = dist.get_world_size(), dist.get_rank()
+    rec, _, offsets, hist, total, index, cap1 = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed, dense=False)
+    bounds = [g * n_buckets // world for g in range(world + 1)]
+    mine = bounds[rank + 1] - bounds[rank]
+    # cut[g] = first bucket-sorted position of owner g's range, of every source: one small all-gather.  It doubles
+    # as the barrier that keeps this step's stores out of buffers a peer's previous bucket pass still reads
+    # (a rank enters it, in stream order, after its own previous step)
+    my_cut = offsets[torch.tensor(bounds, dtype=torch.int64, device=dev)].contiguous()
+    all_cut = torch.empty(world * (world + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_cut, my_cut)
+    all_cut = all_cut.view(world, world + 1).tolist()
+    matrix = [[int(all_cut[s][g + 1] - all_cut[s][g]) for g in range(world)] for s in range(world)]
+    dst_start, seg_start, _ = push_plan(matrix, rank)
+    gd._mark("multi: cut")
+    peers = _PEERS.setdefault(dev.index, PeerBuffers())
+    peers.ensure(max(sum(matrix[s][g] for s in range(world)) for g in range(world)))
+    got_hist = torch.empty(world * mine, dtype=torch.int64, device=dev)
+    work = dist.all_to_all_single(got_hist, hist, output_split_sizes=[mine] * world,
+                                  input_split_sizes=[bounds[g + 1] - bounds[g] for g in range(world)], async_op=True)
+    cut = (C.c_uint64 * (world + 1))(*[int(x) for x in all_cut[rank]])
+    dst_bases = (C.c_void_p * world)(*[peers.bases_at(g, dst_start[g]) for g in range(world)])
+    dst_meta = (C.c_void_p * world)(*[peers.meta_at(g, dst_start[g]) for g in range(world)])
+    with gd._timed("sk_push", reads.windows_total(k)):
+        gn.check(L.ga_sk_push_records(gn.ptr(rec), cap1, gn.ptr(index), gn.ptr(offsets), l1_bits, l2_bits, world,
+                                      cut, dst_bases, dst_meta, gd._stream()))
+    # every rank's stores have landed before anybody counts: a one-word all-reduce, stream-ordered after the push
+    done = torch.zeros(1, dtype=torch.int32, device=dev)
+    barrier = dist.all_reduce(done, async_op=True)
+    return [([work, barrier], _RawBuffer(peers.bases_at(rank, 0), dev), _RawBuffer(peers.meta_at(rank, 0), dev),
+             got_hist, seg_start, mine)]
+
+
+def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
+    dev = reads.words.device
+    world, rank = dist.get_world_size(), dist.get_rank()
+    occ = torch.tensor([reads.windows_total(k)], dtype=torch.int64, device=dev)
+    dist.all_reduce(occ)
+    n_occ = int(occ.item())
+    l1_bits, l2_bits = gd.sk_geometry(n_occ)
+    n_buckets = 1 << (l1_bits + l2_bits)
+    # 1. local records by bucket, 2. every bucket's records to its owner
+    exchange = _exchange_push if (EXCHANGE == "push" and dist.get_backend() == "nccl") else _exchange_nccl
+    received = exchange(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd)
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
     key_parts, stamp_parts = [], []
-    for h in range(phases):
-        works, got_bases, got_meta, got_hist = pending[h]
+    for h, (works, got_bases, got_meta, got_hist, starts, mine) in enumerate(received):
         for wk in works:
             wk.wait()                  # orders the current stream after the transfer; the host does not block
         gd._mark("multi: exchange %d" % h)
-        if not mine[h]:
+        if not mine:
             continue
         # 3. one segment per source rank: positions from the per-source record counts
-        per_source = got_hist.view(world, mine[h])
-        seg_offsets = torch.zeros((world, mine[h] + 1), dtype=torch.int64, device=dev)
+        per_source = got_hist.view(world, mine)
+        seg_offsets = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
         seg_offsets[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
-        starts = [0]
-        for rows in recv_rows[h][:-1]:
-            starts.append(starts[-1] + rows)
         seg_offsets += torch.tensor(starts, dtype=torch.int64, device=dev).view(world, 1)
         summed = per_source.sum(dim=0).contiguous()
         n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
         solid_keys, n_solid, edge_stamp = gd.sk_bucket_pass(
-            got_bases.view(-1), got_meta, seg_offsets.contiguous(), world, summed, mine[h], k, threshold,
+            got_bases, got_meta, seg_offsets.contiguous(), world, summed, mine, k, threshold,
             max(n_occ_mine, 1), reads.status)
         # the pass reuses its output workspace: keep this phase's (small) result
         key_parts.append(solid_keys[:n_solid].clone())
         stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4).clone())
-    del bases, meta, bases2
+    del received
     if key_parts:
         solid_keys, edge_stamp = torch.cat(key_parts), torch.cat(stamp_parts)
     else:

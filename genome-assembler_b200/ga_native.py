@@ -81,6 +81,11 @@ SIGNATURES = {
     "ga_sk_count_build_spill": (_i32, [_vp, _vp, _vp, _u32, _u64, _vp, _u64, _i32, _i64, _u32, _vp, _u32, _vp, _vp, _u64, _vp, _vp,
                                        _vp, _u64, _i32, _vp]),
     "ga_sk_resolve": (_i32, [_vp, _u64, _i32, _vp, _u64, _vp, _vp, _vp]),
+    "ga_peer_alloc": (_i32, [_u64, C.POINTER(_vp), _vp]),
+    "ga_peer_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "ga_peer_close": (_i32, [_vp]),
+    "ga_peer_free": (_i32, [_vp]),
+    "ga_sk_push_records": (_i32, [_vp, _u64, _vp, _vp, _i32, _i32, _u32, _vp, _vp, _vp, _vp]),
     "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
     "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
     "ga_sketch_estimate_bytes": (_i32, [_vp, _vp, _u64, _PS, _vp, _vp]),

@@ -346,6 +346,31 @@ int ga_csr_emit(ga_csr_plan* plan, int32_t* rowptr_dev, int32_t* col_dev, int32_
                 void* node_keys_b_dev, ga_stream stream);
 void ga_csr_plan_free(ga_csr_plan* plan);
 
+/* ---- multi-GPU record exchange over NVLink peer memory ("k-mers routed to their owning GPU by a
+ *      hash-partition all-to-all over NVLink"; the reference is single-process, debruijn_graph.py:113-152 is what
+ *      every rank's share must add up to) -------------------------------------------------------------------- */
+#define GA_PEER_MAX_RANKS 16
+#define GA_PEER_HANDLE_BYTES 64
+/* A receive buffer other processes of this node can map: cudaMalloc + CUDA IPC handle (64 opaque HOST bytes
+ * written to handle_out; ship them to the peers by any means).  ga_peer_open maps a peer's buffer into this
+ * process (peer access over NVLink is enabled on demand); ga_peer_close unmaps it; ga_peer_free releases the
+ * owner's allocation once every peer has closed it.  All four synchronise the device. */
+int ga_peer_alloc(uint64_t bytes, void** ptr_out, void* handle_out);
+int ga_peer_open(const void* handle, void** ptr_out);
+int ga_peer_close(void* ptr);
+int ga_peer_free(void* ptr);
+/* Sort + send in one kernel.  Input: the index form of ga_sk_scatter_buckets (records_dev = 32-byte slots of
+ * ga_sk_scatter_reads, index_dev, offsets_dev over all 2^(l1_bits+l2_bits) buckets).  cut[world+1] (HOST):
+ * bucket-sorted positions [cut[g], cut[g+1]) belong to rank g (cut[g] = offsets[first bucket of rank g]).
+ * dst_bases[g] / dst_meta[g] (HOST arrays of device pointers, local or ga_peer_open'ed): where this rank's
+ * segment starts in rank g's receive arrays (16 bytes of bases and one meta word per record, the dense
+ * form ga_sk_count_build reads with one segment per source rank).  The caller orders the kernel after every
+ * peer has finished reading its buffer, and the peers' reads after this kernel, with stream-ordered
+ * collectives (a barrier on either side). */
+int ga_sk_push_records(const void* records_dev, uint64_t l1_capacity, const uint32_t* index_dev,
+                       const uint64_t* offsets_dev, int l1_bits, int l2_bits, uint32_t world,
+                       const uint64_t* cut, void* const* dst_bases, void* const* dst_meta, ga_stream stream);
+
 /* ---- raw ingest (replaces IOHandler.read_input, assemble.py:40-71) --------------------------------------- */
 /* HOST pointers.  Parses the bytes of stdin with the reference's rules (first line = number of reads n;
  * max(n, 1) read lines, each stripped; "read" or "read1|read2|distance", the kind decided by the first read

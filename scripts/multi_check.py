@@ -20,7 +20,13 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     L = gn.lib()
     ok = True
-    for genome_size, n_reads, read_len, k, F in ((200000, 60000, 100, 31, 3), (50000, 30011, 150, 41, 2)):
+    # unpaired: the bucketed route with both exchanges (one kernel over NVLink peer memory; dense copy + NCCL
+    # all-to-all), a case large enough for several level-1 buckets, and the k > 32 table route
+    for genome_size, n_reads, read_len, k, F, exchange in ((200000, 60000, 100, 31, 3, "push"),
+                                                           (200000, 60000, 100, 31, 3, "nccl"),
+                                                           (3000000, 1500003, 150, 31, 3, "push"),
+                                                           (50000, 30011, 150, 41, 2, "push")):
+        ga_multi.EXCHANGE = exchange
         stride = (read_len + 31) // 32
         genome = torch.empty(genome_size, dtype=torch.uint8, device=dev)
         gn.check(L.ga_gen_genome(gn.ptr(genome), genome_size, 5, None))
@@ -36,8 +42,8 @@ def main():
             want = gd.build_graph(gd.KmerCounts(k, whole), whole, F, to_host=True)
             same = all(np.array_equal(getattr(got, f), getattr(want, f))
                        for f in ("rowptr", "col", "indeg", "branching", "last_char", "keys_a"))
-            print("multi_check world=%d k=%d: nodes %d/%d edges %d/%d identical=%s" %
-                  (world, k, got.n_nodes, want.n_nodes, got.n_edges, want.n_edges, same), flush=True)
+            print("multi_check world=%d k=%d reads=%d exchange=%s: nodes %d/%d edges %d/%d identical=%s" %
+                  (world, k, n_reads, exchange, got.n_nodes, want.n_nodes, got.n_edges, want.n_edges, same), flush=True)
             ok = ok and same and got.n_nodes > 0
     # read pairs (table route: replicated solid set, per-rank query tables merged on rank 0)
     for genome_size, n_pairs, read_len, k, F in ((150000, 40000, 100, 29, 3), (30000, 9001, 100, 41, 2)):
@@ -64,6 +70,7 @@ def main():
             ok = ok and same and got.n_nodes > 0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
+    ga_multi.release_peers()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

@@ -65,6 +65,21 @@ def _worker(rank, world, port, results):
             stamps[0], stamps[2], stamps[3] = 3, 9, 6
         ga_multi.all_reduce_min_u64(stamps)
         assert stamps.tolist() == [3, 1 << 40, 9, 5, -1, -1]
+
+        # bookkeeping of the NVLink push exchange: every rank derives, from the all-gathered cut matrix, where its
+        # segment starts in each owner's receive arrays; the owners' own view of the segments must agree
+        my_cut = torch.tensor([0, 5 + rank, 5 + rank + 3 * (rank + 1)], dtype=torch.int64)   # rows for owner 0, owner 1
+        all_cut = torch.empty(world * (world + 1), dtype=torch.int64)
+        dist.all_gather_into_tensor(all_cut, my_cut)
+        all_cut = all_cut.view(world, world + 1).tolist()
+        matrix = [[all_cut[s][g + 1] - all_cut[s][g] for g in range(world)] for s in range(world)]
+        assert matrix == [[5, 3], [6, 6]]
+        dst_start, seg_start, recv_total = ga_multi.push_plan(matrix, rank)
+        assert recv_total == (11 if rank == 0 else 9)
+        told = torch.empty(world, dtype=torch.int64)           # told[s] = where source s says its segment starts here
+        dist.all_to_all_single(told, torch.tensor(dst_start, dtype=torch.int64))
+        assert told.tolist() == seg_start
+        assert seg_start[0] == 0 and seg_start[1] == matrix[0][rank]
         results[rank] = "ok"
     except Exception as exc:      # noqa: BLE001
         results[rank] = repr(exc)
