@@ -376,6 +376,11 @@ def run_gpu_arm(args):
         if name != "step begin":
             stage_ms[name] = stage_ms.get(name, 0.0) + ev0.elapsed_time(ev1) / args.steps
     kernel_ms = {name: sum(a.elapsed_time(b) for a, b, _ in spans) / args.steps for name, spans in timers.items()}
+    per_rank = None
+    if world > 1:       # every rank's own kernel and stage times (rank 0 alone runs the serial tail; the others wait for it)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"kernel_ms": {a: round(b, 2) for a, b in kernel_ms.items()},
+                                          "stage_ms": {a: round(b, 2) for a, b in stage_ms.items()}})
     dominant = max(kernel_ms, key=kernel_ms.get)
     spans = timers[dominant]
     launch_ms = sum(a.elapsed_time(b) for a, b, _ in spans) / len(spans)
@@ -396,7 +401,7 @@ def run_gpu_arm(args):
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per occurrence (profiles/traffic.json) "
                                   "x occurrences of this launch",
                 "peak_source": peak_src,
-                "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": stage_ms, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
+                "kernel_ms_per_step": kernel_ms, "stage_ms_per_step": stage_ms, "per_rank": per_rank, "launch_ms": launch_ms, "launches_per_step": len(spans) / args.steps,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_occurrence": B_KERNEL.get(dominant, B_TOTAL),
                 "whole_path": {"achieved": occ_total / world * b_total / (ms_per_step * 1e-3) / 1e9,
                                "frac": occ_total / world * b_total / (ms_per_step * 1e-3) / 1e9 / peak,

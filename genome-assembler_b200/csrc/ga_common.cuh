@@ -37,6 +37,7 @@ int ga_cuda_fail(cudaError_t e, const char* what);
         cudaError_t _e = (call);                                  \
         if (_e != cudaSuccess) return ga_cuda_fail(_e, #call);    \
     } while (0)
+void ga_pool_retain();          // default memory pool of the current device keeps freed blocks (call before cudaMallocAsync)
 void ga_note_launches(int n);   // counts this library's own kernel launches (ga_launch_count)
 #define GA_LAUNCH_CHECK(name)        \
     do {                             \

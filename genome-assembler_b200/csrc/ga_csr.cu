@@ -30,27 +30,13 @@ struct ga_csr_plan {
 
 namespace {
 
-// The stream-ordered pool gives memory back to the driver at every synchronisation unless told
-// otherwise; re-mapping a few hundred MB per pass costs far more than the kernels.
-static void keep_pool_warm() {
-    static bool done[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done[dev] = true;
-}
-
 struct Scratch {
     cudaStream_t st;
     std::vector<void*>* keep;   // allocations that outlive the call (owned by the plan)
     std::vector<void*> temp;    // freed when the call ends
     cudaError_t err = cudaSuccess;
     template <class T> T* get(u64 n, bool persistent = false) {
-        keep_pool_warm();
+        ga_pool_retain();
         void* p = nullptr;
         cudaError_t e = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
         if (e != cudaSuccess) {
@@ -68,10 +54,12 @@ struct Scratch {
 
 
 // (stamp, id) of every node that was touched by an accepted occurrence
+// counter[0] = nodes taken; counter[2] = largest stamp taken (the radix sort then skips the all-zero high digits)
 __global__ void compact_nodes_kernel(const u64* __restrict__ node_stamp, u64 n, u64* __restrict__ stamps,
                                      u32* __restrict__ ids, u64* counter) {
     u64 step = (u64)gridDim.x * blockDim.x;
     u64 rounds = (n + step - 1) / step;
+    u64 top = 0;
     for (u64 it = 0; it < rounds; ++it) {
         u64 i = it * step + blockIdx.x * (u64)blockDim.x + threadIdx.x;
         u64 s = i < n ? node_stamp[i] : GA_NONE64;
@@ -80,8 +68,21 @@ __global__ void compact_nodes_kernel(const u64* __restrict__ node_stamp, u64 n, 
         if (take) {
             stamps[pos] = s;
             ids[pos] = (u32)i;
+            top = max(top, s);
         }
     }
+    for (int off = 16; off > 0; off >>= 1) {
+        const u32 lo = __shfl_down_sync(0xFFFFFFFFu, (u32)top, off), hi = __shfl_down_sync(0xFFFFFFFFu, (u32)(top >> 32), off);
+        top = max(top, ((u64)hi << 32) | lo);
+    }
+    if ((threadIdx.x & 31) == 0 && top) atomicMax((unsigned long long*)(counter + 2), (unsigned long long)top);
+}
+
+// bits a radix sort has to look at for keys <= top (whole digits of 8 bits)
+int key_bits(u64 top) {
+    int bits = 8;
+    while (bits < 64 && (top >> bits)) bits += 8;
+    return bits;
 }
 
 __global__ void count_slots_kernel(const StampSlot* __restrict__ t, u64 cap, u64* counter) {
@@ -368,16 +369,15 @@ __global__ void remap_edges_kernel(const StampSlot* __restrict__ qe, u64 qecap, 
 }
 
 template <class KeyT, class ValT>
-cudaError_t sort_pairs(Scratch& sc, const KeyT* kin, KeyT* kout, const ValT* vin, ValT* vout, u64 n) {
+cudaError_t sort_pairs(Scratch& sc, const KeyT* kin, KeyT* kout, const ValT* vin, ValT* vout, u64 n,
+                       int end_bit = (int)(8 * sizeof(KeyT))) {
     if (n == 0) return cudaSuccess;
     size_t bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (long long)n, 0,
-                                                   (int)(8 * sizeof(KeyT)), sc.st);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (long long)n, 0, end_bit, sc.st);
     if (e != cudaSuccess) return e;
     void* tmp = sc.get<u8>(bytes);
     if (!tmp) return sc.err;
-    return cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (long long)n, 0,
-                                           (int)(8 * sizeof(KeyT)), sc.st);
+    return cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (long long)n, 0, end_bit, sc.st);
 }
 
 cudaError_t exclusive_sum(Scratch& sc, const int* in, int* out, u64 n) {
@@ -554,18 +554,18 @@ extern "C" int ga_csr_plan_unpaired(const uint64_t* node_stamp_dev, uint64_t n_s
     Scratch sc{plan->stream, &plan->owned};
     cudaStream_t st = plan->stream;
 
-    u64* counters = sc.get<u64>(2);
+    u64* counters = sc.get<u64>(3);
     u64* stamps0 = sc.get<u64>(n_solid);
     u32* ids0 = sc.get<u32>(n_solid);
     GA_NEED(counters); GA_NEED(stamps0); GA_NEED(ids0);
-    GA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(u64), st));
+    GA_TRY(cudaMemsetAsync(counters, 0, 3 * sizeof(u64), st));
     if (n_solid)
         compact_nodes_kernel<<<scan_grid(n_solid), 256, 0, st>>>((const u64*)node_stamp_dev, n_solid, stamps0, ids0, counters);
     ga_note_launches(1);
     count_slots_kernel<<<scan_grid(edge_capacity), 256, 0, st>>>(plan->etable, edge_capacity, counters + 1);
     ga_note_launches(1);
     GA_TRY(cudaGetLastError());
-    u64 host[2];
+    u64 host[3];
     GA_TRY(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
     GA_TRY(cudaStreamSynchronize(st));
     const u64 nn = host[0];
@@ -573,7 +573,7 @@ extern "C" int ga_csr_plan_unpaired(const uint64_t* node_stamp_dev, uint64_t n_s
     plan->node_a = sc.get<u32>(nn, true);
     plan->rank = sc.get<u32>(n_solid, true);
     GA_NEED(stamps1); GA_NEED(plan->node_a); GA_NEED(plan->rank);
-    GA_TRY((sort_pairs<u64, u32>(sc, stamps0, stamps1, ids0, plan->node_a, nn)));
+    GA_TRY((sort_pairs<u64, u32>(sc, stamps0, stamps1, ids0, plan->node_a, nn, key_bits(host[2]))));
     if (nn) scatter_rank_kernel<<<scan_grid(nn), 256, 0, st>>>(plan->node_a, nn, plan->rank);
     ga_note_launches(1);
     GA_TRY(cudaGetLastError());
@@ -607,18 +607,18 @@ extern "C" int ga_csr_plan_unpaired_dna(const uint64_t* node_stamp_dev, const ui
     plan->w = k - 1;
     Scratch sc{plan->stream, &plan->owned};
     cudaStream_t st = plan->stream;
-    u64* counters = sc.get<u64>(2);
+    u64* counters = sc.get<u64>(3);
     u64* stamps0 = sc.get<u64>(n_solid);
     u32* ids0 = sc.get<u32>(n_solid);
     GA_NEED(counters); GA_NEED(stamps0); GA_NEED(ids0);
-    GA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(u64), st));
+    GA_TRY(cudaMemsetAsync(counters, 0, 3 * sizeof(u64), st));
     if (n_solid) {
         compact_nodes_kernel<<<scan_grid(n_solid), 256, 0, st>>>((const u64*)node_stamp_dev, n_solid, stamps0, ids0, counters);
         count_stamps_kernel<<<scan_grid(4 * n_solid), 256, 0, st>>>((const u64*)edge_stamp_dev, 4 * n_solid, counters + 1);
         ga_note_launches(2);
     }
     GA_TRY(cudaGetLastError());
-    u64 host[2];
+    u64 host[3];
     GA_TRY(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
     GA_TRY(cudaStreamSynchronize(st));
     const u64 nn = host[0];
@@ -626,7 +626,7 @@ extern "C" int ga_csr_plan_unpaired_dna(const uint64_t* node_stamp_dev, const ui
     plan->node_a = sc.get<u32>(nn, true);
     plan->rank = sc.get<u32>(n_solid, true);
     GA_NEED(stamps1); GA_NEED(plan->node_a); GA_NEED(plan->rank);
-    GA_TRY((sort_pairs<u64, u32>(sc, stamps0, stamps1, ids0, plan->node_a, nn)));
+    GA_TRY((sort_pairs<u64, u32>(sc, stamps0, stamps1, ids0, plan->node_a, nn, key_bits(host[2]))));
     if (nn) scatter_rank_kernel<<<scan_grid(nn), 256, 0, st>>>(plan->node_a, nn, plan->rank);
     ga_note_launches(1);
     GA_TRY(cudaGetLastError());

@@ -31,6 +31,23 @@ int ga_cuda_fail(cudaError_t e, const char* what) {
     return GA_ERR_CUDA;
 }
 
+// The stream-ordered allocator (cudaMallocAsync: CSR scratch, note overflow buffer, scan tiles) returns freed
+// memory to the driver at every synchronisation unless the pool is told to keep it; re-creating hundreds of MB
+// of mappings every step costs milliseconds of host time per call.  Once per device.
+void ga_pool_retain() {
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (done.load(std::memory_order_relaxed) & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
 extern "C" int ga_version(void) { return 100; }
 
 extern "C" const char* ga_last_error(void) { return g_error; }

@@ -10,6 +10,7 @@
 // and stores bases and meta straight into the owner's buffer -- coalesced 512-byte / 256-byte runs per warp on
 // the wire, nothing staged in local DRAM, no NCCL call on the data path.  The destination of a position is known
 // up front from the all-gathered cut matrix (rows every source sends to every owner), so no remote atomics.
+#include <cstdlib>
 #include <cstring>
 
 #include "ga_common.cuh"
@@ -72,6 +73,7 @@ sk_push_records_kernel(const u64* __restrict__ rec, u64 cap1, const u32* __restr
                 u32 g = 0;
                 while (g + 1u < world && p >= s_cut[g + 1u]) ++g;
                 const u64 at = p - s_cut[g];
+                if (!s_bases[g]) continue;                   // probe runs only (GA_PUSH_SKIP)
                 asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(s_bases[g] + 2u * at), "l"(hi_[u]), "l"(lo_[u]) : "memory");
                 asm volatile("st.global.u64 [%0], %1;" ::"l"(s_meta[g] + at), "l"(mt[u]) : "memory");
             }
@@ -145,6 +147,15 @@ extern "C" int ga_sk_push_records(const void* records_dev, uint64_t l1_capacity,
         plan.dst_meta[g] = (u64*)dst_meta[g];
     }
     if (cut[world] == cut[0]) return GA_OK;
+    // probe runs (scripts/gpu_r2_multi.sh): GA_PUSH_SKIP=local|remote drops the stores into this rank's own buffer
+    // (the target with the highest address distance is not known here: "local" = the target the caller marked
+    // by passing it LAST in the environment variable GA_PUSH_SELF) -- timing only, the result is then wrong
+    if (const char* skip = getenv("GA_PUSH_SKIP")) {
+        const char* self = getenv("GA_PUSH_SELF");
+        const uint32_t me = self ? (uint32_t)atoi(self) : 0u;
+        for (uint32_t g = 0; g < world; ++g)
+            if ((g == me) == (strcmp(skip, "local") == 0)) plan.dst_bases[g] = nullptr;
+    }
     const u32 n_l1 = 1u << l1_bits;
     const u64 total = (u64)n_l1 * ((l1_capacity + PUSH_TILE - 1) / PUSH_TILE);
     int dev = 0, sms = 148;

@@ -925,6 +925,14 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         while (sg + 1u < n_seg && idx >= ctl.seg_pre[sg + 1]) ++sg;
         return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
     };
+#ifdef GA_SB_PROFILE
+    // probe build: warp-cycles per phase summed into counters[8..13] = n_solid_global[7..12] (clear, walk, wait at
+    // the barrier that ends the walk, notes, output, whole body)
+    const long long pt0 = clock64();
+#define GA_SB_TICK(slot, from) do { if (lane == 0) atomicAdd((unsigned long long*)(n_solid_global + 7 + (slot)), (unsigned long long)(clock64() - (from))); } while (0)
+#else
+#define GA_SB_TICK(slot, from) do { } while (0)
+#endif
     // B. clear
     mem.clear(cap, tid, T);
     if (tid == 0) {
@@ -935,6 +943,10 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         ctl.next_batch = W * 32u;      // records handed out so far (the warps' first spans are 32 each)
     }
     __syncthreads();
+#ifdef GA_SB_PROFILE
+    GA_SB_TICK(0, pt0);
+    const long long pt1 = clock64();
+#endif
     volatile u32* vovf = &ctl.overflow;
     const u32 pmask = parts - 1u;     // this pass takes the windows whose hash bits 3.. equal `part`
     // smallest ordinal of "solid window `idx` followed by symbol c"
@@ -1089,7 +1101,15 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     }
     for (int off = 16; off > 0; off >>= 1) inserted += __shfl_down_sync(FULL, inserted, off);
     if (lane == 0 && inserted) atomicAdd(&ctl.n_distinct, inserted);
+#ifdef GA_SB_PROFILE
+    GA_SB_TICK(1, pt1);
+    const long long pt2 = clock64();
+#endif
     __syncthreads();
+#ifdef GA_SB_PROFILE
+    GA_SB_TICK(2, pt2);
+    const long long pt3 = clock64();
+#endif
     if (ctl.overflow) return false;
     const u32 n_solid = ctl.n_solid;
     if (n_solid == 0) return true;
@@ -1130,6 +1150,10 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         stamp(idx, (u32)(top >> (kshift - 2u)) & 3u, meta_ordinal(mt) + j);
     }
     __syncthreads();
+#ifdef GA_SB_PROFILE
+    GA_SB_TICK(3, pt3);
+    const long long pt4 = clock64();
+#endif
     // E. output
     const u64 base = ctl.out_base;
     if (base + n_solid <= out_capacity) {
@@ -1137,6 +1161,10 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         if (edge_stamp_out)
             for (u32 s = tid; s < 4 * n_solid; s += T) edge_stamp_out[4 * base + s] = mem.stamp_ld(s);
     }
+#ifdef GA_SB_PROFILE
+    GA_SB_TICK(4, pt4);
+    GA_SB_TICK(5, pt0);
+#endif
     return true;
 }
 
@@ -1166,12 +1194,20 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
         asm volatile("mov.u32 %0, %1;" : "=r"(pool) : "r"(raw));
     }
     if (threadIdx.x == 0) ctl.n_obs = 0;
+#ifdef GA_SB_PROFILE
+    const long long pk0 = clock64();
+#endif
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) ctl.bucket = (u32)min((u64)atomicAdd((unsigned long long*)&counters[0], 1ull), n_buckets);
         __syncthreads();
         const u64 b = ctl.bucket;
-        if (b >= n_buckets) break;
+        if (b >= n_buckets) {
+#ifdef GA_SB_PROFILE
+            if ((threadIdx.x & 31u) == 0) atomicAdd((unsigned long long*)&counters[14], (unsigned long long)(clock64() - pk0));
+#endif
+            break;
+        }
         const u64 nw = hist[b] & 0xFFFFFFFFull;
         if (nw == 0) continue;
         if (threadIdx.x == 0) {       // segment s of the bucket: offsets[s][b] .. offsets[s][b+1]
@@ -1445,6 +1481,7 @@ extern "C" int ga_sk_offsets(const uint64_t* hist_dev, uint64_t n_buckets, uint6
     const u64 n_tiles = (n_buckets + OFF_TILE - 1) / OFF_TILE;
     cudaStream_t st = (cudaStream_t)stream;
     u64* tiles = nullptr;
+    ga_pool_retain();
     GA_CUDA(cudaMallocAsync((void**)&tiles, n_tiles * sizeof(u64), st));
     sk_offsets_tile_sums_kernel<<<(unsigned)n_tiles, 256, 0, st>>>((const u64*)hist_dev, n_buckets, tiles);
     sk_offsets_scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, (u64*)offsets_dev + n_buckets);
@@ -1517,6 +1554,7 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
     const unsigned grid = (unsigned)(n_buckets < most ? n_buckets : most);
     // notes that do not fit a CTA's queue in shared memory: SB_NOTE_SPILL two-word notes per CTA, stream-ordered
     u64* note_spill = nullptr;
+    ga_pool_retain();
     GA_CUDA(cudaMallocAsync((void**)&note_spill, (size_t)grid * SB_NOTE_SPILL * 16u, (cudaStream_t)stream));
     sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,

@@ -673,22 +673,31 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
         raise gn.GaError("bucketed count: a bucket holds 2^25 records or more (one repeated window?)")
     if l1_capacity >= (1 << 25):
         raise gn.GaError("bucketed count: level-1 buckets of 2^25 slots or more")
+    _mark("sk bucket: checks")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
     spill_cap = 1 << 16
     while True:
-        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        counters = torch.zeros(16, dtype=torch.int64, device=dev)      # [8..14]: phase cycles of a GA_SB_PROFILE build
         spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
         solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
         edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64) if want_stamps else None
         status.zero_()
+        _mark("sk bucket: buffers")
         with _timed("sk_bucket", n_occ):
             gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
                                          n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
                                          gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
                                          gn.ptr(spill_list), spill_cap, gn.ptr(status), gn.ptr(index), l1_capacity,
                                          l2_bits, _stream()))
-        _, n_solid, n_spill, n_pass, n_distinct, n_cand = (int(v) for v in counters.cpu().tolist()[:6])
+        _mark("sk bucket: kernel")
+        host_counters = counters.cpu().tolist()
+        _, n_solid, n_spill, n_pass, n_distinct, n_cand = (int(v) for v in host_counters[:6])
+        if _TRACE and host_counters[14]:
+            whole = float(host_counters[14])
+            print("  [trace] bucket kernel warp-cycles: clear %.1f%% walk %.1f%% wait-after-walk %.1f%% notes %.1f%% "
+                  "output %.1f%% (body %.1f%% of the kernel)" % tuple(100.0 * host_counters[8 + i] / whole for i in range(6)),
+                  file=_sys.stderr, flush=True)
         if _TRACE:
             print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled, %d distinct, "
                   "%d candidates" % (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill, n_distinct,

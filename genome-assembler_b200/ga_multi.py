@@ -328,6 +328,8 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
     cut = (C.c_uint64 * (world + 1))(*[int(x) for x in all_cut[rank]])
     dst_bases = (C.c_void_p * world)(*[peers.bases_at(g, dst_start[g]) for g in range(world)])
     dst_meta = (C.c_void_p * world)(*[peers.meta_at(g, dst_start[g]) for g in range(world)])
+    if os.environ.get("GA_PUSH_SKIP"):
+        os.environ["GA_PUSH_SELF"] = str(rank)          # timing probe of the push kernel (results are then wrong)
     with gd._timed("sk_push", reads.windows_total(k)):
         gn.check(L.ga_sk_push_records(gn.ptr(rec), cap1, gn.ptr(index), gn.ptr(offsets), l1_bits, l2_bits, world,
                                       cut, dst_bases, dst_meta, gd._stream()))
