@@ -390,14 +390,17 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     b_total = B_TOTAL_SKETCH if args.sketch else B_TOTAL
     traffic = measured_traffic(args.workload, dominant, launch_occ)
-    limiter = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("limiter", {}).get(dominant) \
-        if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")) else None
+    ncu_notes = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))) \
+        if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")) else {}
+    limiter = ncu_notes.get("limiter", {}).get(dominant)
     roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 # `achieved` is an EQUIVALENT bandwidth (the bytes the roofline model charges per occurrence / time):
                 # what the kernel really moves through DRAM, and what ncu says holds it back, stand next to it
                 "dram_gbs_measured": traffic / (launch_ms * 1e-3) / 1e9 if traffic and launch_ms > 0 else None,
-                "limiter": limiter,
+                # "bound" names the roofline the algorithmic bytes are held against (the contract's hbm | tensor);
+                # "limited_by" is what ncu says actually holds the kernel back
+                "limited_by": ncu_notes.get("limited_by", {}).get(dominant), "limiter": limiter,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per occurrence (profiles/traffic.json) "
                                   "x occurrences of this launch",
                 "peak_source": peak_src,

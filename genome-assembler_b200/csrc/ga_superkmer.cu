@@ -849,6 +849,20 @@ struct BucketCtl {     // shared-memory control block of one CTA
     u32 stack[40];
     u64 seg_lo[SB_MAX_SEG];        // the bucket's records: segment s holds [seg_lo[s], +seg_pre[s+1]-seg_pre[s])
     u64 seg_pre[SB_MAX_SEG + 1];
+    // sources form (multi-GPU, records stay where they were cut): segment s is source rank s; its index entries
+    // sit in seg_idx[s], its slots in seg_rec[s] (= first slot of this bucket's level-1 bucket on that rank)
+    const u64* seg_rec[SB_MAX_SEG];
+    const u32* seg_idx[SB_MAX_SEG];
+};
+
+// Sources form: the level-1 slots and the bucket-sorted index of every source rank, mapped into this process
+// over NVLink (ga_peer_open); entry s is rank s's.  n == 0: not used.
+struct SkSources {
+    const u64* rec[SB_MAX_SEG];
+    const u32* index[SB_MAX_SEG];
+    u64 cap1[SB_MAX_SEG];
+    u64 first_bucket;              // global id of this launch's bucket 0 (the level-1 bucket comes from the global id)
+    u32 n;
 };
 
 // where a bucket's records are: index == nullptr: at the positions the offsets give, bases and meta in two
@@ -858,7 +872,9 @@ struct BucketCtl {     // shared-memory control block of one CTA
 struct SkGather {
     const u32* index;
     u64 base;
+    bool sources;                  // sources form: index / slots per segment in the control block
 };
+constexpr u32 SK_ENT_BITS = 26, SK_ENT_MASK = (1u << SK_ENT_BITS) - 1u;    // index entry | segment << 26
 
 __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
     const u32 lo = __shfl_sync(FULL, (u32)v, src), hi = __shfl_sync(FULL, (u32)(v >> 32), src);
@@ -871,6 +887,58 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
 // down (key = top >> (64 - 2w), the symbol after it right below), `ord` its occurrence ordinal, `follows`
 // whether a next symbol exists, `where` = (record tag + 1) << 5 | window number inside the record (the tag is
 // what finds the record again: its index entry, or its number inside the bucket in the dense form).
+// A record's tag (its index entry, or its number inside the bucket: below 2^25, the host checks) travels with the
+// number of identical records it stands for (warp-level merge below): tag | (copies - 1) << 26.
+constexpr u32 SK_TAG_BITS = 26, SK_TAG_MASK = (1u << SK_TAG_BITS) - 1u;
+
+// Optional (-DGA_SK_MERGE, off): identical records inside one batch of 32 are merged before their windows are
+// dealt out.  At the coverage of real read sets most records are exact copies of one another (BASELINE config
+// C4: 300x -- every genomic super-k-mer is cut out of ~240 reads, 44 % of the copies untouched by sequencing
+// errors, read ends or the 32-window cut), and a bucket holds only ~6 genomic sites, so a random batch of 32
+// records carries each frequent record 2-3 times.  Copies have the same windows with the same next symbols;
+// their ordinals differ by a constant.  So the lowest lane of a group keeps the record with the group's smallest
+// ordinal and a weight (copies), the other lanes drop theirs: counts add the weight, stamps take the smallest
+// ordinal -- bit-identical results (GPU suite green with the flag on).  Measured on C4 (profiles/r02): 23.2 % of
+// the windows never reach the table (9.30e9 of 12.1e9; a CPU model of random batches predicts 24 %, of batches
+// sorted by site 60 %), yet the kernel takes 143.1 ms against 138.9 ms: the windows that disappear are the cheap
+// ones (a probe that hits, one state load, one stamp compare), the insertions and state changes of the error
+// windows stay, and MATCH x3 + the gap-closing shuffles cost more than the 1.7 dealt rounds they save.
+// Only the symbols the record uses take part in the comparison (the 64-symbol field runs on into the read).
+__device__ __forceinline__ void sk_merge_copies(u64& hi, u64& lo, u64& meta, u32& rtag, bool& have, int w) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 used = have ? meta_windows(meta) + (u32)w - 1u + (meta_has_next(meta) ? 1u : 0u) : 0u;   // <= 63 symbols
+    const u64 mh = used >= 32u ? hi : (used ? hi & ~(~0ull >> (2u * used)) : 0ull);
+    const u64 ml = used <= 32u ? 0ull : lo & ~(~0ull >> (2u * (used - 32u)));
+    const u32 sig = have ? (u32)(meta & 63u) : 64u + lane;          // windows, has_next; empty lanes stay alone
+    const u32 group = __match_any_sync(FULL, mh) & __match_any_sync(FULL, ml) & __match_any_sync(FULL, sig);
+    const u32 leader = (u32)__ffs(group) - 1u;
+    u32 rest = group & (group - 1u);                                 // the group's lanes above its leader
+    u32 most = __reduce_max_sync(FULL, (u32)__popc(rest));
+    if (most == 0u) return;                                          // warp-uniform: no two records alike
+    const u64 ord0 = meta_ordinal(meta);
+    u64 omin = ord0;
+    for (; most; --most) {
+        const u32 src = rest ? (u32)__ffs(rest) - 1u : lane;
+        rest &= rest - 1u;
+        omin = min(omin, shfl64(ord0, src));
+    }
+    if (lane == leader) {
+        meta = (omin << 16) | (meta & 0xFFFFull);
+        rtag |= ((u32)__popc(group) - 1u) << SK_TAG_BITS;
+    } else {
+        have = false;
+    }
+    // the walk deals windows to records held by lanes 0..n-1: close the gaps the dropped copies left
+    const u32 keep = __ballot_sync(FULL, have);
+    const u32 src = __fns(keep, 0u, (int)lane + 1);                  // lane of the (lane+1)-th survivor, or all ones
+    have = src < 32u;
+    const u32 from = have ? src : lane;
+    hi = shfl64(hi, from);
+    lo = shfl64(lo, from);
+    meta = shfl64(meta, from);
+    rtag = __shfl_sync(FULL, rtag, from);
+}
+
 template <class F>
 __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u32 rtag, bool have, F&& f) {
     const u32 lane = threadIdx.x & 31u;
@@ -898,7 +966,8 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u
         if (active) {
             const u32 nwin = meta_windows(om);
             const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
-            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), ((otag + 1u) << 5) | j);
+            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), (((otag & SK_TAG_MASK) + 1u) << 5) | j,
+              (otag >> SK_TAG_BITS) + 1u);
         }
         __syncwarp();
     }
@@ -920,11 +989,16 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     const u64 nrec = ctl.seg_pre[n_seg];
     // position of the bucket's idx-th entry (segments are few: linear scan); in the index form that entry is a
     // 32-bit index and the record sits at gather.base + index
-    auto where = [&](u64 idx) -> u64 {
-        u32 sg = 0;
+    auto where2 = [&](u64 idx, u32& sg) -> u64 {
+        sg = 0;
         while (sg + 1u < n_seg && idx >= ctl.seg_pre[sg + 1]) ++sg;
         return ctl.seg_lo[sg] + (idx - ctl.seg_pre[sg]);
     };
+    auto where = [&](u64 idx) -> u64 {
+        u32 sg;
+        return where2(idx, sg);
+    };
+    const bool indexed = gather.index != nullptr || gather.sources;
 #ifdef GA_SB_PROFILE
     // probe build: warp-cycles per phase summed into counters[8..13] = n_solid_global[7..12] (clear, walk, wait at
     // the barrier that ends the walk, notes, output, whole body)
@@ -992,7 +1066,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     // span's index entry is requested one span ahead.
     auto entry = [&](u32 sp) -> u32 {
         const u32 idx = (sp & 0x7FFFFFFFu) + lane;
-        return (gather.index && lane < span_take(sp) && idx < nrec32) ? __ldg(gather.index + where(idx)) : 0u;
+        if (!indexed || lane >= span_take(sp) || idx >= nrec32) return 0u;
+        if (!gather.sources) return __ldg(gather.index + where(idx));
+        u32 sg;
+        const u64 at = where2(idx, sg);
+        return __ldg(ctl.seg_idx[sg] + at) | (sg << SK_ENT_BITS);        // the entry may live on another GPU
     };
     u32 ent = entry(warp * 32u);
     for (u32 sp = warp * 32u, sp_next = 0; (sp & 0x7FFFFFFFu) < nrec32 && !*vovf; sp = sp_next) {
@@ -1004,7 +1082,9 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         ulonglong2 b = make_ulonglong2(0, 0);
         u64 mt = 0;
         if (have) {
-            if (gather.index) {
+            if (gather.sources) {
+                sk_load_slot(ctl.seg_rec[ent >> SK_ENT_BITS], ent & SK_ENT_MASK, b, mt);   // local or over NVLink
+            } else if (gather.index) {
                 sk_load_slot((const u64*)bases, gather.base + ent, b, mt);     // a 32-byte slot of the level-1 bucket
             } else {
                 const u64 i = where(idx);
@@ -1014,8 +1094,19 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         }
         const u32 ent_cur = ent;
         ent = ent_next;
-        sk_for_each_window(b.x, b.y, mt, gather.index ? ent_cur : bt + lane, have,
-                           [&](u64 top, u64 ord, bool follows, u32 where_j) {
+        u32 rtag = gather.index ? ent_cur : bt + lane;     // what finds the record again (sources form: its number in the bucket)
+        bool mine_left = have;
+#ifdef GA_SK_MERGE
+        sk_merge_copies(b.x, b.y, mt, rtag, mine_left, w);
+#endif
+#ifdef GA_SB_PROFILE
+        {   // windows that reach the table after the merge -> counters[15]
+            const u32 left = __reduce_add_sync(FULL, mine_left ? meta_windows(mt) : 0u);
+            if (lane == 0) atomicAdd((unsigned long long*)(n_solid_global + 14), (unsigned long long)left);
+        }
+#endif
+        sk_for_each_window(b.x, b.y, mt, rtag, mine_left,
+                           [&](u64 top, u64 ord, bool follows, u32 where_j, u32 copies) {
             const u64 key = top >> kshift;
             const u32 h = sk_slot_hash(key);
             if (((h >> 3) & pmask) != part) return;
@@ -1062,7 +1153,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                     return;
                 }
                 const u32 cnt = a == 0u ? 0u : (a < SA_REPEAT ? 1u : a & SA_PAYLOAD);
-                if (cnt == threshold) {                    // this occurrence takes the window above the threshold
+                if (cnt + copies > threshold) {            // this occurrence (with its copies) takes the window above the threshold
                     const u32 old = mem.cas_a(s, a, SA_PENDING);
                     if (old != a) {
                         a = old;
@@ -1081,14 +1172,14 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                     if (a >= SA_FIRST && a < SA_REPEAT && (a & SA_PAYLOAD)) note(true, s, a & SA_PAYLOAD);
                     return;
                 }
-                if (a == 0u) {                             // first occurrence: where to find it again goes in the slot
+                if (a == 0u && copies == 1u) {             // first occurrence: where to find it again goes in the slot
                     const u32 old = mem.cas_a(s, 0u, SA_FIRST | (follows ? where_j : 0u));
                     if (old == 0u) return;
                     a = old;
                     continue;
                 }
                 // second .. threshold-th occurrence: count, leave a note (and move the first one to the queue)
-                const u32 old = mem.cas_a(s, a, SA_REPEAT | (cnt + 1u));
+                const u32 old = mem.cas_a(s, a, SA_REPEAT | (cnt + copies));
                 if (old != a) {
                     a = old;
                     continue;
@@ -1139,7 +1230,11 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         const u32 tag = (u32)(payload >> 5) - 1u, j = (u32)payload & 31u;
         ulonglong2 b;
         u64 mt;
-        if (gather.index) {
+        if (gather.sources) {
+            u32 sg;
+            const u64 at = where2(tag, sg);
+            sk_load_slot(ctl.seg_rec[sg], __ldg(ctl.seg_idx[sg] + at), b, mt);
+        } else if (gather.index) {
             sk_load_slot((const u64*)bases, gather.base + tag, b, mt);
         } else {
             const u64 at = where(tag);
@@ -1183,7 +1278,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                  u32 solid_limit,
                  u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity, u64* counters,
                  u64* __restrict__ spill_list, u64 spill_capacity, u32* status, const u32* __restrict__ index,
-                 u64 l1_capacity, int l2_bits, u64* __restrict__ note_spill, u32 note_spill_cap) {
+                 u64 l1_capacity, int l2_bits, u64* __restrict__ note_spill, u32 note_spill_cap,
+                 const __grid_constant__ SkSources src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ BucketCtl ctl;
     // keep the pool's shared address in a register: left to itself the compiler re-derives it from the
@@ -1220,6 +1316,10 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
+            for (u32 sg = 0; sg < src.n; ++sg) {
+                ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
+                ctl.seg_idx[sg] = src.index[sg];
+            }
             // prediction for this bucket: pessimistic ratios until the fit has seen a few buckets
             const float x = (float)nw;
             const float first_guess[3] = {0.32f, 0.2f, 0.03f};
@@ -1278,7 +1378,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                 mem.stamps = mem.skeys + 8u * max_solid;
                 mem.queue = mem.stamps + 32u * max_solid;
                 mem.state = mem.queue + SB_NOTE_BYTES * q_cap;
-                const SkGather gather{index, (b >> l2_bits) * l1_capacity};
+                const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
                 ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, q_cap,
                                     note_spill + 2u * (size_t)blockIdx.x * note_spill_cap, note_spill_cap, max_solid,
                                     edge_stamp_out == nullptr, parts, part, ctl,
@@ -1329,7 +1429,8 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
                        const u64* __restrict__ spill_list, u64 n_spill, int w,
                        u32 threshold, u32 cap, unsigned char* __restrict__ scratch, u64 scratch_per_cta,
                        u64* __restrict__ solid_keys_out, u64* __restrict__ edge_stamp_out, u64 out_capacity,
-                       u64* counters, u32* status, const u32* __restrict__ index, u64 l1_capacity, int l2_bits) {
+                       u64* counters, u32* status, const u32* __restrict__ index, u64 l1_capacity, int l2_bits,
+                       const __grid_constant__ SkSources src) {
     __shared__ BucketCtl ctl;
     MemGlobal mem;
     unsigned char* mine = scratch + (u64)blockIdx.x * scratch_per_cta;
@@ -1354,9 +1455,13 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
+            for (u32 sg = 0; sg < src.n; ++sg) {
+                ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
+                ctl.seg_idx[sg] = src.index[sg];
+            }
         }
         __syncthreads();
-        const SkGather gather{index, (b >> l2_bits) * l1_capacity};
+        const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
         const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
                                        edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
                                        out_capacity, counters + 1);
@@ -1531,15 +1636,41 @@ extern "C" int ga_sk_scatter_buckets(const void* records_dev, uint64_t l1_capaci
     return GA_OK;
 }
 
-extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                                 uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k,
-                                 int64_t threshold,
-                                 uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
-                                 uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
-                                 uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
-                                 const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream) {
+// host description of the sources form -> kernel parameter; false: bad description
+static bool sk_sources(const ga_sk_sources* from, uint32_t n_segments, SkSources& src) {
+    memset(&src, 0, sizeof(src));
+    if (!from) return true;
+    if (from->n_sources == 0 || from->n_sources > SB_MAX_SEG || from->n_sources != n_segments) return false;
+    for (uint32_t g = 0; g < from->n_sources; ++g) {
+        if (!from->records[g] || !from->index[g] || ((uintptr_t)from->records[g] & 31u) || from->l1_capacity[g] == 0 ||
+            from->l1_capacity[g] >= (1ull << 25))
+            return false;
+        src.rec[g] = (const u64*)from->records[g];
+        src.index[g] = from->index[g];
+        src.cap1[g] = from->l1_capacity[g];
+    }
+    src.first_bucket = from->first_bucket;
+    src.n = from->n_sources;
+    return true;
+}
+
+static int sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                          uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k,
+                          int64_t threshold,
+                          uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
+                          uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
+                          uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
+                          const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, const ga_sk_sources* sources,
+                          ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || (!meta_dev && !index_dev) || (index_dev && ((uintptr_t)bases_dev & 31u)) || !offsets_dev ||
+    SkSources src;
+    if (!sk_sources(sources, n_segments, src)) {
+        ga_set_error("ga_sk_count_build_from: bad sources (1..%u, one per segment, 32-byte aligned slots, capacities below 2^25)",
+                     SB_MAX_SEG);
+        return GA_ERR_BAD_ARG;
+    }
+    if (sources) bases_dev = sources->records[0];        // the classic arguments are not used in the sources form
+    if ((!bases_dev) || (!meta_dev && !index_dev && !sources) || (index_dev && ((uintptr_t)bases_dev & 31u)) || !offsets_dev ||
         !hist_dev || !solid_keys_out_dev || !counters_dev || !spill_list_dev || !status_dev || n_buckets == 0 || w < 1 || w > 31 || threshold < 0 ||
         threshold > 60000 || !is_pow2(table_slots) || table_slots < 256 || table_slots > SB_MAX_SLOTS ||
         max_solid == 0 || n_segments == 0 || n_segments > SB_MAX_SEG) {
@@ -1560,8 +1691,8 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,
         (const u64*)hist_dev, n_buckets, w,
         (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, index_dev, l1_capacity, l2_bits,
-        note_spill, SB_NOTE_SPILL);
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, sources ? nullptr : index_dev, l1_capacity,
+        l2_bits, note_spill, SB_NOTE_SPILL, src);
     ga_note_launches(1);
     const cudaError_t launched = cudaGetLastError();
     GA_CUDA(cudaFreeAsync(note_spill, (cudaStream_t)stream));
@@ -1569,20 +1700,52 @@ extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev
     return GA_OK;
 }
 
+extern "C" int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                                 uint32_t n_segments, const uint64_t* hist_dev, uint64_t n_buckets, int k,
+                                 int64_t threshold,
+                                 uint32_t table_slots, uint32_t max_solid, uint64_t* solid_keys_out_dev,
+                                 uint64_t* edge_stamp_out_dev, uint64_t out_capacity, uint64_t* counters_dev,
+                                 uint64_t* spill_list_dev, uint64_t spill_capacity, uint32_t* status_dev,
+                                 const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, ga_stream stream) {
+    return sk_count_build(bases_dev, meta_dev, offsets_dev, n_segments, hist_dev, n_buckets, k, threshold, table_slots,
+                          max_solid, solid_keys_out_dev, edge_stamp_out_dev, out_capacity, counters_dev, spill_list_dev,
+                          spill_capacity, status_dev, index_dev, l1_capacity, l2_bits, nullptr, stream);
+}
+
+extern "C" int ga_sk_count_build_from(const ga_sk_sources* sources, const uint64_t* offsets_dev, const uint64_t* hist_dev,
+                                      uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots,
+                                      uint32_t max_solid, uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                                      uint64_t out_capacity, uint64_t* counters_dev, uint64_t* spill_list_dev,
+                                      uint64_t spill_capacity, uint32_t* status_dev, int l2_bits, ga_stream stream) {
+    if (!sources) {
+        ga_set_error("ga_sk_count_build_from: no sources");
+        return GA_ERR_BAD_ARG;
+    }
+    return sk_count_build(nullptr, nullptr, offsets_dev, sources->n_sources, hist_dev, n_buckets, k, threshold,
+                          table_slots, max_solid, solid_keys_out_dev, edge_stamp_out_dev, out_capacity, counters_dev,
+                          spill_list_dev, spill_capacity, status_dev, nullptr, 0, l2_bits, sources, stream);
+}
+
 extern "C" uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots) {
     // per slot: key 8 B + state 4 B, a solid key 8 B + 4 stamps 32 B, two 16-byte notes
     return (uint64_t)table_slots * (8 + 4 + 8 + 32 + 32);
 }
 
-extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
-                                       uint32_t n_segments, uint64_t n_buckets, const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
-                                       uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
-                                       uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
-                                       uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
-                                       const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits,
-                                       ga_stream stream) {
+static int sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                                uint32_t n_segments, uint64_t n_buckets, const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                                uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
+                                uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                                uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
+                                const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits, const ga_sk_sources* sources,
+                                ga_stream stream) {
     const int w = k - 1;
-    if (!bases_dev || (!meta_dev && !index_dev) || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
+    SkSources src;
+    if (!sk_sources(sources, n_segments, src)) {
+        ga_set_error("ga_sk_count_build_spill_from: bad sources");
+        return GA_ERR_BAD_ARG;
+    }
+    if (sources) bases_dev = sources->records[0];
+    if (!bases_dev || (!meta_dev && !index_dev && !sources) || !offsets_dev || !spill_list_dev || !scratch_dev || !solid_keys_out_dev ||
         !counters_dev || !status_dev || w < 1 || w > 31 || threshold < 0 ||
         !is_pow2(table_slots) || table_slots < 256 || n_ctas == 0 || n_segments == 0 || n_segments > SB_MAX_SEG ||
         n_buckets == 0) {
@@ -1595,9 +1758,36 @@ extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* me
         (const u64*)spill_list_dev, n_spill, w,
         (u32)(threshold > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : threshold), table_slots, (unsigned char*)scratch_dev,
         ga_sk_spill_scratch_bytes(table_slots), (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, status_dev, index_dev, l1_capacity, l2_bits);
+        (u64*)counters_dev, status_dev, sources ? nullptr : index_dev, l1_capacity, l2_bits, src);
     GA_LAUNCH_CHECK("sk_bucket_spill");
     return GA_OK;
+}
+
+extern "C" int ga_sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev, const uint64_t* offsets_dev,
+                                       uint32_t n_segments, uint64_t n_buckets, const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                                       uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
+                                       uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                                       uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
+                                       const uint32_t* index_dev, uint64_t l1_capacity, int l2_bits,
+                                       ga_stream stream) {
+    return sk_count_build_spill(bases_dev, meta_dev, offsets_dev, n_segments, n_buckets, spill_list_dev, n_spill, k,
+                                threshold, table_slots, scratch_dev, n_ctas, solid_keys_out_dev, edge_stamp_out_dev,
+                                out_capacity, counters_dev, status_dev, index_dev, l1_capacity, l2_bits, nullptr, stream);
+}
+
+extern "C" int ga_sk_count_build_spill_from(const ga_sk_sources* sources, const uint64_t* offsets_dev, uint64_t n_buckets,
+                                            const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                                            uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
+                                            uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev,
+                                            uint64_t out_capacity, uint64_t* counters_dev, uint32_t* status_dev,
+                                            int l2_bits, ga_stream stream) {
+    if (!sources) {
+        ga_set_error("ga_sk_count_build_spill_from: no sources");
+        return GA_ERR_BAD_ARG;
+    }
+    return sk_count_build_spill(nullptr, nullptr, offsets_dev, sources->n_sources, n_buckets, spill_list_dev, n_spill, k,
+                                threshold, table_slots, scratch_dev, n_ctas, solid_keys_out_dev, edge_stamp_out_dev,
+                                out_capacity, counters_dev, status_dev, nullptr, 0, l2_bits, sources, stream);
 }
 
 extern "C" int ga_sk_resolve(const uint64_t* solid_keys_dev, uint64_t n_solid, int k, const void* solid_dev,

@@ -592,6 +592,18 @@ def _record_groups(reads: "DeviceReads", w: int) -> int:
     return int((-(-win // 32)).sum())
 
 
+def sk_records_estimate(reads: "DeviceReads", k: int) -> int:
+    """Records this read set will be cut into: two per window span of a minimizer, plus the cuts at 32-window groups."""
+    w = k - 1
+    per_window = w - gn.lib().ga_sk_minimizer_len(k) + 1
+    return int(reads.windows_total(k) * 2.0 / (per_window + 1)) + _record_groups(reads, w)
+
+
+def sk_l1_capacity(reads: "DeviceReads", k: int, l1_bits: int, records: int = 0) -> int:
+    """Slots per level-1 bucket: the expected records (of this read set, or `records`) with 8 % to spare."""
+    return int((records or sk_records_estimate(reads, k)) / (1 << l1_bits) * 1.08) + 4096
+
+
 def sk_geometry(n_occ: int):
     """(level-1 bits, level-2 bits) of the bucket id for `n_occ` window occurrences IN TOTAL (all
     ranks): about SUPERKMER_TARGET windows per bucket, at most 2^20 buckets."""
@@ -602,12 +614,22 @@ def sk_geometry(n_occ: int):
     return bits - l2_bits, l2_bits
 
 
-def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None, dense: bool = True):
+class ScatterOverflow(Exception):
+    """A level-1 bucket outgrew a capacity the caller fixed (sk_scatter_local(..., cap1=...)); `.needed` slots would do."""
+
+    def __init__(self, needed: int):
+        super().__init__("level-1 bucket overflow: %d slots needed" % needed)
+        self.needed = needed
+
+
+def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, feed=None, dense: bool = True,
+                     level2: bool = True, cap1: int = 0, alloc=None):
     """This rank's reads -> records sorted by bucket.  dense: (bases int64[2*total], meta int64[total],
     offsets int64[n_buckets+1], hist int64[n_buckets] = records << 32 | windows, total) -- the records
     themselves in bucket order, what the multi-GPU exchange sends.  Not dense: (level-1 slots int64[4 * n_l1 *
     l1_capacity], None, offsets, hist, total, index int32[total], l1_capacity) -- the records stay in the 32-byte
-    slots of their level-1 buckets and only a 32-bit index per record is sorted.
+    slots of their level-1 buckets and only a 32-bit index per record is sorted.  level2=False stops after the
+    offsets: (slots, None, offsets, hist, total, None, l1_capacity, level-1 cursors, exact-offset cursors).
     ga_sk_scatter_reads + ga_sk_offsets + ga_sk_scatter_buckets."""
     L = gn.lib()
     dev = _dev()
@@ -616,11 +638,13 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
     per_window = w - L.ga_sk_minimizer_len(k) + 1
     n_l1, n_buckets = 1 << l1_bits, 1 << (l1_bits + l2_bits)
     status = reads.status
-    est = int(n_occ * 2.0 / (per_window + 1)) + _record_groups(reads, w)
-    cap1 = int(est / n_l1 * 1.08) + 4096
+    fixed = cap1 > 0                          # the caller owns the geometry (multi-GPU: the same on every rank)
+    alloc = alloc or workspace
+    if not fixed:
+        cap1 = sk_l1_capacity(reads, k, l1_bits)
     cstride = L.ga_sk_cursor_stride()
     while True:
-        rec = workspace("sk_l1_records", n_l1 * cap1 * 4, torch.int64)        # 32-byte slots: bases hi, lo, meta, 0
+        rec = alloc("sk_l1_records", n_l1 * cap1 * 4, torch.int64)            # 32-byte slots: bases hi, lo, meta, 0
         cursors1 = torch.zeros(n_l1 * cstride, dtype=torch.int64, device=dev)
         hist = torch.zeros(n_buckets, dtype=torch.int64, device=dev)
         status.zero_()
@@ -640,11 +664,16 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
             raise ValueError("read symbol outside the alphabet")
         if not st & gn.ST_TABLE_FULL:
             break
-        cap1 = int(int(cursors1.max().item()) * 1.05) + 4096      # cursors kept counting past the capacity
+        needed = int(int(cursors1.max().item()) * 1.05) + 4096    # cursors kept counting past the capacity
+        if fixed:
+            raise ScatterOverflow(needed)
+        cap1 = needed
         del rec                              # the view keeps the old slab alive: drop it before workspace() grows
     _mark("sk scatter reads")
+    if not level2:        # the caller splits the level-1 buckets itself (ga_multi: split + send in one kernel)
+        return rec, None, offsets, hist, total, None, cap1, cursors1, cursors2
     if not dense:
-        index = workspace("sk_index", max(total, 1), torch.int32)
+        index = alloc("sk_index", max(total, 1), torch.int32)
         with _timed("sk_scatter2", n_occ):
             gn.check(L.ga_sk_scatter_buckets(gn.ptr(rec), cap1, gn.ptr(cursors1), l1_bits, l2_bits, gn.ptr(cursors2),
                                              None, None, gn.ptr(index), _stream()))
@@ -660,13 +689,14 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
 
 
 def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, k: int, threshold: int,
-                   n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0, want_stamps: bool = True):
+                   n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0, want_stamps: bool = True,
+                   sources=None):
     """Bucket-sorted records -> (solid keys (cap, 1) int64, n_solid, candidate edge stamps int64[4*cap]).
     offsets: n_segments rows of n_buckets+1 record positions (one row on a single GPU, one per source
     rank after the multi-GPU exchange); hist[b] & 0xFFFFFFFF = windows of bucket b over all segments.
     ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
     L = gn.lib()
-    dev = bases.device
+    dev = hist.device
     # the state word of a table slot names a record (its number inside the bucket, or its slot inside the level-1
     # bucket) in 25 bits; that also keeps the 31-bit hand-out counter and the packed histogram inside their bits
     if n_occ >= (1 << 25) and bool((((hist >> 32) >= (1 << 25)) | (hist < 0)).any().item()):
@@ -685,19 +715,26 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
         status.zero_()
         _mark("sk bucket: buffers")
         with _timed("sk_bucket", n_occ):
-            gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
-                                         n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
-                                         gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
-                                         gn.ptr(spill_list), spill_cap, gn.ptr(status), gn.ptr(index), l1_capacity,
-                                         l2_bits, _stream()))
+            if sources is not None:         # records gathered from every source rank's own slots (local or NVLink)
+                gn.check(L.ga_sk_count_build_from(C.byref(sources), gn.ptr(offsets), gn.ptr(hist), n_buckets, k,
+                                                  int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
+                                                  gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
+                                                  gn.ptr(spill_list), spill_cap, gn.ptr(status), l2_bits, _stream()))
+            else:
+                gn.check(L.ga_sk_count_build(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, gn.ptr(hist),
+                                             n_buckets, k, int(threshold), SUPERKMER_TABLE_SLOTS, SUPERKMER_MAX_SOLID,
+                                             gn.ptr(solid_keys), gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
+                                             gn.ptr(spill_list), spill_cap, gn.ptr(status), gn.ptr(index), l1_capacity,
+                                             l2_bits, _stream()))
         _mark("sk bucket: kernel")
         host_counters = counters.cpu().tolist()
         _, n_solid, n_spill, n_pass, n_distinct, n_cand = (int(v) for v in host_counters[:6])
         if _TRACE and host_counters[14]:
             whole = float(host_counters[14])
             print("  [trace] bucket kernel warp-cycles: clear %.1f%% walk %.1f%% wait-after-walk %.1f%% notes %.1f%% "
-                  "output %.1f%% (body %.1f%% of the kernel)" % tuple(100.0 * host_counters[8 + i] / whole for i in range(6)),
-                  file=_sys.stderr, flush=True)
+                  "output %.1f%% (body %.1f%% of the kernel); %d of %d windows reached the table after the merge of "
+                  "identical records" % (tuple(100.0 * host_counters[8 + i] / whole for i in range(6)) +
+                                         (host_counters[15], n_occ)), file=_sys.stderr, flush=True)
         if _TRACE:
             print("  [trace] bucket passes %d (failed %d) over %d buckets, %d solid, %d spilled, %d distinct, "
                   "%d candidates" % (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill, n_distinct,
@@ -715,11 +752,18 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
             n_ctas = max(1, min(n_spill, 148, int(free * 0.4) // per_cta))
             scratch = torch.empty(n_ctas * per_cta, dtype=torch.uint8, device=dev)
             with _timed("sk_bucket_spill"):
-                gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments, n_buckets,
-                                                   gn.ptr(spill_list), n_spill, k, int(threshold), slots,
-                                                   gn.ptr(scratch), n_ctas, gn.ptr(solid_keys), gn.ptr(edge_stamp),
-                                                   out_cap, gn.ptr(counters), gn.ptr(status), gn.ptr(index),
-                                                   l1_capacity, l2_bits, _stream()))
+                if sources is not None:
+                    gn.check(L.ga_sk_count_build_spill_from(C.byref(sources), gn.ptr(offsets), n_buckets,
+                                                            gn.ptr(spill_list), n_spill, k, int(threshold), slots,
+                                                            gn.ptr(scratch), n_ctas, gn.ptr(solid_keys),
+                                                            gn.ptr(edge_stamp), out_cap, gn.ptr(counters),
+                                                            gn.ptr(status), l2_bits, _stream()))
+                else:
+                    gn.check(L.ga_sk_count_build_spill(gn.ptr(bases), gn.ptr(meta), gn.ptr(offsets), n_segments,
+                                                       n_buckets, gn.ptr(spill_list), n_spill, k, int(threshold), slots,
+                                                       gn.ptr(scratch), n_ctas, gn.ptr(solid_keys), gn.ptr(edge_stamp),
+                                                       out_cap, gn.ptr(counters), gn.ptr(status), gn.ptr(index),
+                                                       l1_capacity, l2_bits, _stream()))
             n_solid = int(counters[1].item())
             del scratch
         if _check_status(status) & gn.ST_TABLE_FULL:

@@ -21,10 +21,11 @@ Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_bucke
      depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
   2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
      records of that range.  EXCHANGE = "push" (default): the owners' receive buffers are mapped into every
-     rank over NVLink (CUDA IPC, `PeerBuffers`) and ONE kernel per rank (`ga_sk_push_records`,
-     csrc/ga_peer.cu) sorts its records by bucket and stores them straight into the owners' buffers -- no
-     dense local copy, no NCCL call on the data path (NCCL carries the 8 MB of histograms and the
-     barriers).  EXCHANGE = "nccl": the round-1 route, a dense local copy + `all_to_all_single` per record
+     rank over NVLink (CUDA IPC, `PeerBuffers`) and ONE kernel per rank (`ga_sk_push_sorted`,
+     csrc/ga_peer.cu) splits its level-1 buckets into final buckets and stores the records straight into
+     the owners' buffers -- no index, no dense local copy, no NCCL call on the data path (NCCL carries
+     the 8 MB of histograms and the barriers).  PUSH = "gather" keeps the first version (index pass, then
+     `ga_sk_push_records` gathers through the index).  EXCHANGE = "nccl": the round-1 route, a dense local copy + `all_to_all_single` per record
      array (PHASES = 2 would send a second half while the first is counted -- no gain measured);
   3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
      segment per source rank;
@@ -139,14 +140,13 @@ class _RawBuffer:
         return self._address
 
 
-class PeerBuffers:
-    """The receive arrays of the record exchange (bases 16 B + meta 8 B per row), allocated with
-    ga_peer_alloc on every rank and mapped into every other rank with ga_peer_open.  `ensure(rows)` is
-    collective: every rank passes the same row count (the largest any rank receives), so all ranks decide
-    alike whether to reallocate; reallocation is rare (the buffers only grow)."""
+class PeerRegion:
+    """A device buffer of this rank that every other rank of the node has mapped (ga_peer_alloc / ga_peer_open:
+    cudaMalloc + CUDA IPC, peer access over NVLink).  `ensure(nbytes)` is collective: every rank passes the same
+    size, so all ranks decide alike whether to reallocate; reallocation is rare (the regions only grow)."""
 
     def __init__(self):
-        self.rows = 0
+        self.nbytes = 0
         self.local = None            # this rank's buffer (raw address)
         self.mapped = []             # per rank: address of that rank's buffer in this process
 
@@ -155,7 +155,7 @@ class PeerBuffers:
         L = gn.lib()
         rank = dist.get_rank()
         torch.cuda.synchronize()
-        dist.barrier()                                   # nobody still writes into a buffer about to go
+        dist.barrier()                                   # nobody still uses a buffer about to go
         for g, address in enumerate(self.mapped):
             if g != rank and address:
                 gn.check(L.ga_peer_close(C.c_void_p(address)))
@@ -163,23 +163,23 @@ class PeerBuffers:
         dist.barrier()                                   # every mapping is gone before the owners free
         if self.local:
             gn.check(L.ga_peer_free(C.c_void_p(self.local)))
-        self.rows, self.local, self.mapped = 0, None, []
+        self.nbytes, self.local, self.mapped = 0, None, []
 
-    def ensure(self, rows: int):
+    def ensure(self, nbytes: int):
         import ga_native as gn
-        if rows <= self.rows:
+        if self.local and nbytes <= self.nbytes:
             return
         L = gn.lib()
         world, rank = dist.get_world_size(), dist.get_rank()
         dev = torch.device("cuda", torch.cuda.current_device())
         if self.local:
             self.close()
-        rows = rows + rows // 16 + 1024
+        nbytes = (nbytes + nbytes // 16 + 65536) // 256 * 256
         handle = (C.c_uint8 * 64)()
         address = C.c_void_p()
-        if L.ga_peer_alloc(rows * 24, C.byref(address), handle) != gn.GA_OK:
+        if L.ga_peer_alloc(nbytes, C.byref(address), handle) != gn.GA_OK:
             torch.cuda.empty_cache()                     # the caching allocator may sit on the room
-            gn.check(L.ga_peer_alloc(rows * 24, C.byref(address), handle))
+            gn.check(L.ga_peer_alloc(nbytes, C.byref(address), handle))
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         everyone = torch.empty(world * 64, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(everyone, mine)
@@ -193,7 +193,26 @@ class PeerBuffers:
             raw = (C.c_uint8 * 64)(*[int(x) for x in everyone[g]])
             gn.check(L.ga_peer_open(raw, C.byref(peer)))
             self.mapped.append(peer.value)
-        self.local, self.rows = address.value, rows
+        self.local, self.nbytes = address.value, nbytes
+
+
+class PeerBuffers(PeerRegion):
+    """The receive arrays of the record exchange (bases 16 B + meta 8 B per row) in one region."""
+
+    def __init__(self):
+        super().__init__()
+        self.rows = 0
+
+    def ensure(self, rows: int):
+        if self.local and rows <= self.rows:
+            return
+        rows = rows + rows // 16 + 1024
+        super().ensure(rows * 24)
+        self.rows = rows
+
+    def close(self):
+        super().close()
+        self.rows = 0
 
     def bases_at(self, g: int, row: int) -> int:
         return self.mapped[g] + 16 * row
@@ -248,7 +267,11 @@ def raise_together(error, group=None):
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
-EXCHANGE = os.environ.get("GA_MULTI_EXCHANGE", "push")     # "push": one kernel over NVLink peer memory; "nccl": round 1
+EXCHANGE = os.environ.get("GA_MULTI_EXCHANGE", "peer")     # "peer": the owners gather over NVLink while they count (no
+                                                            # copy); "push": one send kernel over NVLink peer memory;
+                                                            # "nccl": round 1 (dense copy + all_to_all_single)
+PUSH = os.environ.get("GA_MULTI_PUSH", "gather")            # "gather": index pass, then ga_sk_push_records;
+                                                            # "sorted": level-2 split + send in one pass (ga_sk_push_sorted)
 PHASES = 1              # 2 cuts the exchange in two halves so that the second overlaps the counting of the first;
                         # measured on 2 and 8 B200s it gains nothing (77.2 vs 75.4 ms at N=8: the second bucket
                         # pass and its host round trip cost what the overlap saves), so one phase is the default
@@ -307,7 +330,12 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
     L = gn.lib()
     dev = reads.words.device
     world, rank = dist.get_world_size(), dist.get_rank()
-    rec, _, offsets, hist, total, index, cap1 = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed, dense=False)
+    fused = PUSH == "sorted"
+    if fused:
+        rec, _, offsets, hist, total, _, cap1, cursors1, cursors2 = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed,
+                                                                                        dense=False, level2=False)
+    else:
+        rec, _, offsets, hist, total, index, cap1 = gd.sk_scatter_local(reads, k, l1_bits, l2_bits, feed, dense=False)
     bounds = [g * n_buckets // world for g in range(world + 1)]
     mine = bounds[rank + 1] - bounds[rank]
     # cut[g] = first bucket-sorted position of owner g's range, of every source: one small all-gather.  It doubles
@@ -320,7 +348,7 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
     matrix = [[int(all_cut[s][g + 1] - all_cut[s][g]) for g in range(world)] for s in range(world)]
     dst_start, seg_start, _ = push_plan(matrix, rank)
     gd._mark("multi: cut")
-    peers = _PEERS.setdefault(dev.index, PeerBuffers())
+    peers = _PEERS.setdefault((dev.index, "received"), PeerBuffers())
     peers.ensure(max(sum(matrix[s][g] for s in range(world)) for g in range(world)))
     got_hist = torch.empty(world * mine, dtype=torch.int64, device=dev)
     work = dist.all_to_all_single(got_hist, hist, output_split_sizes=[mine] * world,
@@ -331,8 +359,12 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
     if os.environ.get("GA_PUSH_SKIP"):
         os.environ["GA_PUSH_SELF"] = str(rank)          # timing probe of the push kernel (results are then wrong)
     with gd._timed("sk_push", reads.windows_total(k)):
-        gn.check(L.ga_sk_push_records(gn.ptr(rec), cap1, gn.ptr(index), gn.ptr(offsets), l1_bits, l2_bits, world,
-                                      cut, dst_bases, dst_meta, gd._stream()))
+        if fused:
+            gn.check(L.ga_sk_push_sorted(gn.ptr(rec), cap1, gn.ptr(cursors1), l1_bits, l2_bits, gn.ptr(cursors2), world,
+                                         cut, dst_bases, dst_meta, gd._stream()))
+        else:
+            gn.check(L.ga_sk_push_records(gn.ptr(rec), cap1, gn.ptr(index), gn.ptr(offsets), l1_bits, l2_bits, world,
+                                          cut, dst_bases, dst_meta, gd._stream()))
     # every rank's stores have landed before anybody counts: a one-word all-reduce, stream-ordered after the push
     done = torch.zeros(1, dtype=torch.int32, device=dev)
     barrier = dist.all_reduce(done, async_op=True)
@@ -340,19 +372,97 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
              got_hist, seg_start, mine)]
 
 
+_GEOMETRY = {}          # (device, l1_bits) -> slots per level-1 bucket in force (the same on every rank, only grows)
+
+
+def _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots_wanted, feed, gn, gd):
+    """EXCHANGE = "peer": the exchange fused into the count.  Nothing is copied: every rank leaves its records in
+    its own level-1 slots (peer-mapped regions), sorts a 32-bit index, and the owner of a bucket range gathers the
+    records of its buckets from all ranks -- its own memory or NVLink -- inside the bucket kernel
+    (ga_sk_count_build_from).  Returns (solid keys, n_solid, candidate edge stamps) of this rank's buckets."""
+    dev = reads.words.device
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_l1 = 1 << l1_bits
+    key = (dev.index, l1_bits)
+    cap1 = max(_GEOMETRY.get(key, 0), slots_wanted)
+    slots_region = _PEERS.setdefault((dev.index, "slots"), PeerRegion())
+    index_region = _PEERS.setdefault((dev.index, "index"), PeerRegion())
+    bounds = [g * n_buckets // world for g in range(world + 1)]
+    mine = bounds[rank + 1] - bounds[rank]
+    while True:
+        _GEOMETRY[key] = cap1
+        slots_region.ensure(n_l1 * cap1 * 32)
+        index_region.ensure(n_l1 * cap1 * 4)
+        regions = {"sk_l1_records": slots_region, "sk_index": index_region}
+        needed = 0
+        try:
+            rec, _, offsets, hist, total, index, _ = gd.sk_scatter_local(
+                reads, k, l1_bits, l2_bits, feed, dense=False, cap1=cap1,
+                alloc=lambda name, n, dtype: _RawBuffer(regions[name].local, dev))
+        except gd.ScatterOverflow as exc:
+            needed = exc.needed
+        feed = None
+        # every rank must have fitted its records, or all of them cut again with larger buckets
+        worst = torch.tensor([needed], dtype=torch.int64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        worst = int(worst.item())
+        if worst == 0:
+            break
+        cap1 = max(cap1, worst)
+    gd._mark("multi: cut")
+    # the owner of a bucket range needs, from every source, where that source's entries of its buckets sit
+    # (bucket-sorted positions, mine + 1 words) and how many records / windows each bucket holds there
+    send_off = torch.cat([offsets[bounds[g]:bounds[g + 1] + 1] for g in range(world)])
+    got_off = torch.empty(world * (mine + 1), dtype=torch.int64, device=dev)
+    got_hist = torch.empty(world * mine, dtype=torch.int64, device=dev)
+    sizes = [bounds[g + 1] - bounds[g] for g in range(world)]
+    # these two collectives are also the barrier between "every rank has cut and indexed its records" and the gathers
+    dist.all_to_all_single(got_off, send_off, output_split_sizes=[mine + 1] * world,
+                           input_split_sizes=[n + 1 for n in sizes])
+    dist.all_to_all_single(got_hist, hist, output_split_sizes=[mine] * world, input_split_sizes=sizes)
+    gd._mark("multi: exchange 0")
+    if not mine:
+        empty = torch.zeros((0, 1), dtype=torch.int64, device=dev)
+        return empty, 0, torch.zeros(0, dtype=torch.int64, device=dev)
+    summed = got_hist.view(world, mine).sum(dim=0).contiguous()
+    n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
+    sources = gn.GaSkSources()
+    for g in range(world):
+        sources.records[g] = slots_region.mapped[g]
+        sources.index[g] = index_region.mapped[g]
+        sources.l1_capacity[g] = cap1
+    sources.first_bucket, sources.n_sources = bounds[rank], world
+    return gd.sk_bucket_pass(None, None, got_off, world, summed, mine, k, threshold, max(n_occ_mine, 1), reads.status,
+                             l2_bits=l2_bits, sources=sources)
+
+
 def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     dev = reads.words.device
     world, rank = dist.get_world_size(), dist.get_rank()
-    occ = torch.tensor([reads.windows_total(k)], dtype=torch.int64, device=dev)
-    dist.all_reduce(occ)
-    n_occ = int(occ.item())
+    # occurrences of all ranks (the bucket geometry must be the same everywhere); this first collective of a step
+    # is also what keeps a rank from cutting new records over slots a peer's previous bucket pass still gathers from
+    mine_occ = torch.tensor([reads.windows_total(k), gd.sk_records_estimate(reads, k)], dtype=torch.int64, device=dev)
+    every_occ = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every_occ, mine_occ)
+    every_occ = every_occ.view(world, 2).tolist()
+    n_occ = sum(int(row[0]) for row in every_occ)
+    most_records = max(int(row[1]) for row in every_occ)
     l1_bits, l2_bits = gd.sk_geometry(n_occ)
     n_buckets = 1 << (l1_bits + l2_bits)
-    # 1. local records by bucket, 2. every bucket's records to its owner
-    exchange = _exchange_push if (EXCHANGE == "push" and dist.get_backend() == "nccl") else _exchange_nccl
-    received = exchange(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd)
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
     key_parts, stamp_parts = [], []
+    received = []
+    if EXCHANGE == "peer" and dist.get_backend() == "nccl":
+        # 1.-3. in one go: records stay where they were cut, the owners gather them while they count
+        slots = gd.sk_l1_capacity(reads, k, l1_bits, most_records)        # the same number on every rank
+        solid_keys, n_solid, edge_stamp = _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots, feed,
+                                                          gn, gd)
+        key_parts.append(solid_keys[:n_solid])
+        stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4))
+    else:
+        # 1. local records by bucket, 2. every bucket's records to its owner
+        exchange = _exchange_push if (EXCHANGE == "push" and dist.get_backend() == "nccl") else _exchange_nccl
+        received = exchange(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd)
     for h, (works, got_bases, got_meta, got_hist, starts, mine) in enumerate(received):
         for wk in works:
             wk.wait()                  # orders the current stream after the transfer; the host does not block

@@ -36,6 +36,11 @@ class GaPrefilter(C.Structure):
     _fields_ = [("words", C.c_void_p), ("n_cells", C.c_uint64), ("cell_bits", C.c_int32)]
 
 
+class GaSkSources(C.Structure):
+    _fields_ = [("records", C.c_void_p * 16), ("index", C.c_void_p * 16), ("l1_capacity", C.c_uint64 * 16),
+                ("first_bucket", C.c_uint64), ("n_sources", C.c_uint32)]
+
+
 class GaSketch(C.Structure):
     _fields_ = [("cells", C.c_void_p), ("width", C.c_uint32 * MAX_SKETCH_ROWS), ("rows", C.c_int32)]
 
@@ -77,6 +82,10 @@ SIGNATURES = {
     "ga_sk_scatter_buckets": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ga_sk_count_build": (_i32, [_vp, _vp, _vp, _u32, _vp, _u64, _i32, _i64, _u32, _u32, _vp, _vp, _u64, _vp, _vp, _u64, _vp,
                                  _vp, _u64, _i32, _vp]),
+    "ga_sk_count_build_from": (_i32, [C.POINTER(GaSkSources), _vp, _vp, _u64, _i32, _i64, _u32, _u32, _vp, _vp, _u64, _vp, _vp,
+                                      _u64, _vp, _i32, _vp]),
+    "ga_sk_count_build_spill_from": (_i32, [C.POINTER(GaSkSources), _vp, _u64, _vp, _u64, _i32, _i64, _u32, _vp, _u32, _vp, _vp,
+                                            _u64, _vp, _vp, _i32, _vp]),
     "ga_sk_spill_scratch_bytes": (_u64, [_u32]),
     "ga_sk_count_build_spill": (_i32, [_vp, _vp, _vp, _u32, _u64, _vp, _u64, _i32, _i64, _u32, _vp, _u32, _vp, _vp, _u64, _vp, _vp,
                                        _vp, _u64, _i32, _vp]),
@@ -86,6 +95,7 @@ SIGNATURES = {
     "ga_peer_close": (_i32, [_vp]),
     "ga_peer_free": (_i32, [_vp]),
     "ga_sk_push_records": (_i32, [_vp, _u64, _vp, _vp, _i32, _i32, _u32, _vp, _vp, _vp, _vp]),
+    "ga_sk_push_sorted": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _u32, _vp, _vp, _vp, _vp]),
     "ga_sketch_update_table": (_i32, [_vp, _u64, _i32, _i32, _i32, _vp, _PS, _vp]),
     "ga_sketch_update_bytes": (_i32, [_vp, _vp, _vp, _u64, _PS, _vp]),
     "ga_sketch_estimate_bytes": (_i32, [_vp, _vp, _u64, _PS, _vp, _vp]),

@@ -42,6 +42,7 @@ extern "C" {
 #define GA_STATUS_U16_OVERFLOW 8u
 
 #define GA_MAX_SKETCH_ROWS 20
+#define GA_PEER_MAX_RANKS 16    /* ranks of one node that exchange records over NVLink peer memory */
 
 typedef void* ga_stream;
 
@@ -218,6 +219,30 @@ int ga_sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const uin
                       uint64_t out_capacity, uint64_t* counters_dev, uint64_t* spill_list_dev,
                       uint64_t spill_capacity, uint32_t* status_dev, const uint32_t* index_dev,
                       uint64_t l1_capacity, int l2_bits, ga_stream stream);
+/* Sources form (multi-GPU, the exchange fused into the count: nothing is copied): the records stay in the level-1
+ * slots of the rank that cut them, and the owner of a bucket range gathers them while it counts -- from its own
+ * memory or over NVLink from buffers mapped with ga_peer_open.  Segment s of a bucket is source rank s:
+ * offsets_dev row s = rank s's bucket-sorted positions of this launch's buckets (n_buckets + 1 words, addressing
+ * index[s]); the record of entry e is slot (global bucket id >> l2_bits) * l1_capacity[s] + index[s][e] of
+ * records[s], global bucket id = first_bucket + bucket number.  HOST struct; pointers are device pointers valid
+ * in this process.  Everything else as ga_sk_count_build / ga_sk_count_build_spill. */
+typedef struct ga_sk_sources {
+    const void* records[GA_PEER_MAX_RANKS];     /* 32-byte slots of ga_sk_scatter_reads, one array per source rank */
+    const uint32_t* index[GA_PEER_MAX_RANKS];   /* index form of ga_sk_scatter_buckets, one array per source rank */
+    uint64_t l1_capacity[GA_PEER_MAX_RANKS];
+    uint64_t first_bucket;
+    uint32_t n_sources;
+} ga_sk_sources;
+int ga_sk_count_build_from(const ga_sk_sources* sources, const uint64_t* offsets_dev, const uint64_t* hist_dev,
+                           uint64_t n_buckets, int k, int64_t threshold, uint32_t table_slots, uint32_t max_solid,
+                           uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev, uint64_t out_capacity,
+                           uint64_t* counters_dev, uint64_t* spill_list_dev, uint64_t spill_capacity,
+                           uint32_t* status_dev, int l2_bits, ga_stream stream);
+int ga_sk_count_build_spill_from(const ga_sk_sources* sources, const uint64_t* offsets_dev, uint64_t n_buckets,
+                                 const uint64_t* spill_list_dev, uint64_t n_spill, int k, int64_t threshold,
+                                 uint32_t table_slots, void* scratch_dev, uint32_t n_ctas,
+                                 uint64_t* solid_keys_out_dev, uint64_t* edge_stamp_out_dev, uint64_t out_capacity,
+                                 uint64_t* counters_dev, uint32_t* status_dev, int l2_bits, ga_stream stream);
 /* The listed buckets again with tables in global scratch (n_ctas slices of
  * ga_sk_spill_scratch_bytes(table_slots) bytes; table_slots >= twice the windows of the largest). */
 uint64_t ga_sk_spill_scratch_bytes(uint32_t table_slots);
@@ -349,7 +374,6 @@ void ga_csr_plan_free(ga_csr_plan* plan);
 /* ---- multi-GPU record exchange over NVLink peer memory ("k-mers routed to their owning GPU by a
  *      hash-partition all-to-all over NVLink"; the reference is single-process, debruijn_graph.py:113-152 is what
  *      every rank's share must add up to) -------------------------------------------------------------------- */
-#define GA_PEER_MAX_RANKS 16
 #define GA_PEER_HANDLE_BYTES 64
 /* A receive buffer other processes of this node can map: cudaMalloc + CUDA IPC handle (64 opaque HOST bytes
  * written to handle_out; ship them to the peers by any means).  ga_peer_open maps a peer's buffer into this
@@ -370,6 +394,14 @@ int ga_peer_free(void* ptr);
 int ga_sk_push_records(const void* records_dev, uint64_t l1_capacity, const uint32_t* index_dev,
                        const uint64_t* offsets_dev, int l1_bits, int l2_bits, uint32_t world,
                        const uint64_t* cut, void* const* dst_bases, void* const* dst_meta, ga_stream stream);
+/* Level-2 split + send in one pass, no index: input is what ga_sk_scatter_reads + ga_sk_offsets leave behind
+ * (records_dev, l1_cursors_dev, and cursors_dev = the exact-offset cursors, consumed).  A chunk of consecutive
+ * slots is counting-sorted by final bucket in shared memory and its records are stored straight into the owners'
+ * arrays in runs; every slot is streamed from DRAM once.  Same cut / dst_* contract and the same receive layout as
+ * ga_sk_push_records (the order of the records inside a final bucket differs; nothing depends on it). */
+int ga_sk_push_sorted(const void* records_dev, uint64_t l1_capacity, const uint64_t* l1_cursors_dev, int l1_bits,
+                      int l2_bits, uint64_t* cursors_dev, uint32_t world, const uint64_t* cut,
+                      void* const* dst_bases, void* const* dst_meta, ga_stream stream);
 
 /* ---- raw ingest (replaces IOHandler.read_input, assemble.py:40-71) --------------------------------------- */
 /* HOST pointers.  Parses the bytes of stdin with the reference's rules (first line = number of reads n;

@@ -22,11 +22,18 @@ def main():
     ok = True
     # unpaired: the bucketed route with both exchanges (one kernel over NVLink peer memory; dense copy + NCCL
     # all-to-all), a case large enough for several level-1 buckets, and the k > 32 table route
-    for genome_size, n_reads, read_len, k, F, exchange in ((200000, 60000, 100, 31, 3, "push"),
+    for genome_size, n_reads, read_len, k, F, exchange in ((200000, 60000, 100, 31, 3, "peer"),
+                                                           (3000000, 1500003, 150, 31, 3, "peer"),
+                                                           (200000, 60000, 100, 31, 3, "push"),
+                                                           (200000, 60000, 100, 31, 3, "push-gather"),
                                                            (200000, 60000, 100, 31, 3, "nccl"),
                                                            (3000000, 1500003, 150, 31, 3, "push"),
+                                                           (3000000, 1500003, 150, 31, 3, "push-gather"),
                                                            (50000, 30011, 150, 41, 2, "push")):
-        ga_multi.EXCHANGE = exchange
+        ga_multi.EXCHANGE = exchange.split("-")[0]
+        ga_multi.PUSH = "gather" if exchange.endswith("gather") else "sorted"
+        if exchange == "push":
+            ga_multi.PUSH = "sorted"
         stride = (read_len + 31) // 32
         genome = torch.empty(genome_size, dtype=torch.uint8, device=dev)
         gn.check(L.ga_gen_genome(gn.ptr(genome), genome_size, 5, None))
