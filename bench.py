@@ -307,6 +307,11 @@ def run_gpu_arm(args):
         n_reads = args.reads
     if args.genome:
         genome_size = args.genome
+    sketch_widths = None
+    if args.sketch_widths:          # C5: sketch width sweep over the reference's three prime tables
+        from countminsketch import CountMinSketch
+        sketch_widths = {"6e7": CountMinSketch.primes_6_10_7, "1e7": CountMinSketch.primes_1_10_7,
+                         "5e6": CountMinSketch.primes_5_10_6}[args.sketch_widths]
     L = gn.lib()
     mates = 2 if paired else 1
     stride = (read_len + 31) // 32
@@ -329,7 +334,8 @@ def run_gpu_arm(args):
         step_fn = lambda timers=None: ga_multi.sharded_step(reads, k, F, timers=timers)   # noqa: E731
     else:
         step_fn = lambda timers=None: gd.device_step(reads, k, F, timers=timers,            # noqa: E731
-                                                     sketch_rows=10 if args.sketch else 0)
+                                                     sketch_rows=args.sketch_rows if args.sketch else 0,
+                                                     sketch_widths=sketch_widths)
 
     def barrier():
         if world > 1:
@@ -564,9 +570,17 @@ def main():
                                                          "genome together to keep the workload's coverage)")
     ap.add_argument("--sketch", action="store_true", help="the -c route: exact counts poured into the reference's "
                                                           "10-row CountMinSketch, filter on the sketch estimate")
+    ap.add_argument("--k", type=int, default=0, help="override --kmer_length of the workload (C5: k sweep on C3's read pairs)")
+    ap.add_argument("--sketch-rows", type=int, default=10, help="rows of the CountMinSketch with --sketch (reference: 10, "
+                                                                "8 in its -m mode)")
+    ap.add_argument("--sketch-widths", default="", choices=["", "6e7", "1e7", "5e6"],
+                    help="prime table the sketch rows are taken from (reference: 1e7; countminsketch.py:9-24)")
     ap.add_argument("--sample-reads", type=int, default=0, help="cap on the reads (pairs) of the CPU sample "
                                                                 "(default: what fits the time budget)")
     args = ap.parse_args()
+    if args.k:                      # C5: k sweep on the read pairs of C3 (64-bit keys up to k = 32, 128-bit beyond)
+        g, n, length, paired, _, F, desc = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (g, n, length, paired, args.k, F, desc.replace("k=%d" % _, "k=%d" % args.k) + " [k overridden]")
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -975,7 +975,7 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u
 
 // returns false when the pass does not fit (table, queue or solid area full): the caller splits it or lists it
 // for the spill path
-template <class Mem>
+template <class Mem, bool DEEP>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                SkGather gather, int w, u32 threshold, const Mem& mem, u32 cap,
                                                u32 q_cap, u64* __restrict__ q_spill, u32 q_spill_cap, u32 max_solid,
@@ -1072,25 +1072,57 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         const u64 at = where2(idx, sg);
         return __ldg(ctl.seg_idx[sg] + at) | (sg << SK_ENT_BITS);        // the entry may live on another GPU
     };
+    // this lane's record of span `sp` (index entry `e`): nothing for lanes beyond the span or the bucket
+    auto fetch = [&](u32 sp, u32 e, ulonglong2& b, u64& mt) {
+        const u64 idx = (u64)(sp & 0x7FFFFFFFu) + lane;
+        b = make_ulonglong2(0, 0);
+        mt = 0;
+        if (lane >= span_take(sp) || idx >= nrec) return;
+        if (gather.sources) {
+            sk_load_slot(ctl.seg_rec[e >> SK_ENT_BITS], e & SK_ENT_MASK, b, mt);   // local or over NVLink
+        } else if (gather.index) {
+            sk_load_slot((const u64*)bases, gather.base + e, b, mt);       // a 32-byte slot of the level-1 bucket
+        } else {
+            const u64 i = where(idx);
+            b = bases[i];
+            mt = meta[i];
+        }
+    };
+    // DEEP (sources form, GA_SK_DEEP=1): records that sit on another GPU are 2-3 us away, twice over (index entry,
+    // then the slot).  The walk then runs two spans ahead: index entries are requested two spans before their
+    // records are dealt, the records themselves one span before.  Measured on C4 at N = 2 (profiles/r02): bucket
+    // kernel 90.0 / 107.3 ms on the two ranks against 91.1 / 101.1 ms on demand -- what the remote gather costs
+    // (the same kernel takes 67.9 ms over local records) is not latency but the rate at which NVLink serves lone
+    // 32-byte reads (0.46e9 of them per rank: ~5e9/s), so the depth buys nothing and costs balance at the end
+    // of a bucket.  Off by default; on one GPU the same depth was +4.5 % (round 1).
     u32 ent = entry(warp * 32u);
+    u32 sp_ahead = 0, ent_ahead = 0;
+    ulonglong2 b = make_ulonglong2(0, 0);
+    u64 mt = 0;
+    if (DEEP) {
+        sp_ahead = next_span();
+        ent_ahead = entry(sp_ahead);
+        fetch(warp * 32u, ent, b, mt);
+    }
     for (u32 sp = warp * 32u, sp_next = 0; (sp & 0x7FFFFFFFu) < nrec32 && !*vovf; sp = sp_next) {
         const u32 bt = sp & 0x7FFFFFFFu;               // first record of the span
         const u64 idx = (u64)bt + lane;
         const bool have = lane < span_take(sp) && idx < nrec;
-        sp_next = next_span();
-        const u32 ent_next = entry(sp_next);
-        ulonglong2 b = make_ulonglong2(0, 0);
-        u64 mt = 0;
-        if (have) {
-            if (gather.sources) {
-                sk_load_slot(ctl.seg_rec[ent >> SK_ENT_BITS], ent & SK_ENT_MASK, b, mt);   // local or over NVLink
-            } else if (gather.index) {
-                sk_load_slot((const u64*)bases, gather.base + ent, b, mt);     // a 32-byte slot of the level-1 bucket
-            } else {
-                const u64 i = where(idx);
-                b = bases[i];
-                mt = meta[i];
-            }
+        ulonglong2 b_ahead = make_ulonglong2(0, 0);
+        u64 mt_ahead = 0;
+        u32 ent_next;
+        if (DEEP) {
+            const u32 sp_far = next_span();
+            const u32 ent_far = entry(sp_far);
+            fetch(sp_ahead, ent_ahead, b_ahead, mt_ahead);
+            sp_next = sp_ahead;
+            ent_next = ent_ahead;
+            sp_ahead = sp_far;
+            ent_ahead = ent_far;
+        } else {
+            sp_next = next_span();
+            ent_next = entry(sp_next);
+            fetch(sp, ent, b, mt);
         }
         const u32 ent_cur = ent;
         ent = ent_next;
@@ -1189,6 +1221,10 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
                 return;
             }
         });
+        if (DEEP) {
+            b = b_ahead;
+            mt = mt_ahead;
+        }
     }
     for (int off = 16; off > 0; off >>= 1) inserted += __shfl_down_sync(FULL, inserted, off);
     if (lane == 0 && inserted) atomicAdd(&ctl.n_distinct, inserted);
@@ -1272,6 +1308,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
 // parts comes from running estimates of the three per window of the bucket (the first buckets of a CTA start
 // pessimistic); a pass that still does not fit is split in two; only passes that would need more than 32 parts
 // (or buckets of more than 65536 records) go to the spill list (entry = bucket | parts << 32 | part << 48).
+template <bool DEEP>
 __global__ void __launch_bounds__(SB_THREADS, SB_CTAS_PER_SM)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
                  u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
@@ -1379,7 +1416,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                 mem.queue = mem.stamps + 32u * max_solid;
                 mem.state = mem.queue + SB_NOTE_BYTES * q_cap;
                 const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
-                ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, q_cap,
+                ok = sk_bucket_body<MemShared, DEEP>(bases, meta, gather, w, threshold, mem, cap, q_cap,
                                     note_spill + 2u * (size_t)blockIdx.x * note_spill_cap, note_spill_cap, max_solid,
                                     edge_stamp_out == nullptr, parts, part, ctl,
                                     solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
@@ -1462,7 +1499,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         }
         __syncthreads();
         const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
-        const bool ok = sk_bucket_body(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
+        const bool ok = sk_bucket_body<MemGlobal, false>(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
                                        edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
                                        out_capacity, counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
@@ -1679,7 +1716,9 @@ static int sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const
         return GA_ERR_BAD_ARG;
     }
     // the attribute is per device: set it on every call (cheap) instead of caching a process-wide flag
-    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    const bool deep = sources && getenv("GA_SK_DEEP");           // opt-in: loads two spans ahead of the walk (measured: +-0)
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
     if (max_solid > 16000) max_solid = 16000;
     const u64 most = (u64)ga_sm_count() * SB_CTAS_PER_SM;
     const unsigned grid = (unsigned)(n_buckets < most ? n_buckets : most);
@@ -1687,12 +1726,16 @@ static int sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const
     u64* note_spill = nullptr;
     ga_pool_retain();
     GA_CUDA(cudaMallocAsync((void**)&note_spill, (size_t)grid * SB_NOTE_SPILL * 16u, (cudaStream_t)stream));
-    sk_bucket_kernel<<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(
-        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,
-        (const u64*)hist_dev, n_buckets, w,
-        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,
-        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, sources ? nullptr : index_dev, l1_capacity,
-        l2_bits, note_spill, SB_NOTE_SPILL, src);
+#define GA_SB_LAUNCH(DEEP)                                                                                          \
+    sk_bucket_kernel<DEEP><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                               \
+        (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,                    \
+        (const u64*)hist_dev, n_buckets, w,                                                                         \
+        (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,   \
+        (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, sources ? nullptr : index_dev,        \
+        l1_capacity, l2_bits, note_spill, SB_NOTE_SPILL, src)
+    if (deep) GA_SB_LAUNCH(true);
+    else GA_SB_LAUNCH(false);
+#undef GA_SB_LAUNCH
     ga_note_launches(1);
     const cudaError_t launched = cudaGetLastError();
     GA_CUDA(cudaFreeAsync(note_spill, (cudaStream_t)stream));

@@ -1197,16 +1197,16 @@ def emit_paired(graph, solid, solid_cap, solid_keys, n_solid, kw, k, alphabet, q
 
 
 # ----------------------------------------------------------------------------------- whole path
-def _poured_sketch(counts: KmerCounts, rows: int):
+def _poured_sketch(counts: KmerCounts, rows: int, widths=None):
     """The -c route (debruijn_graph.py:181-188, debug_graph.py:66-85): every distinct window's exact count
     poured into a `rows`-row CountMinSketch (uint16 overflow checked as the reference's array('H') would)."""
     from countminsketch import CountMinSketch
-    sketch = CountMinSketch(rows)
+    sketch = CountMinSketch(rows, widths=widths)      # widths: one of the reference's prime tables (countminsketch.py:9-24)
     sketch.pour_counts(counts)
     return sketch
 
 
-def device_step(reads: DeviceReads, k: int, threshold: int, timers=None, sketch_rows: int = 0):
+def device_step(reads: DeviceReads, k: int, threshold: int, timers=None, sketch_rows: int = 0, sketch_widths=None):
     """One pass of the hot path over device-resident packed reads; the CSR stays on the device.
     sketch_rows > 0: the CountMinSketch route (exact table -> sketch -> filter on the estimate -> build)."""
     global TIMERS
@@ -1214,7 +1214,7 @@ def device_step(reads: DeviceReads, k: int, threshold: int, timers=None, sketch_
     try:
         _mark("step begin")
         counts = KmerCounts(k, reads)
-        sketch = _poured_sketch(counts, sketch_rows) if sketch_rows else None
+        sketch = _poured_sketch(counts, sketch_rows, sketch_widths) if sketch_rows else None
         out = build_graph(counts, reads, threshold, to_host=False,
                           sketch=sketch._struct() if sketch is not None else None)
         _mark("step end")

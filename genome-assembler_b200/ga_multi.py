@@ -267,9 +267,11 @@ def raise_together(error, group=None):
 
 
 USE_BUCKETS = True      # scripts/multi_check.py also runs the table route by clearing this
-EXCHANGE = os.environ.get("GA_MULTI_EXCHANGE", "peer")     # "peer": the owners gather over NVLink while they count (no
+EXCHANGE = os.environ.get("GA_MULTI_EXCHANGE", "auto")     # "peer": the owners gather over NVLink while they count (no
                                                             # copy); "push": one send kernel over NVLink peer memory;
-                                                            # "nccl": round 1 (dense copy + all_to_all_single)
+                                                            # "nccl": round 1 (dense copy + all_to_all_single);
+                                                            # "auto": push on 2-3 ranks, peer from 4 on (C4: 157.0 vs
+                                                            # 160.4 ms at N = 2, 67.6 vs 63.6 ms at N = 8)
 PUSH = os.environ.get("GA_MULTI_PUSH", "gather")            # "gather": index pass, then ga_sk_push_records;
                                                             # "sorted": level-2 split + send in one pass (ga_sk_push_sorted)
 PHASES = 1              # 2 cuts the exchange in two halves so that the second overlaps the counting of the first;
@@ -452,7 +454,8 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     graph = gd.BuiltGraph(False, k - 1, reads.alphabet, 1)
     key_parts, stamp_parts = [], []
     received = []
-    if EXCHANGE == "peer" and dist.get_backend() == "nccl":
+    route = EXCHANGE if EXCHANGE != "auto" else ("peer" if world >= 4 else "push")
+    if route == "peer" and dist.get_backend() == "nccl":
         # 1.-3. in one go: records stay where they were cut, the owners gather them while they count
         slots = gd.sk_l1_capacity(reads, k, l1_bits, most_records)        # the same number on every rank
         solid_keys, n_solid, edge_stamp = _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots, feed,
@@ -461,7 +464,7 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
         stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4))
     else:
         # 1. local records by bucket, 2. every bucket's records to its owner
-        exchange = _exchange_push if (EXCHANGE == "push" and dist.get_backend() == "nccl") else _exchange_nccl
+        exchange = _exchange_push if (route == "push" and dist.get_backend() == "nccl") else _exchange_nccl
         received = exchange(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd)
     for h, (works, got_bases, got_meta, got_hist, starts, mine) in enumerate(received):
         for wk in works:

@@ -169,3 +169,45 @@ def test_bucketed_entries_reject_bad_arguments():
     assert L.ga_sk_count_build(ptr, ptr, ptr, 99, ptr, 4, 31, 3, 4096, 16, *tail) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_resolve(None, 5, 31, ptr, 16, ptr, ptr, None) == gn.GA_ERR_BAD_ARG
     assert L.ga_sk_spill_scratch_bytes(1024) == 1024 * 84
+
+
+def test_peer_exchange_entries_reject_bad_arguments():
+    """ga_peer_* / ga_sk_push_* / ga_sk_count_build_from validate their arguments before touching CUDA."""
+    import ga_native as gn
+    L = _lib()
+    dummy = C.create_string_buffer(256)
+    ptr = C.c_void_p((C.addressof(dummy) + 31) & ~31)
+    out = C.c_void_p()
+    handle = (C.c_uint8 * 64)()
+    assert L.ga_peer_alloc(0, C.byref(out), handle) == gn.GA_ERR_BAD_ARG
+    assert L.ga_peer_alloc(1024, None, handle) == gn.GA_ERR_BAD_ARG
+    assert L.ga_peer_open(None, C.byref(out)) == gn.GA_ERR_BAD_ARG
+    assert L.ga_peer_close(None) == gn.GA_OK and L.ga_peer_free(None) == gn.GA_OK      # nothing to do
+    cut = (C.c_uint64 * 3)(0, 10, 20)
+    down = (C.c_uint64 * 3)(0, 10, 5)
+    targets = (C.c_void_p * 2)(ptr.value, ptr.value)
+    holes = (C.c_void_p * 2)(ptr.value, None)
+    # more ranks than a node holds, descending cut, a non-empty range without a target
+    assert L.ga_sk_push_records(ptr, 16, ptr, ptr, 2, 2, 17, cut, targets, targets, None) == gn.GA_ERR_BAD_ARG
+    assert b"1..16 ranks" in L.ga_last_error()
+    assert L.ga_sk_push_records(ptr, 16, ptr, ptr, 2, 2, 2, down, targets, targets, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_push_records(ptr, 16, ptr, ptr, 2, 2, 2, cut, holes, targets, None) == gn.GA_ERR_BAD_ARG
+    assert b"cut must ascend" in L.ga_last_error()
+    assert L.ga_sk_push_sorted(ptr, 16, ptr, 2, 11, ptr, 2, cut, targets, targets, None) == gn.GA_ERR_BAD_ARG
+    assert L.ga_sk_push_sorted(ptr, 16, ptr, 2, 2, ptr, 2, down, targets, targets, None) == gn.GA_ERR_BAD_ARG
+    # nothing to send: returns before any launch
+    empty = (C.c_uint64 * 3)(7, 7, 7)
+    assert L.ga_sk_push_records(ptr, 16, ptr, ptr, 2, 2, 2, empty, holes, holes, None) == gn.GA_OK
+    # sources form: one source per segment, capacities below 2^25, aligned slots
+    src = gn.GaSkSources()
+    tail = (ptr, ptr, 4, 31, 3, 4096, 16, ptr, ptr, 16, ptr, ptr, 16, ptr, 2, None)
+    assert L.ga_sk_count_build_from(None, *tail) == gn.GA_ERR_BAD_ARG
+    src.n_sources = 0
+    assert L.ga_sk_count_build_from(C.byref(src), *tail) == gn.GA_ERR_BAD_ARG
+    src.n_sources = 2
+    src.records[0], src.index[0], src.l1_capacity[0] = ptr.value, ptr.value, 1 << 25
+    src.records[1], src.index[1], src.l1_capacity[1] = ptr.value, ptr.value, 16
+    assert L.ga_sk_count_build_from(C.byref(src), *tail) == gn.GA_ERR_BAD_ARG
+    assert b"sources" in L.ga_last_error()
+    assert L.ga_sk_count_build_spill_from(None, ptr, 4, ptr, 1, 31, 3, 4096, ptr, 1, ptr, ptr, 16, ptr, ptr, 2,
+                                          None) == gn.GA_ERR_BAD_ARG
