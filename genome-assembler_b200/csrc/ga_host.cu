@@ -67,6 +67,16 @@ extern "C" int ga_fill_bytes(void* dev, int value, uint64_t bytes, ga_stream str
     return GA_OK;
 }
 
+extern "C" int ga_copy_bytes(void* dst, const void* src, uint64_t bytes, ga_stream stream) {
+    if (bytes == 0) return GA_OK;
+    if (!dst || !src) {
+        ga_set_error("ga_copy_bytes: null pointer");
+        return GA_ERR_BAD_ARG;
+    }
+    GA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return GA_OK;
+}
+
 extern "C" void ga_free_host(void* p) { free(p); }
 
 // The hot kernels are random 16-byte probes; a DRAM fetch wider than one 32-byte sector is

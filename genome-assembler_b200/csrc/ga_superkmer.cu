@@ -862,6 +862,7 @@ struct SkSources {
     const u32* index[SB_MAX_SEG];
     u64 cap1[SB_MAX_SEG];
     u64 first_bucket;              // global id of this launch's bucket 0 (the level-1 bucket comes from the global id)
+    u64* counter;                  // solid windows written so far, shared by all ranks (the output is one rank's), or null
     u32 n;
 };
 
@@ -1419,7 +1420,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                 ok = sk_bucket_body<MemShared, DEEP>(bases, meta, gather, w, threshold, mem, cap, q_cap,
                                     note_spill + 2u * (size_t)blockIdx.x * note_spill_cap, note_spill_cap, max_solid,
                                     edge_stamp_out == nullptr, parts, part, ctl,
-                                    solid_keys_out, edge_stamp_out, out_capacity, counters + 1);
+                                    solid_keys_out, edge_stamp_out, out_capacity, src.counter ? src.counter : counters + 1);
             }
             if (threadIdx.x == 0) {
                 u32 top = sp - 1u;
@@ -1501,7 +1502,7 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
         const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
         const bool ok = sk_bucket_body<MemGlobal, false>(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
                                        edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
-                                       out_capacity, counters + 1);
+                                       out_capacity, src.counter ? src.counter : counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
         __threadfence();
     }
@@ -1687,6 +1688,7 @@ static bool sk_sources(const ga_sk_sources* from, uint32_t n_segments, SkSources
         src.cap1[g] = from->l1_capacity[g];
     }
     src.first_bucket = from->first_bucket;
+    src.counter = (u64*)from->solid_counter;
     src.n = from->n_sources;
     return true;
 }

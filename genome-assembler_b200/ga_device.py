@@ -690,11 +690,13 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
 
 def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, k: int, threshold: int,
                    n_occ: int, status, index=None, l1_capacity: int = 0, l2_bits: int = 0, want_stamps: bool = True,
-                   sources=None):
+                   sources=None, out=None):
     """Bucket-sorted records -> (solid keys (cap, 1) int64, n_solid, candidate edge stamps int64[4*cap]).
     offsets: n_segments rows of n_buckets+1 record positions (one row on a single GPU, one per source
     rank after the multi-GPU exchange); hist[b] & 0xFFFFFFFF = windows of bucket b over all segments.
-    ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory)."""
+    ga_sk_count_build (+ ga_sk_count_build_spill for what does not fit shared memory).
+    out = (keys buffer, stamps buffer, capacity): write the result there instead (buffers shared by all ranks with
+    sources.solid_counter set -- the caller then reads the total after a barrier; returns (keys, None, stamps))."""
     L = gn.lib()
     dev = hist.device
     # the state word of a table slot names a record (its number inside the bucket, or its slot inside the level-1
@@ -706,12 +708,15 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     _mark("sk bucket: checks")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
     out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
-    spill_cap = 1 << 16
+    spill_cap = 1 << 16 if out is None else max(1 << 16, 2 * n_buckets)   # shared output: the pass cannot be repeated
     while True:
         counters = torch.zeros(16, dtype=torch.int64, device=dev)      # [8..14]: phase cycles of a GA_SB_PROFILE build
         spill_list = torch.empty(spill_cap, dtype=torch.int64, device=dev)
-        solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
-        edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64) if want_stamps else None
+        if out is not None:
+            solid_keys, edge_stamp, out_cap = out
+        else:
+            solid_keys = workspace("sk_solid_keys", (out_cap, 1), torch.int64)
+            edge_stamp = workspace("sk_edge_stamp", 4 * out_cap, torch.int64) if want_stamps else None
         status.zero_()
         _mark("sk bucket: buffers")
         with _timed("sk_bucket", n_occ):
@@ -740,6 +745,8 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
                   "%d candidates" % (n_pass & 0xFFFFFFFF, n_pass >> 32, n_buckets, n_solid, n_spill, n_distinct,
                                      n_cand), file=_sys.stderr, flush=True)
         if n_spill > spill_cap:
+            if out is not None:
+                raise gn.GaError("bucketed count: more passes to spill than the list holds (shared output)")
             spill_cap = n_spill
             continue
         if n_spill:
@@ -768,6 +775,9 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
             del scratch
         if _check_status(status) & gn.ST_TABLE_FULL:
             raise gn.GaError("bucketed count: a spilled bucket overflowed its scratch table")
+        if out is not None:
+            _mark("sk bucket pass")
+            return solid_keys, None, edge_stamp
         if n_solid <= out_cap:
             break
         out_cap = n_solid

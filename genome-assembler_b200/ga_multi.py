@@ -377,11 +377,16 @@ def _exchange_push(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd):
 _GEOMETRY = {}          # (device, l1_bits) -> slots per level-1 bucket in force (the same on every rank, only grows)
 
 
-def _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots_wanted, feed, gn, gd):
+_OUT_ROWS = {}          # device -> rows of the shared result buffers in force (the same on every rank, only grows)
+
+
+def _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots_wanted, n_occ, feed, gn, gd):
     """EXCHANGE = "peer": the exchange fused into the count.  Nothing is copied: every rank leaves its records in
     its own level-1 slots (peer-mapped regions), sorts a 32-bit index, and the owner of a bucket range gathers the
     records of its buckets from all ranks -- its own memory or NVLink -- inside the bucket kernel
-    (ga_sk_count_build_from).  Returns (solid keys, n_solid, candidate edge stamps) of this rank's buckets."""
+    (ga_sk_count_build_from).  The results go where the graph is built: every rank appends its solid windows and
+    candidate edge stamps to rank 0's buffers (mapped everywhere; one shared counter), so no gather follows.
+    Returns (solid keys, n_solid, candidate edge stamps) of ALL ranks on rank 0, (None, 0, None) elsewhere."""
     dev = reads.words.device
     world, rank = dist.get_world_size(), dist.get_rank()
     n_l1 = 1 << l1_bits
@@ -423,19 +428,47 @@ def _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots_want
                            input_split_sizes=[n + 1 for n in sizes])
     dist.all_to_all_single(got_hist, hist, output_split_sizes=[mine] * world, input_split_sizes=sizes)
     gd._mark("multi: exchange 0")
-    if not mine:
-        empty = torch.zeros((0, 1), dtype=torch.int64, device=dev)
-        return empty, 0, torch.zeros(0, dtype=torch.int64, device=dev)
-    summed = got_hist.view(world, mine).sum(dim=0).contiguous()
-    n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
     sources = gn.GaSkSources()
     for g in range(world):
         sources.records[g] = slots_region.mapped[g]
         sources.index[g] = index_region.mapped[g]
         sources.l1_capacity[g] = cap1
     sources.first_bucket, sources.n_sources = bounds[rank], world
-    return gd.sk_bucket_pass(None, None, got_off, world, summed, mine, k, threshold, max(n_occ_mine, 1), reads.status,
-                             l2_bits=l2_bits, sources=sources)
+    if mine:
+        summed = got_hist.view(world, mine).sum(dim=0).contiguous()
+        n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
+    # shared result buffers on rank 0: [counter, padded to 64 B][keys: rows x 8 B][stamps: rows x 32 B]
+    L = gn.lib()
+    out_region = _PEERS.setdefault((dev.index, "solid"), PeerRegion())
+    rows = max(_OUT_ROWS.get(dev.index, 0), 1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    while True:
+        _OUT_ROWS[dev.index] = rows
+        out_region.ensure(64 + rows * 40)             # collective; its barriers order the zeroing below for a retry
+        root = out_region.mapped[0]
+        if rank == 0:
+            gn.check(L.ga_fill_bytes(C.c_void_p(root), 0, 64, gd._stream()))
+        # nobody appends before the counter is zero: a one-word all-reduce, stream-ordered on every rank
+        dist.all_reduce(total)
+        if mine:
+            sources.solid_counter = root
+            gd.sk_bucket_pass(None, None, got_off, world, summed, mine, k, threshold, max(n_occ_mine, 1), reads.status,
+                              l2_bits=l2_bits, sources=sources,
+                              out=(_RawBuffer(root + 64, dev), _RawBuffer(root + 64 + 8 * rows, dev), rows))
+        # every rank's results have landed (all-reduce = barrier), then rank 0 reads the total and tells the others
+        total.zero_()
+        dist.all_reduce(total)
+        if rank == 0:
+            gn.check(L.ga_copy_bytes(gn.ptr(total), C.c_void_p(root), 8, gd._stream()))
+        dist.broadcast(total, 0)
+        n_all = int(total.item())
+        total.zero_()
+        if n_all <= rows:
+            break
+        rows = n_all + n_all // 16               # did not fit (nothing was written beyond the rows): count again
+    if rank != 0:
+        return None, 0, None
+    return _RawBuffer(root + 64, dev), n_all, _RawBuffer(root + 64 + 8 * rows, dev)
 
 
 def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
@@ -458,10 +491,14 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     if route == "peer" and dist.get_backend() == "nccl":
         # 1.-3. in one go: records stay where they were cut, the owners gather them while they count
         slots = gd.sk_l1_capacity(reads, k, l1_bits, most_records)        # the same number on every rank
-        solid_keys, n_solid, edge_stamp = _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots, feed,
-                                                          gn, gd)
-        key_parts.append(solid_keys[:n_solid])
-        stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4))
+        all_keys, n_all, all_stamps = _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots, n_occ,
+                                                      feed, gn, gd)
+        gd._mark("multi: bucket pass")
+        if rank != 0:
+            return None
+        if n_all == 0:
+            return graph
+        return gd.resolve_and_emit(graph, all_keys, n_all, all_stamps, k, reads.alphabet, reads.status, to_host)
     else:
         # 1. local records by bucket, 2. every bucket's records to its owner
         exchange = _exchange_push if (route == "push" and dist.get_backend() == "nccl") else _exchange_nccl

@@ -38,7 +38,7 @@ class GaPrefilter(C.Structure):
 
 class GaSkSources(C.Structure):
     _fields_ = [("records", C.c_void_p * 16), ("index", C.c_void_p * 16), ("l1_capacity", C.c_uint64 * 16),
-                ("first_bucket", C.c_uint64), ("n_sources", C.c_uint32)]
+                ("first_bucket", C.c_uint64), ("solid_counter", C.c_void_p), ("n_sources", C.c_uint32)]
 
 
 class GaSketch(C.Structure):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "ga_launch_count": (_u64, []),
     "ga_set_l2_fetch_granularity": (_i32, [_i32]),
     "ga_fill_bytes": (_i32, [_vp, _i32, _u64, _vp]),
+    "ga_copy_bytes": (_i32, [_vp, _vp, _u64, _vp]),
     "ga_key_words": (_i32, [_i32, _i32]),
     "ga_slot_bytes": (_i32, [_i32]),
     "ga_parse_reads": (_i32, [_vp, _u64, _vp, _vp, _u64, C.POINTER(C.c_uint64), C.POINTER(C.c_int),

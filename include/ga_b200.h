@@ -92,6 +92,7 @@ int ga_device_count(void);                 /* number of CUDA devices, 0 without 
 uint64_t ga_launch_count(void);            /* kernels of this library launched so far (process-wide) */
 int ga_set_l2_fetch_granularity(int bytes); /* 32, 64 or 128: DRAM bytes fetched per L2 miss (hint) */
 int ga_fill_bytes(void* dev, int value, uint64_t bytes, ga_stream stream);
+int ga_copy_bytes(void* dst, const void* src, uint64_t bytes, ga_stream stream);   /* cudaMemcpyAsync, any direction (peer-mapped too) */
 
 /* key geometry: 1 word (64-bit keys) when (k-1)*sym_bits <= 63, 2 words when <= 127,
  * otherwise 0 (unsupported on this build). */
@@ -231,6 +232,10 @@ typedef struct ga_sk_sources {
     const uint32_t* index[GA_PEER_MAX_RANKS];   /* index form of ga_sk_scatter_buckets, one array per source rank */
     uint64_t l1_capacity[GA_PEER_MAX_RANKS];
     uint64_t first_bucket;
+    uint64_t* solid_counter;  /* optional device word shared by all ranks: solid windows appended so far to
+                               * solid_keys_out_dev / edge_stamp_out_dev, which are then the SAME buffers on every rank
+                               * (one rank's, mapped with ga_peer_open) -- results land where the graph is built, no
+                               * gather afterwards; zeroed by the owner before any rank launches.  NULL: counters_dev[1] */
     uint32_t n_sources;
 } ga_sk_sources;
 int ga_sk_count_build_from(const ga_sk_sources* sources, const uint64_t* offsets_dev, const uint64_t* hist_dev,
