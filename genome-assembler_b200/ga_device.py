@@ -822,6 +822,8 @@ def resolve_and_emit(graph, solid_keys, n_solid: int, edge_stamp, k: int, alphab
     L = gn.lib()
     dev = solid_keys.device
     kw = 1
+    if n_solid >= (1 << 31) - 64:        # node ids, CSR row pointers and columns are 32-bit
+        raise gn.GaError("graph too large for the 32-bit CSR: %d solid windows" % n_solid)
     solid_cap = int(1.7 * n_solid) + 64
     solid = torch.empty(solid_cap * L.ga_slot_bytes(kw), dtype=torch.uint8, device=dev)
     status.zero_()

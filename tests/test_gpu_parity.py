@@ -315,6 +315,130 @@ def test_bucket_segments_match_whole(monkeypatch):
     assert torch.equal(st1[o1], st2[o2])
 
 
+def _two_shard_exchange_case(monkeypatch, target=3000):
+    """Two read shards cut separately with ONE geometry (what two ranks hold before the exchange), plus the whole."""
+    import torch
+    import ga_device as gd
+    gold = GOLDEN["cases"]["nd-unpaired"]
+    reads = reads_for(gold["recipe"])
+    k, F = gold["k"], gold["F"]
+    monkeypatch.setattr(gd, "SUPERKMER_TARGET", target)
+    whole = gd.DeviceReads(reads, False)
+    n_occ = whole.windows_total(k)
+    l1_bits, l2_bits = gd.sk_geometry(n_occ)
+    cut = len(reads) // 3
+    shards = [gd.DeviceReads(reads[lo:hi], False, first_read=lo, estride=whole.estride)
+              for lo, hi in ((0, cut), (cut, len(reads)))]
+    cap1 = max(gd.sk_l1_capacity(sh, k, l1_bits) for sh in shards)
+    keys1, n1, st1 = gd.superkmer_stamps(whole, k, F)
+    o1 = torch.argsort(keys1[:n1, 0])
+    want = (keys1[:n1, 0][o1].clone(), st1[:4 * n1].view(-1, 4)[o1].clone())
+    assert n1 == gold["n_solid"]
+    return gd, whole, shards, k, F, n_occ, l1_bits, l2_bits, cap1, want
+
+
+def test_bucket_sources_form_matches_whole(monkeypatch):
+    """The exchange fused into the count (ga_sk_count_build_from, multi-GPU "peer" route) on one GPU: two read shards
+    stay in their own level-1 slots with their own index, the bucket kernel gathers every bucket from both, and the
+    results are appended through a shared counter -- same solid set and candidate stamps as one pass over all reads.
+    Also with the loads two spans ahead of the walk (GA_SK_DEEP)."""
+    import torch
+    import ga_native as gn
+    gd, whole, shards, k, F, n_occ, l1_bits, l2_bits, cap1, want = _two_shard_exchange_case(monkeypatch)
+    dev = whole.words.device
+    n_buckets = 1 << (l1_bits + l2_bits)
+    held = []
+    for sh in shards:
+        keep = {}
+
+        def alloc(name, n, dtype, keep=keep):
+            keep[name] = torch.empty(int(n), dtype=dtype, device=dev)
+            return keep[name]
+        rec, _, offsets, hist, total, index, got_cap = gd.sk_scatter_local(sh, k, l1_bits, l2_bits, dense=False, cap1=cap1,
+                                                                       alloc=alloc)
+        assert got_cap == cap1
+        held.append((rec, index, offsets.clone(), hist.clone(), total))
+    seg = torch.stack([h[2] for h in held]).contiguous()
+    hist = (held[0][3] + held[1][3]).contiguous()
+    for deep in ("", "1"):
+        monkeypatch.setenv("GA_SK_DEEP", deep) if deep else monkeypatch.delenv("GA_SK_DEEP", raising=False)
+        rows = want[0].shape[0] + 100
+        shared = torch.zeros(8 + rows * 5, dtype=torch.int64, device=dev)       # counter | keys | 4 stamps per key
+        src = gn.GaSkSources()
+        for g, h in enumerate(held):
+            src.records[g], src.index[g], src.l1_capacity[g] = h[0].data_ptr(), h[1].data_ptr(), cap1
+        src.first_bucket, src.n_sources, src.solid_counter = 0, 2, shared.data_ptr()
+        keys_out, stamps_out = shared[8:8 + rows], shared[8 + rows:]
+        gd.sk_bucket_pass(None, None, seg, 2, hist, n_buckets, k, F, n_occ, whole.status, l2_bits=l2_bits, sources=src,
+                          out=(keys_out, stamps_out, rows))
+        n2 = int(shared[0].item())
+        assert n2 == want[0].shape[0]
+        o2 = torch.argsort(keys_out[:n2])
+        assert torch.equal(keys_out[:n2][o2], want[0])
+        assert torch.equal(stamps_out[:4 * n2].view(-1, 4)[o2], want[1])
+
+
+@pytest.mark.parametrize("kernel", ["gather", "sorted"])
+def test_push_kernels_deliver_every_record(kernel, monkeypatch):
+    """ga_sk_push_records (index + gather) and ga_sk_push_sorted (level-2 split + send in one pass) with two
+    "ranks" on one GPU: both shards push the records of both owners' bucket ranges into the owners' receive arrays
+    (plain device buffers here, NVLink-mapped ones on a node), and each owner's bucket pass over its two segments
+    gives the solid set and stamps of its bucket range."""
+    import ctypes as C
+    import torch
+    import ga_native as gn
+    gd, whole, shards, k, F, n_occ, l1_bits, l2_bits, cap1, want = _two_shard_exchange_case(monkeypatch)
+    L = gn.lib()
+    dev = whole.words.device
+    world = 2
+    n_buckets = 1 << (l1_bits + l2_bits)
+    bounds = [g * n_buckets // world for g in range(world + 1)]
+    local = []
+    for sh in shards:
+        if kernel == "gather":
+            rec, _, offsets, hist, total, index, _ = gd.sk_scatter_local(sh, k, l1_bits, l2_bits, dense=False, cap1=cap1,
+                                                                     alloc=lambda name, n, dt: torch.empty(int(n), dtype=dt, device=dev))
+            local.append((rec, index, offsets, hist, None, None))
+        else:
+            rec, _, offsets, hist, total, _, _, cursors1, cursors2 = gd.sk_scatter_local(
+                sh, k, l1_bits, l2_bits, dense=False, level2=False, cap1=cap1,
+                alloc=lambda name, n, dt: torch.empty(int(n), dtype=dt, device=dev))
+            local.append((rec, None, offsets, hist, cursors1, cursors2))
+    cuts = [[int(x) for x in l[2][torch.tensor(bounds, device=dev)].tolist()] for l in local]
+    matrix = [[cuts[s][g + 1] - cuts[s][g] for g in range(world)] for s in range(world)]
+    import ga_multi
+    recv = [(torch.zeros(2 * sum(matrix[s][g] for s in range(world)) + 2, dtype=torch.int64, device=dev),
+             torch.zeros(sum(matrix[s][g] for s in range(world)) + 1, dtype=torch.int64, device=dev)) for g in range(world)]
+    plans = [ga_multi.push_plan(matrix, s) for s in range(world)]
+    for s, (rec, index, offsets, hist, cursors1, cursors2) in enumerate(local):
+        dst_start = plans[s][0]
+        cut = (C.c_uint64 * (world + 1))(*cuts[s])
+        dst_b = (C.c_void_p * world)(*[recv[g][0].data_ptr() + 16 * dst_start[g] for g in range(world)])
+        dst_m = (C.c_void_p * world)(*[recv[g][1].data_ptr() + 8 * dst_start[g] for g in range(world)])
+        if kernel == "gather":
+            gn.check(L.ga_sk_push_records(gn.ptr(rec), cap1, gn.ptr(index), gn.ptr(offsets), l1_bits, l2_bits, world, cut,
+                                          dst_b, dst_m, gd._stream()))
+        else:
+            gn.check(L.ga_sk_push_sorted(gn.ptr(rec), cap1, gn.ptr(cursors1), l1_bits, l2_bits, gn.ptr(cursors2), world,
+                                         cut, dst_b, dst_m, gd._stream()))
+    got_keys, got_stamps = [], []
+    for g in range(world):
+        mine = bounds[g + 1] - bounds[g]
+        per_source = torch.stack([l[3][bounds[g]:bounds[g + 1]] for l in local])
+        seg = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
+        seg[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
+        seg += torch.tensor(plans[g][1], dtype=torch.int64, device=dev).view(world, 1)
+        summed = per_source.sum(dim=0).contiguous()
+        keys, n, stamps = gd.sk_bucket_pass(recv[g][0], recv[g][1], seg.contiguous(), world, summed, mine, k, F,
+                                            max(int((summed & 0xFFFFFFFF).sum().item()), 1), whole.status)
+        got_keys.append(keys[:n, 0].clone())
+        got_stamps.append(stamps[:4 * n].view(-1, 4).clone())
+    keys, stamps = torch.cat(got_keys), torch.cat(got_stamps)
+    o = torch.argsort(keys)
+    assert torch.equal(keys[o], want[0])
+    assert torch.equal(stamps[o], want[1])
+
+
 @pytest.mark.parametrize("k", [27, 31, 32])
 def test_scatter_kernels_cut_identical_records(k, monkeypatch):
     """The lane-per-read scatter kernel (both CTA shapes) and the warp-per-read one cut the same reads into the
