@@ -967,8 +967,12 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u
         if (active) {
             const u32 nwin = meta_windows(om);
             const u64 top = j ? (ohi << (2u * j)) | (olo >> (64u - 2u * j)) : ohi;
+#ifdef GA_SK_MERGE
             f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), (((otag & SK_TAG_MASK) + 1u) << 5) | j,
               (otag >> SK_TAG_BITS) + 1u);
+#else
+            f(top, meta_ordinal(om) + j, j + 1u < nwin || meta_has_next(om), ((otag + 1u) << 5) | j, 1u);
+#endif
         }
         __syncwarp();
     }
@@ -976,7 +980,7 @@ __device__ __forceinline__ void sk_for_each_window(u64 rhi, u64 rlo, u64 meta, u
 
 // returns false when the pass does not fit (table, queue or solid area full): the caller splits it or lists it
 // for the spill path
-template <class Mem, bool DEEP>
+template <class Mem, bool DEEP, bool SRC>
 __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                                                SkGather gather, int w, u32 threshold, const Mem& mem, u32 cap,
                                                u32 q_cap, u64* __restrict__ q_spill, u32 q_spill_cap, u32 max_solid,
@@ -999,7 +1003,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         u32 sg;
         return where2(idx, sg);
     };
-    const bool indexed = gather.index != nullptr || gather.sources;
+    const bool indexed = gather.index != nullptr || SRC;
 #ifdef GA_SB_PROFILE
     // probe build: warp-cycles per phase summed into counters[8..13] = n_solid_global[7..12] (clear, walk, wait at
     // the barrier that ends the walk, notes, output, whole body)
@@ -1068,7 +1072,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
     auto entry = [&](u32 sp) -> u32 {
         const u32 idx = (sp & 0x7FFFFFFFu) + lane;
         if (!indexed || lane >= span_take(sp) || idx >= nrec32) return 0u;
-        if (!gather.sources) return __ldg(gather.index + where(idx));
+        if (!SRC) return __ldg(gather.index + where(idx));
         u32 sg;
         const u64 at = where2(idx, sg);
         return __ldg(ctl.seg_idx[sg] + at) | (sg << SK_ENT_BITS);        // the entry may live on another GPU
@@ -1079,7 +1083,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         b = make_ulonglong2(0, 0);
         mt = 0;
         if (lane >= span_take(sp) || idx >= nrec) return;
-        if (gather.sources) {
+        if (SRC) {
             sk_load_slot(ctl.seg_rec[e >> SK_ENT_BITS], e & SK_ENT_MASK, b, mt);   // local or over NVLink
         } else if (gather.index) {
             sk_load_slot((const u64*)bases, gather.base + e, b, mt);       // a 32-byte slot of the level-1 bucket
@@ -1267,7 +1271,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
         const u32 tag = (u32)(payload >> 5) - 1u, j = (u32)payload & 31u;
         ulonglong2 b;
         u64 mt;
-        if (gather.sources) {
+        if (SRC) {
             u32 sg;
             const u64 at = where2(tag, sg);
             sk_load_slot(ctl.seg_rec[sg], __ldg(ctl.seg_idx[sg] + at), b, mt);
@@ -1309,7 +1313,7 @@ __device__ __forceinline__ bool sk_bucket_body(const ulonglong2* __restrict__ ba
 // parts comes from running estimates of the three per window of the bucket (the first buckets of a CTA start
 // pessimistic); a pass that still does not fit is split in two; only passes that would need more than 32 parts
 // (or buckets of more than 65536 records) go to the spill list (entry = bucket | parts << 32 | part << 48).
-template <bool DEEP>
+template <bool DEEP, bool SRC>
 __global__ void __launch_bounds__(SB_THREADS, SB_CTAS_PER_SM)
 sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta, const u64* __restrict__ offsets,
                  u32 n_seg, const u64* __restrict__ hist, u64 n_buckets, int w, u32 threshold, u32 cap_limit,
@@ -1354,10 +1358,11 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
-            for (u32 sg = 0; sg < src.n; ++sg) {
-                ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
-                ctl.seg_idx[sg] = src.index[sg];
-            }
+            if (SRC)
+                for (u32 sg = 0; sg < src.n; ++sg) {
+                    ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
+                    ctl.seg_idx[sg] = src.index[sg];
+                }
             // prediction for this bucket: pessimistic ratios until the fit has seen a few buckets
             const float x = (float)nw;
             const float first_guess[3] = {0.32f, 0.2f, 0.03f};
@@ -1396,8 +1401,9 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
             if (sp == 0) break;
             const u32 item = ctl.stack[sp - 1];
             const u64 ed = (u64)ctl.est[0] + 48u, eq = (u64)ctl.est[1] + 32u, es = (u64)ctl.est[2] + 16u;
-            __syncthreads();
             const u32 parts = item >> 16, part = item & 0xFFFFu;
+            __syncthreads();           // everybody has read the item before thread 0 replaces it below (dropping this
+                                       // barrier where the body's own would do measured 139.1 against 139.3 ms: noise)
             bool ok = false;
             if (parts <= 32u) {
                 // the pool of this pass: solid windows and notes for the expected numbers + a margin, the table gets
@@ -1416,8 +1422,8 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
                 mem.stamps = mem.skeys + 8u * max_solid;
                 mem.queue = mem.stamps + 32u * max_solid;
                 mem.state = mem.queue + SB_NOTE_BYTES * q_cap;
-                const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
-                ok = sk_bucket_body<MemShared, DEEP>(bases, meta, gather, w, threshold, mem, cap, q_cap,
+                const SkGather gather{index, (b >> l2_bits) * l1_capacity, SRC};
+                ok = sk_bucket_body<MemShared, DEEP, SRC>(bases, meta, gather, w, threshold, mem, cap, q_cap,
                                     note_spill + 2u * (size_t)blockIdx.x * note_spill_cap, note_spill_cap, max_solid,
                                     edge_stamp_out == nullptr, parts, part, ctl,
                                     solid_keys_out, edge_stamp_out, out_capacity, src.counter ? src.counter : counters + 1);
@@ -1461,6 +1467,7 @@ sk_bucket_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ m
 
 // spill path: the same body over global scratch (one slice per CTA), for passes that do not fit the
 // shared-memory pool even after splitting
+template <bool SRC>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restrict__ meta,
                        const u64* __restrict__ offsets, u32 n_seg, u64 n_buckets,
@@ -1493,14 +1500,15 @@ sk_bucket_spill_kernel(const ulonglong2* __restrict__ bases, const u64* __restri
             }
             ctl.seg_pre[n_seg] = run;
             ctl.n_seg = n_seg;
-            for (u32 sg = 0; sg < src.n; ++sg) {
-                ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
-                ctl.seg_idx[sg] = src.index[sg];
-            }
+            if (SRC)
+                for (u32 sg = 0; sg < src.n; ++sg) {
+                    ctl.seg_rec[sg] = src.rec[sg] + 4u * (((src.first_bucket + b) >> l2_bits) * src.cap1[sg]);
+                    ctl.seg_idx[sg] = src.index[sg];
+                }
         }
         __syncthreads();
-        const SkGather gather{index, (b >> l2_bits) * l1_capacity, src.n != 0u};
-        const bool ok = sk_bucket_body<MemGlobal, false>(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
+        const SkGather gather{index, (b >> l2_bits) * l1_capacity, SRC};
+        const bool ok = sk_bucket_body<MemGlobal, false, SRC>(bases, meta, gather, w, threshold, mem, cap, 2u * cap, nullptr, 0u, cap,
                                        edge_stamp_out == nullptr, parts, part, ctl, solid_keys_out, edge_stamp_out,
                                        out_capacity, src.counter ? src.counter : counters + 1);
         if (!ok && threadIdx.x == 0) atomicOr(status, GA_ST_TABLE_FULL);
@@ -1719,8 +1727,9 @@ static int sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const
     }
     // the attribute is per device: set it on every call (cheap) instead of caching a process-wide flag
     const bool deep = sources && getenv("GA_SK_DEEP");           // opt-in: loads two spans ahead of the walk (measured: +-0)
-    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
-    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
+    GA_CUDA(cudaFuncSetAttribute(sk_bucket_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_POOL_BYTES));
     if (max_solid > 16000) max_solid = 16000;
     const u64 most = (u64)ga_sm_count() * SB_CTAS_PER_SM;
     const unsigned grid = (unsigned)(n_buckets < most ? n_buckets : most);
@@ -1728,15 +1737,16 @@ static int sk_count_build(const void* bases_dev, const uint64_t* meta_dev, const
     u64* note_spill = nullptr;
     ga_pool_retain();
     GA_CUDA(cudaMallocAsync((void**)&note_spill, (size_t)grid * SB_NOTE_SPILL * 16u, (cudaStream_t)stream));
-#define GA_SB_LAUNCH(DEEP)                                                                                          \
-    sk_bucket_kernel<DEEP><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                               \
+#define GA_SB_LAUNCH(DEEP, SRC)                                                                                     \
+    sk_bucket_kernel<DEEP, SRC><<<grid, SB_THREADS, SB_POOL_BYTES, (cudaStream_t)stream>>>(                          \
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments,                    \
         (const u64*)hist_dev, n_buckets, w,                                                                         \
         (u32)threshold, table_slots, max_solid, (u64*)solid_keys_out_dev, (u64*)edge_stamp_out_dev, out_capacity,   \
         (u64*)counters_dev, (u64*)spill_list_dev, spill_capacity, status_dev, sources ? nullptr : index_dev,        \
         l1_capacity, l2_bits, note_spill, SB_NOTE_SPILL, src)
-    if (deep) GA_SB_LAUNCH(true);
-    else GA_SB_LAUNCH(false);
+    if (deep) GA_SB_LAUNCH(true, true);
+    else if (sources) GA_SB_LAUNCH(false, true);
+    else GA_SB_LAUNCH(false, false);
 #undef GA_SB_LAUNCH
     ga_note_launches(1);
     const cudaError_t launched = cudaGetLastError();
@@ -1798,7 +1808,8 @@ static int sk_count_build_spill(const void* bases_dev, const uint64_t* meta_dev,
         return GA_ERR_BAD_ARG;
     }
     if (n_spill == 0) return GA_OK;
-    sk_bucket_spill_kernel<<<n_ctas, SB_THREADS, 0, (cudaStream_t)stream>>>(
+    auto* spill = sources ? sk_bucket_spill_kernel<true> : sk_bucket_spill_kernel<false>;
+    spill<<<n_ctas, SB_THREADS, 0, (cudaStream_t)stream>>>(
         (const ulonglong2*)bases_dev, (const u64*)meta_dev, (const u64*)offsets_dev, n_segments, n_buckets,
         (const u64*)spill_list_dev, n_spill, w,
         (u32)(threshold > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : threshold), table_slots, (unsigned char*)scratch_dev,
