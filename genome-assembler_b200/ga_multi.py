@@ -166,6 +166,8 @@ class PeerRegion:
         self.nbytes, self.local, self.mapped = 0, None, []
 
     def ensure(self, nbytes: int):
+        """Collective.  A failure on any rank (allocation, CUDA IPC) raises GaError on EVERY rank, after all ranks
+        have passed the same collectives -- nobody is left waiting in one."""
         import ga_native as gn
         if self.local and nbytes <= self.nbytes:
             return
@@ -177,23 +179,42 @@ class PeerRegion:
         nbytes = (nbytes + nbytes // 16 + 65536) // 256 * 256
         handle = (C.c_uint8 * 64)()
         address = C.c_void_p()
+        problem = ""
         if L.ga_peer_alloc(nbytes, C.byref(address), handle) != gn.GA_OK:
             torch.cuda.empty_cache()                     # the caching allocator may sit on the room
-            gn.check(L.ga_peer_alloc(nbytes, C.byref(address), handle))
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
-        everyone = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+            if L.ga_peer_alloc(nbytes, C.byref(address), handle) != gn.GA_OK:
+                problem = gn.last_error()
+        mine = torch.tensor(list(handle) + [0 if problem else 1], dtype=torch.uint8, device=dev)
+        everyone = torch.empty(world * 65, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(everyone, mine)
-        everyone = everyone.cpu().numpy().reshape(world, 64)
-        self.mapped = []
-        for g in range(world):
-            if g == rank:
-                self.mapped.append(address.value)
-                continue
-            peer = C.c_void_p()
-            raw = (C.c_uint8 * 64)(*[int(x) for x in everyone[g]])
-            gn.check(L.ga_peer_open(raw, C.byref(peer)))
-            self.mapped.append(peer.value)
-        self.local, self.nbytes = address.value, nbytes
+        everyone = everyone.cpu().numpy().reshape(world, 65)
+        mapped = []
+        if everyone[:, 64].all():
+            for g in range(world):
+                if g == rank:
+                    mapped.append(address.value)
+                    continue
+                peer = C.c_void_p()
+                raw = (C.c_uint8 * 64)(*[int(x) for x in everyone[g, :64]])
+                if L.ga_peer_open(raw, C.byref(peer)) != gn.GA_OK:
+                    problem = problem or gn.last_error()
+                    mapped.append(0)
+                else:
+                    mapped.append(peer.value)
+        else:
+            problem = problem or "rank %d could not allocate" % int((everyone[:, 64] == 0).argmax())
+        fine = torch.tensor([0 if problem else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(fine, op=dist.ReduceOp.MIN)
+        if not int(fine.item()):
+            for g, at in enumerate(mapped):              # undo what this rank did, then fail on every rank together
+                if g != rank and at:
+                    L.ga_peer_close(C.c_void_p(at))
+            torch.cuda.synchronize()
+            dist.barrier()
+            if address.value:
+                L.ga_peer_free(address)
+            raise gn.GaError("peer memory: %s" % (problem or "another rank failed"))
+        self.mapped, self.local, self.nbytes = mapped, address.value, nbytes
 
 
 class PeerBuffers(PeerRegion):
@@ -222,6 +243,33 @@ class PeerBuffers(PeerRegion):
 
 
 _PEERS = {}
+_PEER_OK = {}
+
+
+def peers_available() -> bool:
+    """Collective, once per process and device: can every rank map every other rank's memory (CUDA IPC between the
+    processes of this node)?  If any rank cannot, all ranks take the NCCL route -- the exchange is then two
+    all_to_all_single calls instead of one kernel over peer memory, the result is the same."""
+    dev = torch.cuda.current_device()
+    if dev not in _PEER_OK:
+        import sys
+        ok, probe, why = 1, PeerRegion(), ""
+        try:
+            probe.ensure(4096)
+        except Exception as exc:        # noqa: BLE001 -- reported below, every rank must reach the all-reduce
+            ok, why = 0, str(exc)
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", dev))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        _PEER_OK[dev] = bool(int(flag.item()))
+        if ok:
+            try:
+                probe.close()
+            except Exception:           # noqa: BLE001
+                pass
+        if not _PEER_OK[dev] and dist.get_rank() == 0:
+            print("ga_multi: peer memory over CUDA IPC is not available (%s); records travel by NCCL all-to-all"
+                  % (why or "another rank failed"), file=sys.stderr)
+    return _PEER_OK[dev]
 
 
 def release_peers():
@@ -488,7 +536,9 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
     key_parts, stamp_parts = [], []
     received = []
     route = EXCHANGE if EXCHANGE != "auto" else ("peer" if world >= 4 else "push")
-    if route == "peer" and dist.get_backend() == "nccl":
+    if route != "nccl" and not (dist.get_backend() == "nccl" and peers_available()):
+        route = "nccl"
+    if route == "peer":
         # 1.-3. in one go: records stay where they were cut, the owners gather them while they count
         slots = gd.sk_l1_capacity(reads, k, l1_bits, most_records)        # the same number on every rank
         all_keys, n_all, all_stamps = _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots, n_occ,
@@ -501,7 +551,7 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
         return gd.resolve_and_emit(graph, all_keys, n_all, all_stamps, k, reads.alphabet, reads.status, to_host)
     else:
         # 1. local records by bucket, 2. every bucket's records to its owner
-        exchange = _exchange_push if (route == "push" and dist.get_backend() == "nccl") else _exchange_nccl
+        exchange = _exchange_push if route == "push" else _exchange_nccl
         received = exchange(reads, k, l1_bits, l2_bits, n_buckets, feed, gn, gd)
     for h, (works, got_bases, got_meta, got_hist, starts, mine) in enumerate(received):
         for wk in works:
