@@ -498,14 +498,23 @@ def _count_in_place(reads, k, threshold, l1_bits, l2_bits, n_buckets, slots_want
             gn.check(L.ga_fill_bytes(C.c_void_p(root), 0, 64, gd._stream()))
         # nobody appends before the counter is zero: a one-word all-reduce, stream-ordered on every rank
         dist.all_reduce(total)
+        error = None
         if mine:
             sources.solid_counter = root
-            gd.sk_bucket_pass(None, None, got_off, world, summed, mine, k, threshold, max(n_occ_mine, 1), reads.status,
-                              l2_bits=l2_bits, sources=sources,
-                              out=(_RawBuffer(root + 64, dev), _RawBuffer(root + 64 + 8 * rows, dev), rows))
-        # every rank's results have landed (all-reduce = barrier), then rank 0 reads the total and tells the others
-        total.zero_()
+            try:
+                gd.sk_bucket_pass(None, None, got_off, world, summed, mine, k, threshold, max(n_occ_mine, 1),
+                                  reads.status, l2_bits=l2_bits, sources=sources,
+                                  out=(_RawBuffer(root + 64, dev), _RawBuffer(root + 64 + 8 * rows, dev), rows))
+            except Exception as exc:        # noqa: BLE001 -- raised on every rank below, nobody waits in a collective
+                error = exc
+        # every rank's results have landed (all-reduce = barrier; it also carries "some rank failed"), then rank 0
+        # reads the total and tells the others
+        total.fill_(0 if error is None else 1)
         dist.all_reduce(total)
+        if error is not None:
+            raise error
+        if int(total.item()):
+            raise RuntimeError("sharded build: the bucket pass failed on another rank (see its traceback)")
         if rank == 0:
             gn.check(L.ga_copy_bytes(gn.ptr(total), C.c_void_p(root), 8, gd._stream()))
         dist.broadcast(total, 0)
@@ -557,21 +566,25 @@ def _sharded_step_buckets(reads, k, threshold, to_host, gn, gd, feed=None):
         for wk in works:
             wk.wait()                  # orders the current stream after the transfer; the host does not block
         gd._mark("multi: exchange %d" % h)
-        if not mine:
-            continue
-        # 3. one segment per source rank: positions from the per-source record counts
-        per_source = got_hist.view(world, mine)
-        seg_offsets = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
-        seg_offsets[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
-        seg_offsets += torch.tensor(starts, dtype=torch.int64, device=dev).view(world, 1)
-        summed = per_source.sum(dim=0).contiguous()
-        n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
-        solid_keys, n_solid, edge_stamp = gd.sk_bucket_pass(
-            got_bases, got_meta, seg_offsets.contiguous(), world, summed, mine, k, threshold,
-            max(n_occ_mine, 1), reads.status)
-        # the pass reuses its output workspace: keep this phase's (small) result
-        key_parts.append(solid_keys[:n_solid].clone())
-        stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4).clone())
+        error = None
+        try:
+            if mine:
+                # 3. one segment per source rank: positions from the per-source record counts
+                per_source = got_hist.view(world, mine)
+                seg_offsets = torch.zeros((world, mine + 1), dtype=torch.int64, device=dev)
+                seg_offsets[:, 1:] = torch.cumsum(per_source >> 32, dim=1)
+                seg_offsets += torch.tensor(starts, dtype=torch.int64, device=dev).view(world, 1)
+                summed = per_source.sum(dim=0).contiguous()
+                n_occ_mine = int((summed & 0xFFFFFFFF).sum().item())
+                solid_keys, n_solid, edge_stamp = gd.sk_bucket_pass(
+                    got_bases, got_meta, seg_offsets.contiguous(), world, summed, mine, k, threshold,
+                    max(n_occ_mine, 1), reads.status)
+                # the pass reuses its output workspace: keep this phase's (small) result
+                key_parts.append(solid_keys[:n_solid].clone())
+                stamp_parts.append(edge_stamp[:4 * n_solid].view(-1, 4).clone())
+        except Exception as exc:            # noqa: BLE001 -- reported on every rank before the next collective
+            error = exc
+        raise_together(error)
     del received
     if key_parts:
         solid_keys, edge_stamp = torch.cat(key_parts), torch.cat(stamp_parts)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Turn the ncu outputs of scripts/gpu_prof_final.sh (launch list CSV + `--page raw --csv` of the full capture)
+"""Turn the ncu outputs of scripts/gpu_r2_evidence.sh (launch list CSV + `--page raw --csv` of the full capture)
 into the markdown summary kept under profiles/.  Usage:
-    python scripts/summarize_ncu.py gpurun_out/launches_c4.csv gpurun_out/prof_sk_raw.csv > profiles/r01/ncu_summary_v3.md
+    python scripts/summarize_ncu.py gpurun_out/launches_c4.csv gpurun_out/prof_sk_raw.csv > profiles/r02/ncu_summary_final.md
 """
 import csv
 import re
