@@ -211,3 +211,42 @@ def test_peer_exchange_entries_reject_bad_arguments():
     assert b"sources" in L.ga_last_error()
     assert L.ga_sk_count_build_spill_from(None, ptr, 4, ptr, 1, 31, 3, 4096, ptr, 1, ptr, ptr, 16, ptr, ptr, 2,
                                           None) == gn.GA_ERR_BAD_ARG
+
+
+def test_output_writers_keep_the_reference_format(tmp_path, monkeypatch, capsys):
+    """IOHandler.write_FASTQ / write_stdout (assemble.py:74-99 of the reference): file name, line layout, no trailing
+    newline in the file, two blanks after the colon on stdout, exclusive creation.  Where the unmodified reference is at
+    hand (oracle/_ref, this container) its own writer must produce the same bytes."""
+    import importlib.util
+    import time
+    import assemble
+    monkeypatch.chdir(tmp_path)
+    contigs, constants, start = ["ACGTACGT", "TTGA"], (28, 3, 2), 1_700_000_000.0
+    assemble.IOHandler.write_FASTQ(contigs, constants, start)
+    stamp = time.strftime("%b_%d_%H:%M:%S_%Y", time.localtime(start))
+    path = tmp_path / "output" / ("%s_k28_f3_e2.FASTQ" % stamp)
+    text = path.read_text()
+    lines = text.split("\n")
+    assert lines[0] == ">Time started: " + time.strftime("%c", time.localtime(start))
+    assert lines[1:6] == [">Number of contigs: 2", ">CONTIG1", "ACGTACGT", ">CONTIG2", "TTGA"]
+    assert lines[6].startswith(">Time finished: ") and len(lines) == 7 and not text.endswith("\n")
+    with pytest.raises(FileExistsError):                       # mode 'x', as upstream
+        assemble.IOHandler.write_FASTQ(contigs, constants, start)
+    assemble.IOHandler.write_stdout(contigs, constants, start)
+    out = capsys.readouterr().out.split("\n")
+    assert out[0] == ">Time started:  " + time.strftime("%c", time.localtime(start))
+    assert out[1:6] == [">Number of contigs:  2", ">CONTIG1", "ACGTACGT", ">CONTIG2", "TTGA"] and out[7] == ""
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "assemble.py")
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("reference_assemble", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        monkeypatch.syspath_prepend(os.path.dirname(ref_path))
+        spec.loader.exec_module(ref)
+        other = tmp_path / "ref"
+        other.mkdir()
+        monkeypatch.chdir(other)
+        ref.IOHandler.write_FASTQ(contigs, constants, start)
+        theirs = (other / "output" / path.name).read_text().split("\n")
+        assert theirs[:6] == lines[:6] and theirs[6].startswith(">Time finished: ") and len(theirs) == 7
+        ref.IOHandler.write_stdout(contigs, constants, start)
+        assert capsys.readouterr().out.split("\n")[:6] == out[:6]
