@@ -72,3 +72,54 @@ def test_raw_reads_sequence_surface():
     assert [r for r in reads] == [("AAAA", "CCCC"), ("GG", "TT"), ("A", "C")]
     with pytest.raises(IndexError):
         reads[3]
+
+
+THREADED = [c for c in CASES if "\r" not in c] + [
+    "7\nACGT\nGG\n\nTTTTTTTT\nA\nCC\nGGG\nextra\nlines\n",
+    "5\nAC|GT|3\nAAAA|CCCC|3\nG|T|3\nGGGG|TTTT|3\nA|C|41\nXX|YY|9\n",
+    "9\nACGT\nGG\n",                                # more reads announced than lines present
+    "1\n" + "ACGT" * 300 + "\n",
+]
+
+
+@pytest.mark.parametrize("threads", [2, 3, 8])
+@pytest.mark.parametrize("text", THREADED)
+def test_parallel_parse_equals_serial_parse(text, threads, monkeypatch):
+    """ga_parse_reads cuts big inputs into one byte range per thread; forced here on small inputs (one-byte grain):
+    same reads, kind, distance and base count as the serial scan and as the text parser."""
+    monkeypatch.setenv("GA_PARSE_THREADS", "1")
+    serial = ga_ingest.parse(text.encode("ascii"))
+    monkeypatch.setenv("GA_PARSE_THREADS", str(threads))
+    monkeypatch.setenv("GA_PARSE_GRAIN", "1")
+    got = ga_ingest.parse(text.encode("ascii"))
+    want = _text_path(text)
+    for reads, paired, distance, bases in (serial, got):
+        assert (list(reads), paired, distance, bases) == (list(want[0]), want[1], want[2], want[3])
+
+
+@pytest.mark.parametrize("text", ["2\nACGT|TT|1\nGGCA\n", "2\nAC|GT|1|9\nAA|CC|1\n", "3\nAC|GT|1\nAA|CC|1\n",
+                                  "2\nAA|CC|1\nAC|GT|x\n"])
+def test_parallel_parse_rejects_what_the_serial_parse_rejects(text, monkeypatch):
+    monkeypatch.setenv("GA_PARSE_THREADS", "4")
+    monkeypatch.setenv("GA_PARSE_GRAIN", "1")
+    with pytest.raises(ValueError):
+        _text_path(text)
+    with pytest.raises(ValueError):
+        ga_ingest.parse(text.encode("ascii"))
+
+
+def test_parallel_parse_large_input(monkeypatch):
+    """A few MB through the default thread count: equal to the serial scan byte for byte."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    n = 40000
+    lens = rng.integers(0, 180, n)
+    body = b"".join(bytes(rng.integers(65, 91, int(m), dtype=np.uint8)) + b"\n" for m in lens)
+    text = (b"%d\n" % n) + body
+    monkeypatch.setenv("GA_PARSE_THREADS", "1")
+    a = ga_ingest.parse(text)
+    monkeypatch.setenv("GA_PARSE_THREADS", "6")
+    monkeypatch.setenv("GA_PARSE_GRAIN", "65536")
+    b = ga_ingest.parse(text)
+    assert a[1:] == b[1:] and np.array_equal(a[0].lens, b[0].lens) and np.array_equal(a[0].symbols, b[0].symbols)
+    assert a[0].lens.tolist() == lens.tolist()
