@@ -121,6 +121,7 @@ SIGNATURES = {
     "ga_traverse_contigs": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32,
                                    C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _vp]),
     "ga_free_host": (None, [_vp]),
+    "ga_traverse_last_route": (_i32, []),
 }
 
 _lib = None

@@ -431,6 +431,10 @@ int ga_traverse_contigs(const int32_t* rowptr, const int32_t* col, const int32_t
                         int64_t num_edges_attr, int paired, uint8_t** text_out,
                         uint64_t** offsets_out, uint64_t* n_contigs, int32_t* left_out);
 void ga_free_host(void* p);
+/* Which routine answered this thread's last ga_traverse_contigs call: 1 = chains walked piecewise on
+ * several host threads (graphs from 65536 nodes on whose edges all go in the reference's first sweep),
+ * 0 = the serial edge-by-edge sweep.  Same output either way.  GA_TRAVERSE_THREADS=0 forces the serial one. */
+int ga_traverse_last_route(void);
 
 #ifdef __cplusplus
 }

@@ -82,26 +82,61 @@ def test_read_input_rules():
     assert (args.kmer_length, args.filter_threshold, args.stdout, args.paired) == (28, 3, True, True)
 
 
-def _traverse(graph):
+def _traverse_arrays(rowptr, col, indeg, br, last, num_edges, paired, mode=None):
+    """ga_traverse_contigs on host arrays -> (contigs, left).  mode: None = the library's own choice,
+    "serial" = the edge-by-edge sweep, "parallel" = the piecewise routine forced (it may still decline
+    and hand over to the serial one -- the result must be the same either way)."""
     lib = _lib()
-    n = len(graph.keys)
-    rowptr = np.zeros(n + 1, dtype=np.int32)
-    rowptr[1:] = np.cumsum([len(s) for s in graph.succ])
-    col = np.array([j for s in graph.succ for j in s] or [0], dtype=np.int32)
-    indeg = np.array(graph.indeg or [0], dtype=np.int32)
-    br = np.array(graph.branching or [0], dtype=np.uint8)
-    last = np.array([ord(graph.last_char(i)) for i in range(n)] or [0], dtype=np.uint8)
-    text, offs, cnt = C.c_void_p(), C.c_void_p(), C.c_uint64()
-    left = np.zeros(max(n, 1), dtype=np.int32)
-    rc = lib.ga_traverse_contigs(rowptr.ctypes.data, col.ctypes.data, indeg.ctypes.data, br.ctypes.data,
-                                 last.ctypes.data, n, graph.num_edges, int(graph.paired), C.byref(text),
-                                 C.byref(offs), C.byref(cnt), left.ctypes.data)
-    assert rc == 0
+    n = len(rowptr) - 1
+    env = {"serial": {"GA_TRAVERSE_THREADS": "0"},
+           "parallel": {"GA_TRAVERSE_THREADS": "3", "GA_TRAVERSE_MIN_NODES": "0"}}.get(mode, {})
+    saved = {key: os.environ.get(key) for key in ("GA_TRAVERSE_THREADS", "GA_TRAVERSE_MIN_NODES")}
+    for key in saved:
+        os.environ.pop(key, None)
+    os.environ.update(env)
+    try:
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        col = np.ascontiguousarray(col if len(col) else [0], dtype=np.int32)
+        indeg = np.ascontiguousarray(indeg if len(indeg) else [0], dtype=np.int32)
+        br = np.ascontiguousarray(br if len(br) else [0], dtype=np.uint8)
+        last = np.ascontiguousarray(last if len(last) else [0], dtype=np.uint8)
+        text, offs, cnt = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        left = np.full(max(n, 1), -7, dtype=np.int32)
+        rc = lib.ga_traverse_contigs(rowptr.ctypes.data, col.ctypes.data, indeg.ctypes.data, br.ctypes.data,
+                                     last.ctypes.data, n, int(num_edges), int(paired), C.byref(text),
+                                     C.byref(offs), C.byref(cnt), left.ctypes.data)
+        assert rc == 0
+        route = lib.ga_traverse_last_route()
+    finally:
+        for key, value in saved.items():
+            os.environ.pop(key, None)
+            if value is not None:
+                os.environ[key] = value
     off = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_uint64)), shape=(cnt.value + 1,)).copy()
     raw = C.string_at(text, int(off[-1]))
     lib.ga_free_host(text)
     lib.ga_free_host(offs)
-    return [raw[int(off[i]):int(off[i + 1])].decode("latin-1") for i in range(cnt.value)]
+    _traverse_arrays.route = route
+    return [raw[int(off[i]):int(off[i + 1])].decode("latin-1") for i in range(cnt.value)], left[:n]
+
+
+def _graph_arrays(graph):
+    n = len(graph.keys)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum([len(s) for s in graph.succ])
+    col = np.array([j for s in graph.succ for j in s], dtype=np.int32)
+    last = np.array([ord(graph.last_char(i)) for i in range(n)], dtype=np.uint8)
+    return rowptr, col, np.array(graph.indeg, dtype=np.int32), np.array(graph.branching, dtype=np.uint8), last
+
+
+def _traverse(graph):
+    """Contigs of an oracle-built graph through ga_traverse_contigs: the serial sweep and the forced
+    piecewise routine must agree on the contigs and on what is left of every node."""
+    arrays = _graph_arrays(graph)
+    serial, left_s = _traverse_arrays(*arrays, graph.num_edges, graph.paired, "serial")
+    forced, left_p = _traverse_arrays(*arrays, graph.num_edges, graph.paired, "parallel")
+    assert forced == serial and np.array_equal(left_s, left_p)
+    return serial
 
 
 def test_host_traversal_matches_oracle():
@@ -114,6 +149,84 @@ def test_host_traversal_matches_oracle():
         _, _, graph = po.assemble(reads_for(gold["recipe"]), gold["k"], gold["F"], gold["recipe"]["paired"])
         got = _traverse(graph)
         assert po.contig_digest(got) == gold["contig_digest"], name
+
+
+def _chain_graph(rng, n, n_branch, cycles=0):
+    """A random graph of the shape the traversal sees: `n_branch` branching nodes joined by chains of
+    1-in-1-out nodes (ids shuffled), plus `cycles` rings without any branching node."""
+    ids = rng.permutation(n).tolist()
+    hubs = [ids.pop() for _ in range(n_branch)]
+    rings = []
+    for _ in range(cycles):
+        size = int(rng.integers(1, 40))
+        rings.append([ids.pop() for _ in range(size)])
+    succ = [[] for _ in range(n)]
+    while ids:
+        length = min(len(ids), int(rng.integers(0, 3000)))
+        chain = [ids.pop() for _ in range(length)]
+        src = hubs[int(rng.integers(len(hubs)))]
+        path = [src] + chain
+        if rng.random() < 0.8:
+            path.append(hubs[int(rng.integers(len(hubs)))])      # else: dead end
+        for a, b in zip(path, path[1:]):
+            succ[a].append(b)
+    for ring in rings:
+        for a, b in zip(ring, ring[1:] + ring[:1]):
+            succ[a].append(b)
+    indeg = np.zeros(n, dtype=np.int32)
+    for s in succ:
+        for j in s:
+            indeg[j] += 1
+    br = np.array([len(succ[i]) > 1 or indeg[i] > 1 for i in range(n)], dtype=np.uint8)
+    rowptr = np.zeros(n + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum([len(s) for s in succ])
+    col = np.array([j for s in succ for j in s], dtype=np.int32)
+    last = rng.integers(65, 91, n).astype(np.uint8)
+    return rowptr, col, indeg, br, last
+
+
+def test_piecewise_traversal_equals_the_serial_sweep():
+    """Long chains cut at splitter nodes, walked piece by piece on several threads and stitched
+    (csrc/ga_traverse.cu) give the serial sweep's contigs; shapes the piecewise routine does not
+    take -- rings without a branching node, an edge counter that disagrees with the CSR, in-degree
+    bookkeeping that hides a second way into a chain -- fall back to the serial sweep."""
+    rng = np.random.default_rng(11)
+    for n, hubs, cycles, paired in ((60000, 40, 0, False), (60000, 40, 0, True), (30000, 3, 0, False),
+                                    (20000, 25, 3, False), (20000, 25, 3, True), (5000, 1, 0, False)):
+        arrays = _chain_graph(rng, n, hubs, cycles)
+        m = int(arrays[0][-1])
+        serial, left_s = _traverse_arrays(*arrays, m, paired, "serial")
+        forced, left_p = _traverse_arrays(*arrays, m, paired, "parallel")
+        assert _traverse_arrays.route == (1 if cycles == 0 else 0)      # taken, not declined (rings: declined)
+        auto, left_a = _traverse_arrays(*arrays, m, paired)
+        assert forced == serial and auto == serial, (n, hubs, cycles, paired)
+        assert np.array_equal(left_s, left_p) and np.array_equal(left_s, left_a)
+        if cycles == 0:
+            assert sum(map(len, serial)) == m and not left_s.any()
+        # the reference's own edge counter may differ from the CSR (paired corner cases): early exit
+        for attr in (m - 5, m + 5, 3):
+            a, la = _traverse_arrays(*arrays, attr, paired, "serial")
+            b, lb = _traverse_arrays(*arrays, attr, paired, "parallel")
+            assert a == b and np.array_equal(la, lb)
+    # bookkeeping that hides a second entry into a chain: node x has in-degree 2 but says 1
+    rowptr, col, indeg, br, last = _chain_graph(rng, 4000, 6)
+    chain_nodes = [i for i in range(4000) if not br[i] and rowptr[i + 1] - rowptr[i] == 1 and indeg[i] == 1]
+    a, b = chain_nodes[10], chain_nodes[500]
+    col = col.copy()
+    col[rowptr[a]] = b                      # a now also leads to b; b keeps "in-degree 1, not branching"
+    m = int(rowptr[-1])
+    for paired in (False, True):
+        s, ls = _traverse_arrays(rowptr, col, indeg, br, last, m, paired, "serial")
+        p, lp = _traverse_arrays(rowptr, col, indeg, br, last, m, paired, "parallel")
+        assert s == p and np.array_equal(ls, lp) and _traverse_arrays.route == 0
+    # a "not branching" node with two edges
+    rowptr, col, indeg, br, last = _chain_graph(rng, 3000, 5)
+    hub = int(np.flatnonzero(br)[0])
+    br = br.copy()
+    br[hub] = 0
+    s, ls = _traverse_arrays(rowptr, col, indeg, br, last, int(rowptr[-1]), False, "serial")
+    p, lp = _traverse_arrays(rowptr, col, indeg, br, last, int(rowptr[-1]), False, "parallel")
+    assert s == p and np.array_equal(ls, lp)
 
 
 def test_prime_tables_and_hash_helper():
