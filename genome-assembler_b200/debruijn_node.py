@@ -10,8 +10,7 @@ import sys
 
 
 class Node:
-    __slots__ = ("data", "edges", "was_branching", "num_edges_in", "total_mem")
-
+    # plain instances (no __slots__): object.__sizeof__ enters the reference's -m totals (debruijn_node.py:35-53)
     def __init__(self, data):
         self.data = data
         self.edges = {}
@@ -60,8 +59,6 @@ class Node:
 
 
 class PairedNode(Node):
-    __slots__ = ("paired_data",)
-
     def __init__(self, data, paired_data):
         self.paired_data = paired_data
         super().__init__(data)

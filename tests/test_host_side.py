@@ -363,3 +363,35 @@ def test_output_writers_keep_the_reference_format(tmp_path, monkeypatch, capsys)
         assert theirs[:6] == lines[:6] and theirs[6].startswith(">Time finished: ") and len(theirs) == 7
         ref.IOHandler.write_stdout(contigs, constants, start)
         assert capsys.readouterr().out.split("\n")[:6] == out[:6]
+
+
+def test_node_records_weigh_what_the_reference_says():
+    """The -m report sums sys.getsizeof over the Node objects (debruijn_node.py:35-53 of the reference, incl. the
+    cached second answer that is one int larger than the first).  Where the unmodified reference is at hand
+    (oracle/_ref, this container) its classes must report the same numbers in the same interpreter."""
+    import importlib.util
+    import sys
+    import debruijn_node as ours
+    node = ours.Node("ACGT")
+    node.append_edge("CGTA")
+    node.append_edge("CGTC")
+    first = sys.getsizeof(node)
+    assert sys.getsizeof(node) == first + sys.getsizeof(first)       # the cached answer: one int more
+    assert node.pop_edge() == ("CGTC", True) and node.outdegree == 1 and node.indegree == 0
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "debruijn_node.py")
+    if not os.path.exists(ref_path):
+        return
+    spec = importlib.util.spec_from_file_location("reference_debruijn_node", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    def weigh(mod, paired, edges):
+        n = mod.PairedNode("ACGT", "TTGA") if paired else mod.Node("ACGT")
+        for e in edges:
+            n.append_edge(e)
+        n.num_edges_in = 2
+        return sys.getsizeof(n), sys.getsizeof(n)
+
+    for paired in (False, True):
+        for edges in ([], ["CGTA"], ["CGTA", "CGTC", "CGTG"], [("CGTA", "TGAC")], [("CGTA", "TGAC"), ("CGTT", "TGAA")]):
+            assert weigh(ours, paired, edges) == weigh(ref, paired, edges), (paired, edges)
