@@ -64,6 +64,14 @@ def make_reads(recipe):
     if recipe["kind"] == "explicit":
         reads = recipe["reads"]
         return [tuple(r) for r in reads] if recipe["paired"] else list(reads)
+    if recipe["kind"] == "splitmix":
+        # the bench's input class (150-bp reads, per-base substitutions): made by the oracle-side numpy model of the
+        # device generator -- the reference only ever sees the resulting strings
+        for extra in (os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)):    # repo root (oracle/), tests/
+            if extra not in sys.path:
+                sys.path.append(extra)
+        from helpers import splitmix_reads
+        return splitmix_reads(recipe)
     genome = genome_text(recipe["genome"])
     ref_gen.seed = lambda *a: random.seed(recipe["seed"])
     lines = ref_gen.generate_reads(genome, read_len=recipe["L"], num_reads=recipe["N"],
@@ -199,6 +207,19 @@ def main():
         ("nd-unpaired-k32", refgen("n_delto", 100, 20000, False, 5), 32, 2, "DeBruijnGraph"),
         ("nd-paired-k64", refgen("n_delto", 100, 12000, True, 6, 1), 64, 1, "PairedDeBruijnGraph"),
         ("nd-paired-k35", refgen("n_delto", 100, 12000, True, 6, 1), 35, 2, "PairedDeBruijnGraph"),
+    ]
+    def splitmix(G, N, L, paired, seed, dist=0):
+        return {"kind": "splitmix", "G": G, "N": N, "L": L, "paired": paired, "seed": seed, "sub_per_10k": 100,
+                "dist": dist}
+
+    # BASELINE config C4's input class at 300x coverage (and C3 / C5's as bench.py generates them): reads only the
+    # device generator and its numpy model can make (generate_reads.py:54 refuses L > 100)
+    medium += [
+        ("mix-c4-sample", splitmix(10000, 20000, 150, False, 4), 31, 3, "DeBruijnGraph"),
+        ("mix-c4-sample-cms", splitmix(10000, 20000, 150, False, 4), 31, 3, "CMSDeBruijnGraph"),
+        ("mix-c4-sample-k32", splitmix(8000, 12000, 150, False, 5), 32, 3, "DeBruijnGraph"),
+        ("mix-c3-pairs", splitmix(40000, 12000, 100, True, 6, 125), 29, 3, "PairedDeBruijnGraph"),
+        ("mix-c5-pairs-k41", splitmix(40000, 12000, 100, True, 6, 125), 41, 3, "PairedDeBruijnGraph"),
     ]
     big = [
         ("c2-s-aureus", refgen("s_aureus", 100, 861831, False, 1234), 31, 3, "DeBruijnGraph"),

@@ -7,7 +7,10 @@ from oracle import py_oracle as po
 import recipes
 
 SMALL = [n for n, c in GOLDEN["cases"].items() if c.get("ref_seconds", 0) < 3 and "cms" not in n]
-MEDIUM = ["nd-unpaired", "nd-paired-jitter2", "nd-unpaired-k65"]
+MEDIUM = ["nd-unpaired", "nd-paired-jitter2", "nd-unpaired-k65",
+          # the bench's input class (150-bp reads, 1 % per-base substitutions; pairs as bench.py makes them), digests
+          # from the unmodified reference run on these very reads
+          "mix-c4-sample", "mix-c3-pairs", "mix-c5-pairs-k41"]
 
 
 def test_murmur_known_answers():
