@@ -214,7 +214,7 @@ class DeviceReads:
         if type(reads).__name__ == "RawReads" and reads.paired == self.paired:
             # raw ingest (ga_ingest.parse): the symbols already sit in one (pinned) buffer, lengths in an array
             n = int(reads.lens.size)
-            lens = reads.lens.astype(np.int64)
+            lens = reads.lens                  # int32, as parsed: no copy, no widening pass over a million entries
             buf = reads.symbols
             pinned = reads._keep
         else:
@@ -236,17 +236,18 @@ class DeviceReads:
         guess_dna = pinned is not None
         self.alphabet = Alphabet(np.zeros(0) if guess_dna or not buf.size else
                                  np.flatnonzero(np.bincount(buf, minlength=256)))
-        if self.paired and n and np.any(lens[1::2] < lens[0::2]):
+        self.max_len = int(lens.max()) if n else 0
+        uniform = n > 0 and int(lens.min()) == self.max_len
+        if self.paired and n and not uniform and np.any(lens[1::2] < lens[0::2]):
             raise ValueError("paired reads: mate 2 shorter than mate 1 is not supported "
                              "(the reference would slice truncated k-mers)")
         self.lens = lens
-        self.max_len = int(lens.max()) if n else 0
+        self._windows = {}
         self.estride = int(estride) if estride is not None else max(self.max_len, 1)
         self.first_read = int(first_read)
         spw = 64 // self.alphabet.storage_bits
         dev = _dev()
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        uniform = n > 0 and int(lens.min()) == self.max_len
         self.uniform = uniform
         if pinned is not None and buf.size:
             ascii_dev = pinned[:buf.size].to(dev, non_blocking=True)
@@ -296,6 +297,7 @@ class DeviceReads:
         self.n_reads = int(n_reads)
         self.alphabet = alphabet if alphabet is not None else Alphabet(np.zeros(0))
         self.lens = None
+        self._windows = {}
         self.max_len = int(read_len)
         self.uniform = True
         self.estride = int(estride) if estride is not None else max(self.max_len, 1)
@@ -332,10 +334,12 @@ class DeviceReads:
         w = k - 1
         if self.n_reads == 0:
             return 0
-        if self.lens is None:
+        if self.lens is None or self.uniform:
             return self.n_reads * max(self.max_len - w + 1, 0)
-        eff = np.repeat(self.lens[0::2], 2) if self.paired else self.lens
-        return int(np.maximum(eff - w + 1, 0).sum())
+        if k not in self._windows:             # ragged reads: one pass over the lengths per k, not per caller
+            eff = np.repeat(self.lens[0::2], 2) if self.paired else self.lens
+            self._windows[k] = int(np.maximum(eff.astype(np.int64) - w + 1, 0).sum())
+        return self._windows[k]
 
     def struct(self) -> gn.GaReads:
         if self._struct is None:
@@ -586,9 +590,9 @@ def superkmer_supported(reads: "DeviceReads", k: int, threshold: int, counting_o
 
 def _record_groups(reads: "DeviceReads", w: int) -> int:
     """Upper bound on the extra records caused by cutting runs at 32-window groups."""
-    if reads.lens is None:
+    if reads.lens is None or reads.uniform:
         return reads.n_reads * max(-(-max(reads.max_len - w + 1, 0) // 32), 0)
-    win = np.maximum(reads.lens - w + 1, 0)
+    win = np.maximum(reads.lens.astype(np.int64) - w + 1, 0)
     return int((-(-win // 32)).sum())
 
 
@@ -706,8 +710,11 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     if l1_capacity >= (1 << 25):
         raise gn.GaError("bucketed count: level-1 buckets of 2^25 slots or more")
     _mark("sk bucket: checks")
-    # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand
-    out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), n_occ // 48) + 1024)
+    # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand (a second run of the
+    # kernel).  Big inputs: one solid window per 48 occurrences (sequencing depth >= 60x; C4: one per 212).  Inputs
+    # whose whole bound is small get room for one per 8 occurrences, so that a 30x read set such as C2 (one solid
+    # window per 21 occurrences) is not counted twice.
+    out_cap = max(1 << 20, min(n_occ // (int(threshold) + 1), max(n_occ // 48, min(n_occ // 8, 16 << 20))) + 1024)
     spill_cap = 1 << 16 if out is None else max(1 << 16, 2 * n_buckets)   # shared output: the pass cannot be repeated
     while True:
         counters = torch.zeros(16, dtype=torch.int64, device=dev)      # [8..14]: phase cycles of a GA_SB_PROFILE build
@@ -1071,7 +1078,7 @@ def build_dna4(reads, k, solid, solid_cap, solid_keys, n_solid, kw, node_stamp, 
     L = gn.lib()
     dev = node_stamp.device
     n = reads.n_reads
-    per_read = max(reads.max_len - (k - 1) + 1, 0) if reads.lens is None else 0
+    per_read = max(reads.max_len - (k - 1) + 1, 0) if reads.lens is None or reads.uniform else 0
 
     def run(r0, r1):
         with _timed("build", (r1 - r0) * per_read):
