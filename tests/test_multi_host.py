@@ -80,6 +80,22 @@ def _worker(rank, world, port, results):
         dist.all_to_all_single(told, torch.tensor(dst_start, dtype=torch.int64))
         assert told.tolist() == seg_start
         assert seg_start[0] == 0 and seg_start[1] == matrix[0][rank]
+        # a failure on one rank between two collectives is raised on every rank (nobody is left waiting in the next
+        # collective): the failing rank raises its own exception, the others name it
+        ga_multi.raise_together(None)                              # nobody failed: returns
+        try:
+            ga_multi.raise_together(MemoryError("bucket pass failed") if rank == 1 else None)
+            raised = None
+        except MemoryError as exc:
+            raised = "own:" + str(exc)
+        except RuntimeError as exc:
+            raised = "other:" + str(exc)
+        assert raised == ("own:bucket pass failed" if rank == 1 else
+                          "other:sharded build: rank 1 failed (see its own traceback)"), raised
+        # both ranks are still in step afterwards
+        probe = torch.tensor([rank + 1], dtype=torch.int64)
+        dist.all_reduce(probe)
+        assert int(probe) == 3
         results[rank] = "ok"
     except Exception as exc:      # noqa: BLE001
         results[rank] = repr(exc)
