@@ -295,16 +295,19 @@ bool traverse_parallel(const CsrView& g, unsigned threads, uint8_t** text_out, s
                 // a few steps per visit: consecutive nodes of a chain often share a cache line
                 for (int step = 0; step < GA_TRV_STEPS; ++step) {
                     const int32_t j = ln.at;
-                    const Rec r = rec[j];
-                    ln.text.push_back(r.last);
-                    if ((r.flags & R_BRANCH) || !(r.flags & R_OUT)) {
+                    // field by field: `marked` of this record may be written by another thread right now (a piece
+                    // that starts at this splitter), the other fields do not change during the walk
+                    const int32_t next = rec[j].next;
+                    const uint8_t flags = rec[j].flags;
+                    ln.text.push_back(rec[j].last);
+                    if ((flags & R_BRANCH) || !(flags & R_OUT)) {
                         finish(ln, -1);
-                    } else if (r.flags & R_SPLIT) {
+                    } else if (flags & R_SPLIT) {
                         finish(ln, j);
                     } else {
                         mark(j);
-                        ln.at = r.next;
-                        __builtin_prefetch(&rec[r.next]);
+                        ln.at = next;
+                        __builtin_prefetch(&rec[next]);
                         if ((int64_t)ln.text.size() > n) decline.store(1, std::memory_order_relaxed);   // going round in circles
                         continue;
                     }
