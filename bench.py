@@ -364,6 +364,14 @@ def run_gpu_arm(args):
                        "device_free": round(torch.cuda.mem_get_info()[0] / 1e9, 1),
                        "alloc_retries": torch.cuda.memory_stats().get("num_alloc_retries", 0)}
     clocks = sampler.stop() if sampler else None
+    # fingerprint of the last step's CSR (outside the timed region): lines at different N, or of different exchange
+    # routes, must agree -- the driver's own scaling runs then show bit-identity across 1/2/4/8 GPUs
+    graph_sum = None
+    if result is not None:
+        try:
+            graph_sum = result.checksum()
+        except Exception as exc:      # noqa: BLE001  (never lose the bench line to the fingerprint)
+            graph_sum = "unavailable: %r" % (exc,)
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -550,7 +558,8 @@ def run_gpu_arm(args):
                               "device_free": round(torch.cuda.mem_get_info()[0] / 1e9, 1),
                               "after_timed_steps": mem_after_steps},
                 "clocks": clocks,
-                "graph": {"nodes": result.n_nodes, "edges": result.n_edges} if result is not None else None}
+                "graph": {"nodes": result.n_nodes, "edges": result.n_edges, "checksum": graph_sum}
+                if result is not None else None}
         print(json.dumps(line))
     if world > 1:
         import ga_multi

@@ -867,6 +867,31 @@ class BuiltGraph:
             return a
         return list(zip(a, self.alphabet.decode_strings(self.keys_b, self.w)))
 
+    def checksum(self) -> str:
+        """64-bit fingerprint of the graph (row pointers, columns, in-degrees, was_branching, node keys in node
+        order; the last symbol is part of the key): position-weighted wrap-around sums, computed where the arrays are
+        (device tensors of a `to_host=False` build, or the host arrays).  Two builds of the same reads -- one GPU or
+        eight, any exchange route -- must print the same value; bench.py reports it next to the node / edge counts."""
+        nn, ne = self.n_nodes, self.n_edges
+        dev = getattr(self, "device", None)
+        if dev is not None:
+            arrs = [dev["rowptr"][:nn + 1], dev["col"][:ne], dev["indeg"][:nn], dev["branching"][:nn], dev["keys_a"][:nn]]
+            if dev.get("keys_b") is not None:
+                arrs.append(dev["keys_b"][:nn])
+        else:
+            host = [self.rowptr[:nn + 1], self.col[:ne], self.indeg[:nn], self.branching[:nn], self.keys_a[:nn]]
+            if self.keys_b is not None:
+                host.append(self.keys_b[:nn])
+            arrs = [torch.from_numpy(np.ascontiguousarray(a).view(np.int64) if a.dtype == np.uint64
+                                     else np.ascontiguousarray(a)) for a in host]
+        acc, m64 = 0, (1 << 64) - 1
+        for x in arrs:
+            x = x.reshape(-1).to(torch.int64)
+            weight = torch.arange(1, x.numel() + 1, dtype=torch.int64, device=x.device) * -0x61C8864680B583EB | 1
+            part = int((x * weight).sum().item()) if x.numel() else 0          # int64 arithmetic wraps: sums mod 2^64
+            acc = (acc * 0x100000001B3 + (part & m64) + x.numel()) & m64
+        return "%016x" % acc
+
     def contigs(self):
         """Host traversal (libga_b200's ga_traverse_contigs) -> (contigs, edges left, left per node)."""
         L = gn.lib()

@@ -395,3 +395,31 @@ def test_node_records_weigh_what_the_reference_says():
     for paired in (False, True):
         for edges in ([], ["CGTA"], ["CGTA", "CGTC", "CGTG"], [("CGTA", "TGAC")], [("CGTA", "TGAC"), ("CGTT", "TGAA")]):
             assert weigh(ours, paired, edges) == weigh(ref, paired, edges), (paired, edges)
+
+
+def test_graph_checksum_host_and_tensor_paths_agree():
+    """BuiltGraph.checksum(): the same value from the host arrays and from tensors holding the same numbers (the
+    form a `to_host=False` build keeps on the device), keys with the top bit set included; sensitive to order."""
+    import torch
+    import ga_device as gd
+    rng = np.random.default_rng(0)
+    n = 1000
+    rowptr = np.zeros(n + 1, np.int32)
+    rowptr[1:] = np.cumsum(rng.integers(0, 3, n))
+    m = int(rowptr[-1])
+    g = gd.BuiltGraph(False, 30, None, 1)
+    g.n_nodes, g.n_edges = n, m
+    g.rowptr, g.col, g.indeg = rowptr, rng.integers(0, n, m).astype(np.int32), rng.integers(0, 3, n).astype(np.int32)
+    g.branching = rng.integers(0, 2, n).astype(np.uint8)
+    g.keys_a = rng.integers(0, 2 ** 62, (n, 1)).astype(np.uint64)
+    g.keys_a[3, 0] = 2 ** 64 - 5
+    want = g.checksum()
+    t = gd.BuiltGraph(False, 30, None, 1)
+    t.n_nodes, t.n_edges = n, m
+    t.device = dict(rowptr=torch.from_numpy(rowptr), col=torch.from_numpy(g.col), indeg=torch.from_numpy(g.indeg),
+                    branching=torch.from_numpy(g.branching), keys_a=torch.from_numpy(g.keys_a.view(np.int64)), keys_b=None)
+    assert t.checksum() == want and len(want) == 16
+    i = int(np.flatnonzero(g.col[:-1] != g.col[1:])[0])
+    g.col[[i, i + 1]] = g.col[[i + 1, i]]
+    assert g.checksum() != want
+    assert gd.BuiltGraph(True, 27, None, 1).checksum() == gd.BuiltGraph(True, 27, None, 1).checksum()     # empty graph
