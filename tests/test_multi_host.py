@@ -106,7 +106,7 @@ def _worker(rank, world, port, results):
 def test_multi_rank_helpers_gloo():
     world = 2
     port = 29600 + os.getpid() % 300
-    with mp.Manager() as manager:
+    with mp.get_context("spawn").Manager() as manager:      # not fork: the pytest process has threads by now
         results = manager.dict()
         mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
         assert dict(results) == {0: "ok", 1: "ok"}
