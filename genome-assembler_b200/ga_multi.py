@@ -20,13 +20,17 @@ Unpaired DNA with k <= 32 takes the bucketed route instead (`_sharded_step_bucke
   1. each rank cuts its read shard into super-k-mer records sorted by bucket (the bucket of a window
      depends on its content only, so all its occurrences -- on any rank -- share one bucket id);
   2. hash-partition all-to-all: rank g owns a contiguous range of bucket ids and receives every rank's
-     records of that range.  EXCHANGE = "push" (default): the owners' receive buffers are mapped into every
-     rank over NVLink (CUDA IPC, `PeerBuffers`) and ONE kernel per rank (`ga_sk_push_sorted`,
-     csrc/ga_peer.cu) splits its level-1 buckets into final buckets and stores the records straight into
-     the owners' buffers -- no index, no dense local copy, no NCCL call on the data path (NCCL carries
-     the 8 MB of histograms and the barriers).  PUSH = "gather" keeps the first version (index pass, then
-     `ga_sk_push_records` gathers through the index).  EXCHANGE = "nccl": the round-1 route, a dense local copy + `all_to_all_single` per record
-     array (PHASES = 2 would send a second half while the first is counted -- no gain measured);
+     records of that range.  EXCHANGE = "auto" (default) takes "push" on 2-3 ranks and "peer" from 4 on.
+     "push": the owners' receive buffers are mapped into every rank over NVLink (CUDA IPC, `PeerBuffers`) and
+     ONE kernel per rank (csrc/ga_peer.cu) stores the records straight into the owners' buffers -- no dense
+     local copy, no NCCL call on the data path (NCCL carries the 8 MB of histograms and the barriers).
+     PUSH = "gather" (default): index pass, then `ga_sk_push_records` gathers through the index; PUSH = "sorted":
+     `ga_sk_push_sorted` splits the level-1 buckets and sends in one pass, no index (measured slower).
+     "peer": nothing is copied -- the owner's bucket kernel gathers the records from every rank's own level-1
+     slots over NVLink while it counts (`_count_in_place`, ga_sk_count_build_from).
+     "nccl": the round-1 route, a dense local copy + `all_to_all_single` per record array (PHASES = 2 would
+     send a second half while the first is counted -- no gain measured); also what every rank falls back to
+     when peer memory cannot be mapped (`peers_available`);
   3. the owner counts and stamps each of its buckets in shared memory, reading the bucket as one
      segment per source rank;
   4. solid keys + candidate edge stamps are gathered on rank 0, which resolves them into the CSR.
