@@ -95,8 +95,14 @@ def _free_bytes() -> int:
     dev = torch.cuda.current_device()
     if dev not in _TOTAL_MEM:
         _TOTAL_MEM[dev] = torch.cuda.get_device_properties(dev).total_memory
-    stats_reserved = torch.cuda.memory_reserved(dev)
-    return max(_TOTAL_MEM[dev] - stats_reserved, 0) + (stats_reserved - torch.cuda.memory_allocated(dev))
+    # (total - reserved) + (reserved - allocated) = total - allocated.  The allocator's counters come as a nested
+    # dict straight from C++; torch.cuda.memory_allocated() flattens all of them in Python first (~0.1 ms per call,
+    # twice per graph: 7 % of a C1 step)
+    try:
+        allocated = int(torch.cuda.memory_stats_as_nested_dict(dev)["allocated_bytes"]["all"]["current"])
+    except (KeyError, TypeError):
+        allocated = torch.cuda.memory_allocated(dev)
+    return max(_TOTAL_MEM[dev] - allocated, 0)
 
 
 # Persistent device workspace for the large intermediates of the bucketed path (records, bucket-sorted
