@@ -76,7 +76,7 @@ sk_push_records_kernel(const u64* __restrict__ rec, u64 cap1, const u32* __restr
         for (int u = 0; u < PUSH_PER; ++u) {
             const u64 p = lo + (u64)u * PUSH_THREADS + tid;
             if (p < last) {
-                u64 pad;
+                [[maybe_unused]] u64 pad;
                 asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
                              : "=l"(hi_[u]), "=l"(lo_[u]), "=l"(mt[u]), "=l"(pad)
                              : "l"(rec + 4u * (slot0 + idx[u])));
@@ -183,7 +183,8 @@ sk_push_sorted_kernel(const u64* __restrict__ rec, u64 cap1, const u64* __restri
         for (int u = 0; u < PS_PER; ++u) {
             const u32 i = (u32)u * PS_THREADS + tid;
             if (i < n) {
-                u64 hi, lw, mt, pad;
+                u64 hi, lw, mt;
+                [[maybe_unused]] u64 pad;
                 asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
                              : "=l"(hi), "=l"(lw), "=l"(mt), "=l"(pad)
                              : "l"(slots + 4u * i));

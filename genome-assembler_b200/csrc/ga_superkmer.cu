@@ -61,7 +61,7 @@ __device__ __forceinline__ void sk_store_slot(u64* __restrict__ rec, u64 slot, u
                  : "memory");
 }
 __device__ __forceinline__ void sk_load_slot(const u64* __restrict__ rec, u64 slot, ulonglong2& bases, u64& meta) {
-    u64 pad;
+    [[maybe_unused]] u64 pad;
     asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(bases.x), "=l"(bases.y), "=l"(meta), "=l"(pad)
                  : "l"(rec + 4u * slot));
@@ -717,11 +717,6 @@ constexpr u32 SA_PENDING = SA_SOLID | SA_PAYLOAD;
 // ---- table, queue and solid storage: shared memory (byte addresses in the shared window) or global scratch
 struct MemShared {
     u32 keys, state, queue, skeys, stamps;      // shared byte addresses
-    __device__ __forceinline__ u64 ld_k(u32 s) const {
-        u64 v;
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(keys + 8u * s));
-        return v;
-    }
     __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
         u64 old;
         asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(keys + 8u * s), "l"(cmp), "l"(val) : "memory");
@@ -750,7 +745,6 @@ struct MemShared {
         asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "r"(keys + 8u * s0));
     }
     // notes, 8 bytes: first << 63 | slot << 49 | payload (c << 47 | ordinal, or what the FIRST state held)
-    static constexpr u32 kNoteBytes = 8;
     __device__ __forceinline__ void q_st(u32 i, bool first, u32 slot, u64 payload) const {
         const u64 v = ((u64)first << 63) | ((u64)slot << 49) | payload;
         asm volatile("st.shared.u64 [%0], %1;" ::"r"(queue + 8u * i), "l"(v) : "memory");
@@ -791,7 +785,6 @@ struct MemGlobal {
     u64* queue;
     u64* skeys;
     u64* stamps;
-    __device__ __forceinline__ u64 ld_k(u32 s) const { return ((volatile u64*)keys)[s]; }
     __device__ __forceinline__ u64 cas_k(u32 s, u64 cmp, u64 val) const {
         return atomicCAS((unsigned long long*)(keys + s), cmp, val);
     }
@@ -808,7 +801,7 @@ struct MemGlobal {
         k0 = ((volatile u64*)keys)[s0];
         k1 = ((volatile u64*)keys)[s0 + 1u];
     }
-    static constexpr u32 kNoteBytes = 16;       // tables beyond 2^14 slots: two words per note
+    // (tables beyond 2^14 slots: two words per note)
     __device__ __forceinline__ void q_st(u32 i, bool first, u32 slot, u64 payload) const {
         queue[2u * (size_t)i] = ((u64)first << 63) | slot;
         queue[2u * (size_t)i + 1u] = payload;
@@ -890,7 +883,7 @@ __device__ __forceinline__ u64 shfl64(u64 v, u32 src) {
 // what finds the record again: its index entry, or its number inside the bucket in the dense form).
 // A record's tag (its index entry, or its number inside the bucket: below 2^25, the host checks) travels with the
 // number of identical records it stands for (warp-level merge below): tag | (copies - 1) << 26.
-constexpr u32 SK_TAG_BITS = 26, SK_TAG_MASK = (1u << SK_TAG_BITS) - 1u;
+[[maybe_unused]] constexpr u32 SK_TAG_BITS = 26, SK_TAG_MASK = (1u << SK_TAG_BITS) - 1u;
 
 // Optional (-DGA_SK_MERGE, off): identical records inside one batch of 32 are merged before their windows are
 // dealt out.  At the coverage of real read sets most records are exact copies of one another (BASELINE config
@@ -905,7 +898,7 @@ constexpr u32 SK_TAG_BITS = 26, SK_TAG_MASK = (1u << SK_TAG_BITS) - 1u;
 // ones (a probe that hits, one state load, one stamp compare), the insertions and state changes of the error
 // windows stay, and MATCH x3 + the gap-closing shuffles cost more than the 1.7 dealt rounds they save.
 // Only the symbols the record uses take part in the comparison (the 64-symbol field runs on into the read).
-__device__ __forceinline__ void sk_merge_copies(u64& hi, u64& lo, u64& meta, u32& rtag, bool& have, int w) {
+[[maybe_unused]] __device__ __forceinline__ void sk_merge_copies(u64& hi, u64& lo, u64& meta, u32& rtag, bool& have, int w) {
     const u32 lane = threadIdx.x & 31u;
     const u32 used = have ? meta_windows(meta) + (u32)w - 1u + (meta_has_next(meta) ? 1u : 0u) : 0u;   // <= 63 symbols
     const u64 mh = used >= 32u ? hi : (used ? hi & ~(~0ull >> (2u * used)) : 0ull);
