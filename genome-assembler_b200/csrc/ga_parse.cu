@@ -284,8 +284,9 @@ extern "C" int ga_parse_reads(const uint8_t* text, uint64_t n_bytes, uint8_t* sy
             const uint8_t* b1 = (const uint8_t*)memchr(l, '|', (size_t)(h - l));
             const uint8_t* b2 = (const uint8_t*)memchr(b1 + 1, '|', (size_t)(h - b1 - 1));
             if (!ga_parse_int(b2 + 1, h, distance_out)) {
-                ga_set_error("ga_parse_reads: the distance field of the last pair is not an integer");
-                return GA_ERR_BAD_ARG;
+                // not a plain decimal number: Python's int() decides (it takes "1_0", refuses "x"), as upstream
+                ga_set_error("ga_parse_reads: the distance field of the last pair is not a plain integer");
+                return GA_ERR_ALPHABET;
             }
         }
         *n_symbols_out = sym;
@@ -306,8 +307,8 @@ extern "C" int ga_parse_reads(const uint8_t* text, uint64_t n_bytes, uint8_t* sy
             const uint8_t* b1 = (const uint8_t*)memchr(lo, '|', (size_t)(hi - lo));
             const uint8_t* b2 = (const uint8_t*)memchr(b1 + 1, '|', (size_t)(hi - b1 - 1));
             if (!ga_parse_int(b2 + 1, hi, distance_out)) {
-                ga_set_error("ga_parse_reads: the distance field of the last pair is not an integer");
-                return GA_ERR_BAD_ARG;
+                ga_set_error("ga_parse_reads: the distance field of the last pair is not a plain integer");
+                return GA_ERR_ALPHABET;
             }
         }
     }

@@ -414,7 +414,9 @@ int ga_sk_push_sorted(const void* records_dev, uint64_t l1_capacity, const uint6
  * line; missing lines are empty reads, or GA_ERR_BAD_ARG for pairs; trailing lines ignored) into one buffer
  * of symbols (mates of a pair back to back) and one length per read / mate -- no per-read objects.
  * symbols_out == NULL: sizing call, only *n_reads_out, *paired_out and *n_symbols_out (an upper bound) are
- * set.  GA_ERR_ALPHABET (parsing call): the input is not plain ASCII (the caller parses it as text instead).
+ * set.  GA_ERR_ALPHABET (parsing call): the input is not plain ASCII, or the distance field of the last pair line
+ * is not a plain decimal integer -- the caller parses the input as text instead, so that Python's own rules decide
+ * (int("1_0") is 10, int("x") raises, exactly as upstream).
  * Inputs of several MB whose only line break is "\n" are parsed by up to 16 host threads (GA_PARSE_THREADS), one
  * byte range each; the result is that of the serial scan. */
 int ga_parse_reads(const uint8_t* text, uint64_t n_bytes, uint8_t* symbols_out, int32_t* lens_out,

@@ -104,8 +104,13 @@ def test_parallel_parse_rejects_what_the_serial_parse_rejects(text, monkeypatch)
     monkeypatch.setenv("GA_PARSE_GRAIN", "1")
     with pytest.raises(ValueError):
         _text_path(text)
+    if text.endswith("|x\n"):       # a distance only Python can judge: the raw parser hands the input to the text path
+        assert ga_ingest.parse(text.encode("ascii")) is None
+    else:
+        with pytest.raises(ValueError):
+            ga_ingest.parse(text.encode("ascii"))
     with pytest.raises(ValueError):
-        ga_ingest.parse(text.encode("ascii"))
+        assemble.IOHandler.read_input(io.BytesIO(text.encode("ascii")))
 
 
 def test_parallel_parse_large_input(monkeypatch):
@@ -123,3 +128,88 @@ def test_parallel_parse_large_input(monkeypatch):
     b = ga_ingest.parse(text)
     assert a[1:] == b[1:] and np.array_equal(a[0].lens, b[0].lens) and np.array_equal(a[0].symbols, b[0].symbols)
     assert a[0].lens.tolist() == lens.tolist()
+
+
+def _reference_read_input(raw: bytes):
+    """The UNMODIFIED reference's IOHandler.read_input (oracle/_ref, copied from /root/reference by oracle/make_ref.py)
+    over `raw` as its stdin: ("ok", reads, paired, distance, bases) or ("err", exception name)."""
+    import importlib.util
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref_dir = os.path.join(os.path.dirname(here), "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "assemble.py")):
+        pytest.skip("oracle/_ref is only present where /root/reference is")
+    if "_ref_assemble" not in sys.modules:
+        sys.path.insert(0, ref_dir)
+        try:
+            spec = importlib.util.spec_from_file_location("_ref_assemble", os.path.join(ref_dir, "assemble.py"))
+            module = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(module)
+            sys.modules["_ref_assemble"] = module
+        finally:
+            sys.path.remove(ref_dir)
+            for name in ("debruijn_graph", "debug_graph", "debruijn_node", "countminsketch"):
+                mod = sys.modules.get(name)          # the reference's siblings must not shadow the product's modules
+                if mod is not None and getattr(mod, "__file__", "").startswith(ref_dir):
+                    del sys.modules[name]
+    ref = sys.modules["_ref_assemble"]
+    old = sys.stdin
+    sys.stdin = io.TextIOWrapper(io.BytesIO(raw), encoding="ascii")
+    try:
+        return ("ok",) + tuple(ref.IOHandler.read_input())
+    except Exception as exc:        # noqa: BLE001 -- the exception TYPE is what is compared
+        return ("err", type(exc).__name__)
+    finally:
+        sys.stdin = old
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_fuzz_against_the_unmodified_reference(threads, monkeypatch):
+    """Adversarial stdin texts (odd headers, white space of every kind Python strips, CR / CRLF / LF, empty and
+    missing lines, malformed pair lines, distance fields only Python's int() understands) through the product's
+    IOHandler.read_input and through the reference's own: same reads, kind, distance, base count -- or the same
+    exception type."""
+    import random
+    monkeypatch.setenv("GA_PARSE_THREADS", str(threads))
+    monkeypatch.setenv("GA_PARSE_GRAIN", "1")
+    rng = random.Random(20261019 + threads)
+    alphabet = "ACGTNacgt_;x"
+    spaces = [" ", "\t", "\x0b", "\x0c", "\x1c", "\x1d", "\x1e", "\x1f"]
+
+    def read():
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 8)))
+        if rng.random() < 0.1:
+            at = rng.randrange(len(s) + 1)
+            s = s[:at] + rng.choice(spaces) + s[at:]
+        return s
+
+    for _ in range(2500):
+        n = rng.randrange(0, 6)
+        paired = rng.random() < 0.5
+        lines = []
+        for _line in range(rng.randrange(0, 7)):
+            if paired and rng.random() < 0.93:
+                parts = [read(), read(), rng.choice(["125", " 7", "3 ", "-2", "+4", "x", "", "1_0", "0x10", "1e3"])]
+                if rng.random() < 0.05:
+                    parts.append("9")
+                if rng.random() < 0.05:
+                    parts = parts[:2]
+                line = "|".join(parts)
+            else:
+                line = read()
+            if rng.random() < 0.15:
+                line = rng.choice(spaces) + line
+            if rng.random() < 0.15:
+                line = line + rng.choice(spaces)
+            lines.append(line)
+        head = rng.choice([str(n), " %d " % n, "+%d" % n, "-%d" % n, "0%d" % n, "%d.0" % n, "", "1_0", str(n) + "\t"])
+        nl = rng.choice(["\n", "\n", "\r\n", "\r"])
+        raw = (head + nl + nl.join(lines) + (nl if rng.random() < 0.7 else "")).encode("ascii")
+        want = _reference_read_input(raw)
+        try:
+            got = assemble.IOHandler.read_input(io.BytesIO(raw))
+            got = ("ok", list(got[0]), got[1], got[2], got[3])
+        except Exception as exc:        # noqa: BLE001
+            got = ("err", type(exc).__name__)
+        assert got == want, raw
