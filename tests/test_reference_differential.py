@@ -1,0 +1,197 @@
+"""Live differential tests against the UNMODIFIED reference (oracle/_ref, a verbatim copy of /root/reference made by
+oracle/make_ref.py; run in a separate process by tests/ref_worker.py because its modules carry the product's names).
+
+Fresh random inputs every time the seeds below change -- the committed golden vectors (tests/golden/golden.json) pin
+the named cases and 206 fuzz graphs; these tests widen that to inputs nobody has looked at: both oracles on new
+graphs (ragged reads, 2-5 letter alphabets, pairs with jitter, k from 3 up), the CLI's argument parser, the static
+helpers, and the node records.  CPU only.  Skipped where oracle/_ref is absent (the GPU box)."""
+import json
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "debruijn_graph.py")),
+                                reason="oracle/_ref is only present where /root/reference is")
+
+
+def ask_reference(jobs):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), REF_DIR],
+                         input=json.dumps(jobs), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout)
+
+
+def _random_case(i: int):
+    """Small read sets that force repeats, branching, fuzzy groups, ragged reads and perfect cycles; other shapes
+    than tests/golden/recipes.fuzz_recipe (longer reads, larger k, more coverage spread, circular and linear)."""
+    rng = random.Random(910000 + i)
+    alphabet = rng.choice(["AC", "ACG", "ACGT", "ACGT", "ACGTN", "ab_;"])
+    glen = rng.randint(8, 160)
+    genome = "".join(rng.choice(alphabet) for _ in range(glen))
+    if rng.random() < 0.2:                                   # tandem repeat: cycles and branching
+        unit = genome[:rng.randint(2, 7)]
+        genome = (unit * (glen // len(unit) + 1))[:glen]
+    paired = bool(i % 3 == 0)
+    L = rng.randint(5, 24)
+    k = rng.randint(3, min(L, 16))
+    F = rng.choice([0, 0, 1, 2, 3, 5])
+    N = rng.randint(1, 160)
+    circ = genome * (2 + (L + 12) // glen + 1)
+    reads = []
+    for _ in range(N):
+        s = rng.randrange(glen)
+        r1 = circ[s:s + L]
+        if rng.random() < 0.25:
+            p = rng.randrange(L)
+            r1 = r1[:p] + rng.choice(alphabet) + r1[p + 1:]
+        if paired:
+            s2 = (s + rng.randint(2, 10) + rng.randint(-2, 2)) % glen
+            r2 = circ[s2:s2 + L]
+            if rng.random() < 0.1:
+                p = rng.randrange(L)
+                r2 = r2[:p] + rng.choice(alphabet) + r2[p + 1:]
+            reads.append([r1, r2])
+        else:
+            if rng.random() < 0.12:
+                r1 = r1[:rng.randint(0, L)]
+            reads.append(r1)
+    return {"job": "graph", "reads": reads, "paired": paired, "k": k, "F": F}
+
+
+def test_both_oracles_on_fresh_graphs():
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+    from helpers import counts_sha
+    jobs = [_random_case(i) for i in range(800)]
+    answers = ask_reference(jobs)
+    shapes = set()
+    for job, want in zip(jobs, answers):
+        assert "error" not in want, want
+        reads = [tuple(r) for r in job["reads"]] if job["paired"] else job["reads"]
+        tally, _, graph = po.assemble(reads, job["k"], job["F"], job["paired"])
+        assert counts_sha(tally.items()) == want["counts_sha"] and len(tally) == want["n_distinct"]
+        assert (len(graph.keys), graph.num_edges, graph.digest()) == \
+            (want["n_nodes"], want["num_edges"], want["graph_digest"]), job
+        assert po.contigs(graph) == want["contigs"], job
+        res = co.assemble(reads, job["k"], job["F"], job["paired"])
+        assert counts_sha(res.counts_dict().items()) == want["counts_sha"]
+        assert (res.n_nodes, res.num_edges, res.digest()) == (want["n_nodes"], want["num_edges"], want["graph_digest"]), job
+        assert res.contigs() == want["contigs"], job
+        res.close()
+        shapes.add((job["paired"], want["n_nodes"] > 0, len(want["contigs"]) > 1))
+    assert len(shapes) >= 6            # empty and non-empty graphs, one and several contigs, both kinds
+
+
+def test_cli_argument_parser():
+    """assemble.py's flags, abbreviations and refusals (assemble.py:13-37 of the reference).  `-p/--paired` is the one
+    deliberate addition (the reference exits with status 2 on it; BASELINE.json's north star names it)."""
+    import assemble
+    rng = random.Random(4)
+    pool = ["-t", "-m", "-c", "-s", "--time", "--memory", "--count_min_sketch", "--stdout", "--std", "--mem", "--count",
+            "-k", "--kmer_length", "--kmer", "--k", "-f", "--filter_threshold", "--filter", "--fil", "--f", "-e",
+            "--error", "--err", "--e", "-ts", "-tmcs", "-k31", "-f3", "--kmer_length=28", "--filter=2", "-x", "--bogus",
+            "extra", "--t", "--m", "--s", "--c"]
+    values = ["31", "3", "0", "-1", "x", "2.5", "", "28"]
+    vectors = [[], ["-k", "28", "-f", "3", "-s"], ["--kmer_length", "28", "--filter", "3", "--stdout"], ["-h"]]
+    for _ in range(400):
+        argv = []
+        for _piece in range(rng.randint(0, 5)):
+            flag = rng.choice(pool)
+            argv.append(flag)
+            if flag.lstrip("-") and flag in ("-k", "--kmer_length", "--kmer", "--k", "-f", "--filter_threshold", "--filter",
+                                             "--fil", "--f", "-e", "--error", "--err", "--e") and rng.random() < 0.85:
+                argv.append(rng.choice(values))
+        vectors.append(argv)
+    answers = ask_reference([{"job": "args", "argv": v} for v in vectors])
+    import contextlib
+    import io
+    for argv, want in zip(vectors, answers):
+        try:
+            with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+                ns = vars(assemble.IOHandler.read_args(argv))
+            assert ns.pop("paired") is False
+            got = {"ok": ns}
+        except SystemExit as exc:
+            got = {"exit": exc.code}
+        assert got == want, argv
+    with contextlib.redirect_stderr(io.StringIO()):
+        assert vars(assemble.IOHandler.read_args(["-p", "-k", "5"]))["paired"] is True
+        assert vars(assemble.IOHandler.read_args(["--paired"]))["paired"] is True
+
+
+def test_static_helpers():
+    """_hash (MurmurHash3_x86_32 incl. seeds and bytes above 0x7f), the overlap rule, read breaking (also reads shorter
+    than a window and ragged mates), _pairwise, valid_allowed_error -- countminsketch.py:46-95,
+    debruijn_graph.py:36-44, 154-157, 336-347, 369-374 of the reference."""
+    import countminsketch
+    import debruijn_graph as dg
+    rng = random.Random(8)
+
+    def word(alphabet, lo, hi):
+        return "".join(rng.choice(alphabet) for _ in range(rng.randint(lo, hi)))
+
+    job = {"job": "helpers",
+           "hash": [[word("ACGT", 0, 70), 0] for _ in range(300)] +
+                   [[word("ACGTN_;ab\x7f\x80\xe9\xff", 0, 40), rng.choice([0, 1, 42, 0xFFFFFFFF, 0x9747B28C])] for _ in range(300)],
+           "overlap": [[word("AC", 0, 9), word("AC", 0, 9)] for _ in range(600)] +
+                      [[word("ACGT", 3, 30), word("ACGT", 3, 30)] for _ in range(100)],
+           "break": [[rng.randint(2, 12), word("ACGT", 0, 20)] for _ in range(300)],
+           "break_paired": [[rng.randint(2, 12), [word("ACGT", 0, 20), word("ACGT", 0, 20)]] for _ in range(300)],
+           "pairwise": [[rng.randrange(100) for _ in range(rng.randint(0, 9))] for _ in range(50)],
+           "valid": [[rng.randint(-2, 40), rng.randint(-2, 40)] for _ in range(100)]}
+    same_len = [[word("ACGT", n, n), word("ACGT", n, n)] for n in range(3, 40) for _ in range(4)]
+    job["overlap"] += same_len
+    (want,) = ask_reference([job])
+    assert [countminsketch.CountMinSketch._hash(s, seed) for s, seed in job["hash"]] == want["hash"]
+    assert [dg.PairedDeBruijnGraph._find_longest_overlap_brute(a, b) for a, b in job["overlap"]] == want["overlap"]
+    assert [dg.DeBruijnGraph._break_read_into_k_minus_one_mers(k, r) for k, r in job["break"]] == want["break"]
+    assert [[list(t) for t in dg.PairedDeBruijnGraph._break_read_into_k_minus_one_mers(k, tuple(r))]
+            for k, r in job["break_paired"]] == want["break_paired"]
+    assert [[list(t) for t in dg.AbstractDeBruijnGraph._pairwise(x)] for x in job["pairwise"]] == want["pairwise"]
+    assert [bool(dg.AbstractDeBruijnGraph.valid_allowed_error(k, e)) for k, e in job["valid"]] == want["valid"]
+
+
+def test_node_records_behave_alike():
+    """Node / PairedNode under random scripts of append_edge / pop_edge / in-degree changes: the same observable
+    state after every step (debruijn_node.py:4-33, 56-63), popping from an empty node included."""
+    import debruijn_node as ours
+    rng = random.Random(15)
+    jobs = []
+    for i in range(120):
+        paired = bool(i & 1)
+        ops = []
+        for _ in range(rng.randint(1, 14)):
+            r = rng.random()
+            if r < 0.5:
+                e = "".join(rng.choice("AC") for _ in range(3))
+                ops.append(["append", [e, e[::-1]] if paired else e])
+            elif r < 0.85:
+                ops.append(["pop", None])
+            else:
+                ops.append(["in", rng.randint(0, 3)])
+        jobs.append({"job": "nodes", "paired": paired, "data": ["ACG", "TTA"] if paired else "ACG", "ops": ops})
+    answers = ask_reference(jobs)
+    for job, want in zip(jobs, answers):
+        node = ours.PairedNode(*job["data"]) if job["paired"] else ours.Node(job["data"])
+        trace = []
+        for op, arg in job["ops"]:
+            got = None
+            if op == "append":
+                node.append_edge(tuple(arg) if job["paired"] else arg)
+            elif op == "pop":
+                try:
+                    got = node.pop_edge()
+                    got = [list(got[0]) if isinstance(got[0], tuple) else got[0], got[1]]
+                except Exception as exc:        # noqa: BLE001
+                    got = "raised " + type(exc).__name__
+            else:
+                node.num_edges_in += arg
+            edges = [list(e) if isinstance(e, tuple) else e for e in node.edges]
+            trace.append([got, node.outdegree, node.indegree, edges, node.num_edges_in, node.was_branching])
+        assert trace == want, job
