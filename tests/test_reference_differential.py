@@ -3,7 +3,8 @@ oracle/make_ref.py; run in a separate process by tests/ref_worker.py because its
 
 Fresh random inputs every time the seeds below change -- the committed golden vectors (tests/golden/golden.json) pin
 the named cases and 206 fuzz graphs; these tests widen that to inputs nobody has looked at: both oracles on new
-graphs (ragged reads, 2-5 letter alphabets, pairs with jitter, k from 3 up), the CLI's argument parser, the static
+graphs (ragged reads, 2-5 letter alphabets, pairs with jitter, k from 3 up) and the product's host contig traversal
+over them, the CLI's argument parser, the static
 helpers, and the node records.  CPU only.  Skipped where oracle/_ref is absent (the GPU box)."""
 import json
 import os
@@ -68,6 +69,7 @@ def test_both_oracles_on_fresh_graphs():
     from oracle import c_oracle as co
     from oracle import py_oracle as po
     from helpers import counts_sha
+    from test_host_side import _traverse
     jobs = [_random_case(i) for i in range(800)]
     answers = ask_reference(jobs)
     shapes = set()
@@ -79,6 +81,8 @@ def test_both_oracles_on_fresh_graphs():
         assert (len(graph.keys), graph.num_edges, graph.digest()) == \
             (want["n_nodes"], want["num_edges"], want["graph_digest"]), job
         assert po.contigs(graph) == want["contigs"], job
+        # the product's host traversal (ga_traverse_contigs: serial sweep and forced piecewise walk) over the same graph
+        assert _traverse(graph) == want["contigs"], job
         res = co.assemble(reads, job["k"], job["F"], job["paired"])
         assert counts_sha(res.counts_dict().items()) == want["counts_sha"]
         assert (res.n_nodes, res.num_edges, res.digest()) == (want["n_nodes"], want["num_edges"], want["graph_digest"]), job
