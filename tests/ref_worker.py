@@ -64,7 +64,9 @@ def job_graph(job):
     n_nodes, digest = graph_digest(graph, job["paired"])
     num_edges = graph.num_edges
     contigs = graph.enumerate_contigs()
-    return {"counts_sha": sha16("".join("%s:%d\n" % kc for kc in items).encode()), "n_distinct": len(items),
+    after = graph_digest(graph, job["paired"])[1]          # what is left of the nodes once the contigs are out
+    return {"digest_after": after, "edges_left": graph.num_edges,
+            "counts_sha": sha16("".join("%s:%d\n" % kc for kc in items).encode()), "n_distinct": len(items),
             "n_nodes": n_nodes, "num_edges": num_edges, "graph_digest": digest, "contigs": contigs,
             "constants": [graph.KMER_LEN, graph.HAMMING_DIST, graph.ALLOWED_PAIRED_DIST_ERROR]}
 

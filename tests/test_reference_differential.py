@@ -199,3 +199,82 @@ def test_node_records_behave_alike():
             edges = [list(e) if isinstance(e, tuple) else e for e in node.edges]
             trace.append([got, node.outdegree, node.indegree, edges, node.num_edges_in, node.was_branching])
         assert trace == want, job
+
+
+def _graph_digest(graph, paired):
+    """tests/ref_worker.graph_digest, on the product's graph object."""
+    import hashlib
+    h = hashlib.sha256()
+    if paired:
+        it = (((a, b), node) for a, inner in graph.nodes.items() for b, node in inner.items())
+    else:
+        it = iter(graph.nodes.items())
+    n = 0
+    for key, node in it:
+        h.update(repr((key, list(node.edges), node.num_edges_in, node.was_branching)).encode())
+        n += 1
+    return n, h.hexdigest()[:16]
+
+
+def _product_graph(job, graph):
+    """The product's graph object (debruijn_graph.DeBruijnGraph / PairedDeBruijnGraph) around a CSR that was NOT built
+    on the GPU: the arrays come from the oracle's graph, packed the way ga_csr_emit hands them over.
+    Everything above the CSR -- lazy `nodes`, Node objects, traversal on the CSR and on objects -- is the product's."""
+    import numpy as np
+    import debruijn_graph as dg
+    import ga_device as gd
+    from test_host_side import _graph_arrays
+    paired = job["paired"]
+    symbols = sorted({ord(ch) for r in job["reads"] for ch in ("".join(r) if paired else r)})
+    alphabet = gd.Alphabet(np.array(symbols))
+    w = job["k"] - 1
+    kw = 1 if w * alphabet.sym_bits <= 64 else 2
+    csr = gd.BuiltGraph(paired, w, alphabet, kw)
+    rowptr, col, indeg, branching, last = _graph_arrays(graph)
+    csr.n_nodes, csr.n_edges, csr.num_edges_attr = len(graph.keys), len(col), graph.num_edges
+    csr.rowptr, csr.col, csr.indeg, csr.branching, csr.last_char = rowptr, col, indeg, branching, last
+
+    def pack(strings):
+        out = np.zeros((len(strings), kw), dtype=np.uint64)
+        for i, text in enumerate(strings):
+            lo, hi = alphabet.pack_key(text, kw)
+            out[i, 0] = lo
+            if kw > 1:
+                out[i, 1] = hi
+        return out
+
+    if paired:
+        csr.keys_a, csr.keys_b = pack([a for a, _ in graph.keys]), pack([b for _, b in graph.keys])
+    else:
+        csr.keys_a = pack(list(graph.keys))
+    cls = dg.PairedDeBruijnGraph if paired else dg.DeBruijnGraph
+    g = cls.__new__(cls)
+    g.KMER_LEN, g.HAMMING_DIST = job["k"], job["F"]
+    g.num_edges = csr.num_edges_attr
+    g._csr, g._nodes, g._nodes_dirty, g._left = csr, None, False, None
+    return g
+
+
+def test_node_facade_and_both_traversals_on_fresh_graphs():
+    """What a user of the reference sees above the CSR: `graph.nodes` (dict / dict of dicts of Node objects, in the
+    reference's order, with edges, in-degrees and was_branching), `enumerate_contigs()` on the CSR and on the
+    objects (after somebody looked at `nodes`), `num_edges` and what is left of `nodes` afterwards."""
+    from oracle import py_oracle as po
+    jobs = [_random_case(i) for i in range(5000, 5400)]
+    answers = ask_reference(jobs)
+    for job, want in zip(jobs, answers):
+        reads = [tuple(r) for r in job["reads"]] if job["paired"] else job["reads"]
+        _, _, graph = po.assemble(reads, job["k"], job["F"], job["paired"])
+        # 1. contigs from the CSR first, then the nodes: only what was not popped is left
+        g = _product_graph(job, graph)
+        assert g.num_edges == want["num_edges"]
+        assert g.enumerate_contigs() == want["contigs"], job
+        assert g.num_edges == want["edges_left"]
+        assert _graph_digest(g, job["paired"]) == (want["n_nodes"], want["digest_after"]), job
+        assert g.enumerate_contigs() == []          # as upstream: nothing is left to walk
+        # 2. nodes first (materialised Node objects), then the traversal on those objects
+        g = _product_graph(job, graph)
+        assert _graph_digest(g, job["paired"]) == (want["n_nodes"], want["graph_digest"]), job
+        assert g.enumerate_contigs() == want["contigs"], job
+        assert g.num_edges == want["edges_left"]
+        assert _graph_digest(g, job["paired"]) == (want["n_nodes"], want["digest_after"]), job
