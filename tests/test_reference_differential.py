@@ -278,3 +278,81 @@ def test_node_facade_and_both_traversals_on_fresh_graphs():
         assert g.enumerate_contigs() == want["contigs"], job
         assert g.num_edges == want["edges_left"]
         assert _graph_digest(g, job["paired"]) == (want["n_nodes"], want["digest_after"]), job
+
+
+def _install_cpu_shim(monkeypatch):
+    """TEST-ONLY stand-ins for the two GPU hooks, so that everything AROUND them (the CLI, the -t / -m mixin, hook
+    order, output writers) can be run next to the reference on a machine without a GPU: `_count_kmers` answers from
+    the Python oracle, `_build_graph` installs a CSR taken from the oracle's graph (`_product_graph`).  The product
+    itself has no such path."""
+    import debruijn_graph as dg
+    from oracle import py_oracle as po
+
+    def count_for(paired):
+        def count(k, reads):
+            reads = list(reads)
+            return po.count_paired(k, reads) if paired else po.count_unpaired(k, reads)
+        return staticmethod(count)
+
+    def build(self, kmer_counts, reads):
+        reads = list(reads)
+        _, _, graph = po.assemble(reads, self.KMER_LEN, self.HAMMING_DIST, self._PAIRED)
+        job = {"paired": self._PAIRED, "reads": reads, "k": self.KMER_LEN, "F": self.HAMMING_DIST}
+        made = _product_graph(job, graph)
+        self._csr, self.num_edges = made._csr, made.num_edges
+        self._nodes, self._nodes_dirty, self._left = None, False, None
+
+    monkeypatch.setattr(dg.DeBruijnGraph, "_count_kmers", count_for(False))
+    monkeypatch.setattr(dg.PairedDeBruijnGraph, "_count_kmers", count_for(True))
+    monkeypatch.setattr(dg._GpuGraphBase, "_build_graph", build)
+
+
+def _mask(lines, sizes_too=()):
+    import re
+    out = []
+    for line in lines:
+        if line.startswith(">Time"):
+            continue
+        line = re.sub(r"T ?= ?[0-9]+\.[0-9]+", "T=#", line)
+        if any(line.startswith(label) for label in sizes_too):
+            line = re.sub(r"[0-9,]+$", "#", line)
+        out.append(line)
+    return out
+
+
+@pytest.mark.parametrize("flags", [["-s"], ["-s", "-t"], ["-s", "-m"], ["-s", "-t", "-m"], [], ["-t"]])
+def test_cli_around_the_hooks(flags, monkeypatch, capsys, tmp_path):
+    """The product's assemble.main() next to the reference's own CLI (a subprocess of oracle/_ref/assemble.py) on the
+    same stdin: every printed line -- banners of -t, size reports of -m, the contig report on stdout or in
+    ./output/*.FASTQ -- with wall-clock values masked.  Of the -m sizes only those of the two containers whose TYPE
+    differs by design (the read sequence and the k-mer counts facade) are masked; graph and node sizes must agree."""
+    import io
+    import assemble
+    _install_cpu_shim(monkeypatch)
+    hidden = (">SIZE OF READ CONTAINER", ">SIZE OF COUNTS CONTAINER", ">SIZE OF STRINGS IN COUNTS")
+    rng = random.Random(77)
+    for i in (3, 4, 6, 7, 9, 12):                  # pairs and plain reads
+        job = _random_case(7000 + i)
+        if job["k"] < 4:
+            job["k"] = 4
+        lines = ["|".join(r) + "|7" if job["paired"] else r for r in job["reads"]]
+        text = "%d\n%s\n" % (len(lines), "\n".join(lines))
+        argv = flags + ["-k", str(job["k"]), "-f", str(job["F"])] + (["-e", "1"] if rng.random() < 0.5 else [])
+        ref_dir = tmp_path / ("ref%d" % i)
+        our_dir = tmp_path / ("our%d" % i)
+        ref_dir.mkdir()
+        our_dir.mkdir()
+        ref = subprocess.run([sys.executable, os.path.join(REF_DIR, "assemble.py")] + argv, input=text,
+                             capture_output=True, text=True, cwd=ref_dir, timeout=300)
+        assert ref.returncode == 0, ref.stderr[-1500:]
+        monkeypatch.chdir(our_dir)
+        monkeypatch.setattr(sys, "stdin", io.TextIOWrapper(io.BytesIO(text.encode("ascii")), encoding="ascii"))
+        capsys.readouterr()
+        assemble.main(argv)
+        ours = capsys.readouterr().out
+        assert _mask(ours.split("\n"), hidden) == _mask(ref.stdout.split("\n"), hidden), (argv, job)
+        if "-s" not in flags:
+            (theirs,) = list((ref_dir / "output").iterdir())
+            (mine,) = list((our_dir / "output").iterdir())
+            assert mine.name.split("_k")[1] == theirs.name.split("_k")[1]            # ..._k{K}_f{F}_e{E}.FASTQ
+            assert _mask(mine.read_text().split("\n")) == _mask(theirs.read_text().split("\n"))
