@@ -130,7 +130,7 @@ def test_parallel_parse_large_input(monkeypatch):
     assert a[0].lens.tolist() == lens.tolist()
 
 
-def _reference_read_input(raw: bytes):
+def _reference_read_input(raw: bytes, encoding: str = "ascii"):
     """The UNMODIFIED reference's IOHandler.read_input (oracle/_ref, copied from /root/reference by oracle/make_ref.py)
     over `raw` as its stdin: ("ok", reads, paired, distance, bases) or ("err", exception name)."""
     import importlib.util
@@ -155,7 +155,7 @@ def _reference_read_input(raw: bytes):
                     del sys.modules[name]
     ref = sys.modules["_ref_assemble"]
     old = sys.stdin
-    sys.stdin = io.TextIOWrapper(io.BytesIO(raw), encoding="ascii")
+    sys.stdin = io.TextIOWrapper(io.BytesIO(raw), encoding=encoding)
     try:
         return ("ok",) + tuple(ref.IOHandler.read_input())
     except Exception as exc:        # noqa: BLE001 -- the exception TYPE is what is compared
@@ -207,6 +207,51 @@ def test_fuzz_against_the_unmodified_reference(threads, monkeypatch):
         nl = rng.choice(["\n", "\n", "\r\n", "\r"])
         raw = (head + nl + nl.join(lines) + (nl if rng.random() < 0.7 else "")).encode("ascii")
         want = _reference_read_input(raw)
+        try:
+            got = assemble.IOHandler.read_input(io.BytesIO(raw))
+            got = ("ok", list(got[0]), got[1], got[2], got[3])
+        except Exception as exc:        # noqa: BLE001
+            got = ("err", type(exc).__name__)
+        assert got == want, raw
+
+
+def test_fuzz_unicode_against_the_unmodified_reference():
+    """The same with UTF-8 input -- letters outside ASCII, white space only str.strip() knows (NBSP, U+2003, U+0085,
+    U+3000), digits only int() knows (Arabic-Indic, full-width), a stray 0xFF byte: the raw parser steps aside and the
+    text path must apply Python's rules exactly as the reference does."""
+    import random
+    rng = random.Random(20261020)
+    alphabet = "ACGT\u00e9\u0663x"
+    spaces = [" ", "\t", "\u00a0", "\u2003", "\u0085", "\u2009", "\x1c", "\u3000"]
+
+    def read():
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 7)))
+        if rng.random() < 0.15:
+            at = rng.randrange(len(s) + 1)
+            s = s[:at] + rng.choice(spaces) + s[at:]
+        return s
+
+    for _ in range(2500):
+        n = rng.randrange(0, 5)
+        paired = rng.random() < 0.5
+        lines = []
+        for _line in range(rng.randrange(0, 6)):
+            if paired and rng.random() < 0.93:
+                line = "|".join([read(), read(), rng.choice(["125", " 7", "\u0663", "\u00a05", "x", "", "\uff11\uff12"])])
+            else:
+                line = read()
+            if rng.random() < 0.2:
+                line = rng.choice(spaces) + line
+            if rng.random() < 0.2:
+                line = line + rng.choice(spaces)
+            lines.append(line)
+        head = rng.choice([str(n), " %d " % n, "\u0663", "\u00a0%d" % n, "%d\u2003" % n, ""])
+        nl = rng.choice(["\n", "\n", "\r\n", "\r"])
+        raw = (head + nl + nl.join(lines) + (nl if rng.random() < 0.7 else "")).encode("utf-8")
+        if rng.random() < 0.03:
+            at = rng.randrange(len(raw) + 1)
+            raw = raw[:at] + b"\xff" + raw[at:]
+        want = _reference_read_input(raw, "utf-8")
         try:
             got = assemble.IOHandler.read_input(io.BytesIO(raw))
             got = ("ok", list(got[0]), got[1], got[2], got[3])
