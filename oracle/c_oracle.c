@@ -14,7 +14,8 @@
  *   - paired build + fuzzy key   debruijn_graph.py:269-347
  *   - contig traversal           debruijn_graph.py:72-111, :222-267
  * Parity pin: tests/test_oracle.py checks it against tests/golden/golden.json (outputs of
- * the unmodified reference) and against oracle/py_oracle.py.
+ * the unmodified reference) and against oracle/py_oracle.py; tests/test_reference_differential.py runs it
+ * next to the live reference (oracle/_ref/, where present) on fresh random inputs.
  */
 #include <stdint.h>
 #include <stdlib.h>

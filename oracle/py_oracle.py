@@ -13,7 +13,8 @@ checkout, ``/root/reference`` in the build container).
 Parity pin: ``tests/golden/golden.json`` holds digests produced by the *unmodified*
 reference (``tests/golden/make_golden.py``); ``tests/test_oracle.py`` checks this
 module against every one of them, plus the README known-answer test and the
-MurmurHash3 vectors of SURVEY App. B.1.
+MurmurHash3 vectors of SURVEY App. B.1; where ``oracle/_ref/`` (the unmodified reference) is present,
+``tests/test_reference_differential.py`` also runs it next to the reference on fresh random inputs.
 """
 from __future__ import annotations
 
