@@ -531,6 +531,12 @@ class KmerCounts:
     def __bool__(self):
         return self.n_occ > 0
 
+    def __sizeof__(self):
+        """The -m report prints sys.getsizeof(counts) (debug_graph.py:51-63 of the reference): answer with the size
+        of its defaultdict(int) holding as many string keys."""
+        from py_sizes import for_instance, grown_str_dict_sizeof
+        return for_instance(grown_str_dict_sizeof(len(self)))
+
     def lookup_many(self, kmers):
         keys = np.zeros((len(kmers), self.key_words), dtype=np.uint64)
         known = np.zeros(len(kmers), dtype=bool)

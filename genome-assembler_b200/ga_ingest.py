@@ -60,6 +60,12 @@ class RawReads(Sequence):
     def __eq__(self, other):
         return list(self) == list(other)
 
+    def __sizeof__(self):
+        """The -m report prints sys.getsizeof(reads) (assemble.py:107-114 of the reference): answer with the size of
+        the list of as many appended entries."""
+        from py_sizes import appended_list_sizeof, for_instance
+        return for_instance(appended_list_sizeof(len(self)))
+
 
 def parse(raw: bytes):
     """(reads: RawReads, paired, distance, number of bases), or None when the bytes are not plain ASCII or the

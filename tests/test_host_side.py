@@ -423,3 +423,45 @@ def test_graph_checksum_host_and_tensor_paths_agree():
     g.col[[i, i + 1]] = g.col[[i + 1, i]]
     assert g.checksum() != want
     assert gd.BuiltGraph(True, 27, None, 1).checksum() == gd.BuiltGraph(True, 27, None, 1).checksum()     # empty graph
+
+
+def test_container_sizes_follow_the_interpreter():
+    """py_sizes: what sys.getsizeof reports for a list grown by appends and a defaultdict(int) grown by string-key
+    insertions -- the containers the reference's -m report weighs -- against the real objects, entry by entry; and
+    the product's stand-ins (RawReads, KmerCounts) answering with those numbers."""
+    import sys
+    from collections import defaultdict
+    import py_sizes
+    import ga_ingest
+    import ga_device as gd
+    grown, counts = [], defaultdict(int)
+    assert py_sizes.appended_list_sizeof(0) == grown.__sizeof__()
+    assert py_sizes.grown_str_dict_sizeof(0) == counts.__sizeof__()
+    for n in range(1, 70001):
+        grown.append(None)
+        counts["ACGT%d" % n] += 1
+        assert py_sizes.appended_list_sizeof(n) == grown.__sizeof__(), n
+        assert py_sizes.grown_str_dict_sizeof(n) == counts.__sizeof__(), n
+    big = []
+    for i in range(3 * 10 ** 6):                          # one large point each (C3 has 1.4 M reads, 15 M distinct windows)
+        big.append(None)
+    assert py_sizes.appended_list_sizeof(len(big)) == big.__sizeof__()
+    big = defaultdict(int)
+    for i in range(1500000):
+        big[str(i)] += 1
+    assert py_sizes.grown_str_dict_sizeof(1500000) == big.__sizeof__()
+    reads, _, _, _ = ga_ingest.parse(b"5\nAC\nGT\nAA\nCC\nGG\n")
+    five = []
+    for r in ("AC", "GT", "AA", "CC", "GG"):
+        five.append(r)
+    assert sys.getsizeof(reads) == sys.getsizeof(five)
+
+    class Counted(gd.KmerCounts):
+        def __init__(self, n):
+            self._n = n
+
+        def __len__(self):
+            return self._n
+
+    assert sys.getsizeof(Counted(70000)) == sys.getsizeof(counts)
+    assert sys.getsizeof(Counted(0)) == sys.getsizeof(defaultdict(int))
