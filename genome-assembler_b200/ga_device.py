@@ -718,9 +718,9 @@ def sk_bucket_pass(bases, meta, offsets, n_segments: int, hist, n_buckets: int, 
     # the state word of a table slot names a record (its number inside the bucket, or its slot inside the level-1
     # bucket) in 25 bits; that also keeps the 31-bit hand-out counter and the packed histogram inside their bits
     if n_occ >= (1 << 25) and bool((((hist >> 32) >= (1 << 25)) | (hist < 0)).any().item()):
-        raise gn.GaError("bucketed count: a bucket holds 2^25 records or more (one repeated window?)")
+        raise gn.GaBucketLimit("bucketed count: a bucket holds 2^25 records or more (one repeated window?)")
     if l1_capacity >= (1 << 25):
-        raise gn.GaError("bucketed count: level-1 buckets of 2^25 slots or more")
+        raise gn.GaBucketLimit("bucketed count: level-1 buckets of 2^25 slots or more")
     _mark("sk bucket: checks")
     # solid windows are at most n_occ / (threshold + 1); start from a guess and grow on demand (a second run of the
     # kernel).  Big inputs: one solid window per 48 occurrences (sequencing depth >= 60x; C4: one per 212).  Inputs
@@ -983,14 +983,24 @@ def build_graph(counts: KmerCounts, reads: DeviceReads, threshold: int, sketch=N
     counted = (not bucketed and keep_fn is None and sketch is None and counts._table is None and not counts._cand and
                reads.paired and counts.n_occ >= max(SUPERKMER_MIN_OCC, SUPERKMER_MIN_OCC_PAIRS) and
                superkmer_supported(reads, k, threshold, counting_only=True))
-    if bucketed:
-        solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold, feed)
-    elif counted:
-        solid_keys, n_solid = superkmer_solid(reads, k, threshold)       # read pairs: the solid set from the buckets
-    elif keep_fn is not None:
-        solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
-    else:
-        solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
+    solid_keys = None
+    if bucketed or counted:
+        try:
+            if bucketed:
+                solid_keys, n_solid, edge_stamp = superkmer_stamps(reads, k, threshold, feed)
+            else:
+                solid_keys, n_solid = superkmer_solid(reads, k, threshold)   # read pairs: the solid set from the buckets
+        except gn.GaBucketLimit:
+            # one window repeated tens of millions of times (adapter or poly-A reads): its bucket is beyond what a
+            # shared-memory pass can name.  The global-table kernels have no such limit; every read is resident by
+            # now (the scatter drained `feed`), and the buckets' workspace makes room for the tables
+            release_workspace()
+            bucketed = counted = False
+    if solid_keys is None:
+        if keep_fn is not None:
+            solid_keys, n_solid = _solid_keys_from_flags(counts, keep_fn)
+        else:
+            solid_keys, n_solid = _solid_keys(counts, threshold, sketch)
     _mark("select solid")
     if n_solid == 0 or reads.n_reads == 0:
         return graph

@@ -24,6 +24,12 @@ class GaError(RuntimeError):
     """A libga_b200 call failed (message from ga_last_error())."""
 
 
+class GaBucketLimit(GaError):
+    """The read set is outside what the bucketed kernels can name (a bucket of 2^25 records or more: one window
+    repeated tens of millions of times, e.g. adapter or poly-A reads).  ga_device.build_graph then takes the
+    global-table kernels, which have no such limit."""
+
+
 class GaReads(C.Structure):
     _fields_ = [("words", C.c_void_p), ("offsets", C.c_void_p), ("lengths", C.c_void_p),
                 ("n_reads", C.c_uint64), ("first_read", C.c_uint64),

@@ -465,3 +465,48 @@ def test_container_sizes_follow_the_interpreter():
 
     assert sys.getsizeof(Counted(70000)) == sys.getsizeof(counts)
     assert sys.getsizeof(Counted(0)) == sys.getsizeof(defaultdict(int))
+
+
+def test_bucket_limit_switches_to_the_table_kernels(monkeypatch):
+    """A bucket beyond what the shared-memory pass can name (GaBucketLimit: one window repeated tens of millions of
+    times) must not end the build: build_graph frees the buckets' workspace and goes on with the global-table
+    kernels.  Control flow only (the kernels themselves are stubbed; no GPU here)."""
+    import types
+    import torch
+    import ga_device as gd
+    import ga_native as gn
+
+    class Reached(Exception):
+        pass
+
+    calls = []
+
+    def refuse(*a, **kw):
+        calls.append("buckets")
+        raise gn.GaBucketLimit("bucketed count: a bucket holds 2^25 records or more (one repeated window?)")
+
+    def table_route(counts, threshold, sketch):
+        calls.append("tables")
+        raise Reached()
+
+    monkeypatch.setattr(gd, "_dev", lambda: torch.device("cpu"))
+    monkeypatch.setattr(gd, "superkmer_stamps", refuse)
+    monkeypatch.setattr(gd, "superkmer_solid", refuse)
+    monkeypatch.setattr(gd, "_solid_keys", table_route)
+    monkeypatch.setattr(gd, "release_workspace", lambda: calls.append("release"))
+    assert issubclass(gn.GaBucketLimit, gn.GaError)           # callers that catch GaError still see it
+    alphabet = gd.Alphabet(np.zeros(0))
+    for paired, n_occ in ((False, 1 << 23), (True, 1 << 29)):
+        reads = types.SimpleNamespace(paired=paired, alphabet=alphabet, first_read=0, n_reads=1000, estride=150,
+                                      status=None)
+        counts = types.SimpleNamespace(k=31, w=30, key_words=1, _table=None, _cand={}, n_occ=n_occ, slot_bytes=16)
+        calls.clear()
+        with pytest.raises(Reached):
+            gd.build_graph(counts, reads, 3)
+        assert calls == ["buckets", "release", "tables"]
+    # any other failure of the bucketed route is not swallowed
+    monkeypatch.setattr(gd, "superkmer_stamps", lambda *a, **kw: (_ for _ in ()).throw(gn.GaError("something else")))
+    reads = types.SimpleNamespace(paired=False, alphabet=alphabet, first_read=0, n_reads=1000, estride=150, status=None)
+    counts = types.SimpleNamespace(k=31, w=30, key_words=1, _table=None, _cand={}, n_occ=1 << 23, slot_bytes=16)
+    with pytest.raises(gn.GaError, match="something else"):
+        gd.build_graph(counts, reads, 3)
