@@ -683,6 +683,10 @@ def sk_scatter_local(reads: "DeviceReads", k: int, l1_bits: int, l2_bits: int, f
         needed = int(int(cursors1.max().item()) * 1.05) + 4096    # cursors kept counting past the capacity
         if fixed:
             raise ScatterOverflow(needed)
+        # level-1 buckets are slabs of one size: a read set whose records crowd into one of them (a window repeated
+        # tens of millions of times) would need that size n_l1 times over
+        if needed >= (1 << 25) or n_l1 * needed * 32 > 0.8 * _free_bytes() + rec.numel() * 8:
+            raise gn.GaBucketLimit("bucketed count: one level-1 bucket needs %d slots" % needed)
         cap1 = needed
         del rec                              # the view keeps the old slab alive: drop it before workspace() grows
     _mark("sk scatter reads")
