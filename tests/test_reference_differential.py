@@ -65,12 +65,41 @@ def _random_case(i: int):
     return {"job": "graph", "reads": reads, "paired": paired, "k": k, "F": F}
 
 
+def _random_case_long(i: int):
+    """Longer reads and windows of 16 ... 71 symbols (64-bit, 128-bit and -- beyond what the GPU path takes -- wider
+    keys), pairs a few dozen symbols apart."""
+    rng = random.Random(555000 + i)
+    alphabet = rng.choice(["ACGT", "ACGT", "AC", "ACGTN"])
+    glen = rng.randint(60, 400)
+    genome = "".join(rng.choice(alphabet) for _ in range(glen))
+    paired = i % 2 == 0
+    L = rng.randint(30, 90)
+    k = rng.randint(17, min(L, 72))
+    F = rng.choice([0, 1, 2, 3])
+    circ = genome * (3 + (L + 40) // glen)
+    reads = []
+    for _ in range(rng.randint(20, 200)):
+        s = rng.randrange(glen)
+        r1 = circ[s:s + L]
+        if rng.random() < 0.2:
+            p = rng.randrange(L)
+            r1 = r1[:p] + rng.choice(alphabet) + r1[p + 1:]
+        if paired:
+            s2 = (s + rng.randint(5, 30) + rng.randint(-2, 2)) % glen
+            reads.append([r1, circ[s2:s2 + L]])
+        else:
+            if rng.random() < 0.1:
+                r1 = r1[:rng.randint(0, L)]
+            reads.append(r1)
+    return {"job": "graph", "reads": reads, "paired": paired, "k": k, "F": F}
+
+
 def test_both_oracles_on_fresh_graphs():
     from oracle import c_oracle as co
     from oracle import py_oracle as po
     from helpers import counts_sha
     from test_host_side import _traverse
-    jobs = [_random_case(i) for i in range(800)]
+    jobs = [_random_case(i) for i in range(800)] + [_random_case_long(i) for i in range(200)]
     answers = ask_reference(jobs)
     shapes = set()
     for job, want in zip(jobs, answers):
