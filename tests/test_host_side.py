@@ -504,6 +504,21 @@ def test_bucket_limit_switches_to_the_table_kernels(monkeypatch):
         with pytest.raises(Reached):
             gd.build_graph(counts, reads, 3)
         assert calls == ["buckets", "release", "tables"]
+    # the ordinary case: the bucketed route answers, the table route is not asked
+    calls.clear()
+    monkeypatch.setattr(gd, "superkmer_stamps", lambda *a, **kw: (calls.append("buckets"), (torch.zeros((1, 1), dtype=torch.int64), 0, None))[1])
+    monkeypatch.setattr(gd, "superkmer_solid", lambda *a, **kw: (calls.append("solid"), (torch.zeros((1, 1), dtype=torch.int64), 0))[1])
+    for paired, n_occ, want in ((False, 1 << 23, ["buckets"]), (True, 1 << 29, ["solid"]), (False, 1 << 10, ["tables"])):
+        reads = types.SimpleNamespace(paired=paired, alphabet=alphabet, first_read=0, n_reads=1000, estride=150, status=None)
+        counts = types.SimpleNamespace(k=31, w=30, key_words=1, _table=None, _cand={}, n_occ=n_occ, slot_bytes=16)
+        calls.clear()
+        if want == ["tables"]:
+            with pytest.raises(Reached):
+                gd.build_graph(counts, reads, 3)
+        else:
+            graph = gd.build_graph(counts, reads, 3)
+            assert graph.n_nodes == 0 and graph.paired == paired
+        assert calls == want
     # any other failure of the bucketed route is not swallowed
     monkeypatch.setattr(gd, "superkmer_stamps", lambda *a, **kw: (_ for _ in ()).throw(gn.GaError("something else")))
     reads = types.SimpleNamespace(paired=False, alphabet=alphabet, first_read=0, n_reads=1000, estride=150, status=None)
